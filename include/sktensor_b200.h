@@ -1,0 +1,173 @@
+/*
+ * sktensor_b200.h -- C ABI of libsktensor_b200.so: the B200 (sm_100a) kernels behind
+ * scikit-tensor's CP-ALS / MTTKRP / HOOI hot path.
+ *
+ * The reference (mnick/scikit-tensor) is pure Python and has no FFI; the boundary this
+ * library replaces is the set of NumPy/SciPy calls made underneath the Python methods
+ * named below.  Each entry point cites the reference file:line it stands in for.  The
+ * reference-side binding (ctypes) is shown in INTEGRATION.md and implemented in
+ * scikit-tensor_b200/sktensor/_lib.py.
+ *
+ * Conventions
+ *   - every function returns SKT_OK (0) or a negative SKT_E* code; it never throws or
+ *     aborts.  skt_last_error() returns a thread-local, human-readable message.
+ *   - pointers named *_d are DEVICE pointers (any allocator: cudaMalloc, torch, ...),
+ *     pointers named *_h are HOST pointers.  Unless stated, buffers are borrowed for the
+ *     duration of the call only.  All matrices are row-major FP64; tensors are C-order FP64.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device
+ *     entry points only enqueue work; they do not synchronise.  *_host entry points copy
+ *     in, compute, copy out and synchronise before returning.
+ *   - workspaces: call the matching *_workspace() query, hand in at least that many bytes,
+ *     256-byte aligned.  Workspaces carry no state between calls.
+ *   - no CPU fallback exists anywhere in this library.
+ */
+#ifndef SKTENSOR_B200_H
+#define SKTENSOR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SKT_API __attribute__((visibility("default")))
+#else
+#define SKT_API
+#endif
+
+#define SKT_MAX_NDIM 8
+#define SKT_MAX_RANK 64          /* solve / update kernels; MTTKRP kernels accept any rank */
+
+#define SKT_OK            0
+#define SKT_EINVAL       -1      /* bad argument (NULL, ndim, mode, rank ...)          */
+#define SKT_ESHAPE       -2      /* shape too large / inconsistent                      */
+#define SKT_ECUDA        -3      /* CUDA runtime error (message has the cudaError text) */
+#define SKT_EWORKSPACE   -4      /* workspace too small                                 */
+#define SKT_ENONFINITE   -5      /* NaN/Inf met where the reference raises ValueError   */
+#define SKT_EUNSUPPORTED -6
+
+typedef void *skt_stream;
+
+/* ---------------------------------------------------------------- library / device */
+SKT_API int         skt_version(void);
+SKT_API const char *skt_last_error(void);
+/* SM count, compute capability and opt-in shared memory of the current device. */
+SKT_API int skt_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
+
+/* ---------------------------------------------------------------- dense MTTKRP
+ * M[i_n, r] = sum_{all other i} X[i_0..i_{N-1}] * prod_{m != n} U_m[i_m, r]
+ * Replaces dtensor.uttkrp (sktensor/dtensor.py:163-167) = unfold (dtensor.py:103-150) +
+ * khatrirao (core.py:333-378) + dot.  Neither the unfolding nor the Khatri-Rao matrix is
+ * formed.  U_d is a HOST array of `ndim` device pointers; U_d[mode] is ignored and may be
+ * NULL (cp.py:194,143).  M_d is (shape[mode] x rank).                                   */
+SKT_API size_t skt_mttkrp_dense_workspace(const int64_t *shape, int ndim, int rank, int mode);
+SKT_API int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndim,
+                     const double *const *U_d, int rank, int mode, double *M_d,
+                     void *ws_d, size_t ws_bytes, skt_stream stream);
+/* Straightforward one-thread-per-output kernel; used by tests as an independent GPU check. */
+SKT_API int skt_mttkrp_dense_naive(const double *X_d, const int64_t *shape, int ndim,
+                           const double *const *U_d, int rank, int mode, double *M_d,
+                           skt_stream stream);
+/* Host-buffer form (end-to-end through the ABI): uploads X and the factors, runs
+ * skt_mttkrp_dense, downloads M.  X_h is C-order.                                       */
+SKT_API int skt_mttkrp_dense_host(const double *X_h, const int64_t *shape, int ndim,
+                          const double *const *U_h, int rank, int mode, double *M_h);
+
+/* ---------------------------------------------------------------- sparse (COO) MTTKRP
+ * Replaces sptensor.uttkrp (sktensor/sptensor.py:216-229) and its per-rank-column
+ * ttv/_ttv_compute passes (sptensor.py:153-177: gather, unique, searchsorted, bincount).
+ * skt_coo_build sorts the non-zeros once per output mode (stable radix sort on the mode's
+ * subscript, int32 indices) and keeps the sorted copies on the device; skt_mttkrp_coo then
+ * runs a segmented reduction with no global atomics.  Duplicate coordinates are summed
+ * (sptensor.py:172); rows without non-zeros come out as zeros (sptensor.py:221).        */
+typedef struct skt_coo skt_coo;
+/* subs_h: `ndim` host arrays of nnz int64 subscripts; vals_h: nnz doubles.  modes_mask:
+ * bit n set = build the sorted copy for output mode n (0 = all modes).                  */
+SKT_API int skt_coo_build_host(const int64_t *const *subs_h, const double *vals_h, int64_t nnz,
+                       const int64_t *shape, int ndim, unsigned modes_mask, skt_coo **out);
+/* Same, from device arrays (int64 subscripts). */
+SKT_API int skt_coo_build(const int64_t *const *subs_d, const double *vals_d, int64_t nnz,
+                  const int64_t *shape, int ndim, unsigned modes_mask, skt_stream stream,
+                  skt_coo **out);
+SKT_API int     skt_coo_destroy(skt_coo *t);
+SKT_API int64_t skt_coo_nnz(const skt_coo *t);
+SKT_API size_t  skt_coo_device_bytes(const skt_coo *t);
+SKT_API size_t  skt_mttkrp_coo_workspace(const skt_coo *t, int rank, int mode);
+SKT_API int skt_mttkrp_coo(const skt_coo *t, const double *const *U_d, int rank, int mode,
+                   double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream);
+/* Unsorted-COO kernel with FP64 global atomics; tests use it as an independent GPU check. */
+SKT_API int skt_mttkrp_coo_atomic(const skt_coo *t, const double *const *U_d, int rank, int mode,
+                          double *M_d, skt_stream stream);
+/* <P, X> for sparse X: sum_nnz val * sum_r lambda_r prod_m U_m[i_m, r]
+ * (ktensor.innerprod, ktensor.py:128-150 -> sptensor.py:154-163).  out_d: one double.   */
+SKT_API size_t skt_coo_innerprod_workspace(const skt_coo *t, int rank);
+SKT_API int skt_coo_innerprod(const skt_coo *t, const double *const *U_d, const double *lambda_d,
+                      int rank, double *out_d, void *ws_d, size_t ws_bytes, skt_stream stream);
+/* sum of squares of the stored values (sptensor.norm, sptensor.py:274-282, squared). */
+SKT_API int skt_coo_sumsq(const skt_coo *t, double *out_d, void *ws_d, size_t ws_bytes, skt_stream stream);
+
+/* ---------------------------------------------------------------- reductions
+ * out_d[0] = sum_i x[i]^2   (dtensor.norm, dtensor.py:152-161, squared).  Deterministic.  */
+SKT_API size_t skt_sumsq_workspace(int64_t n);
+SKT_API int skt_sumsq(const double *x_d, int64_t n, double *out_d, void *ws_d, size_t ws_bytes,
+              skt_stream stream);
+
+/* out_d[0] = sum_i sum_r lambda_r U[i,r] M[i,r] (lambda_d NULL = ones).  With M the MTTKRP of
+ * the last mode this is <P, X> (ktensor.innerprod, ktensor.py:128-150) without the reference's
+ * rank-many passes over X.  Workspace: skt_sumsq_workspace(rows*rank).                    */
+SKT_API int skt_weighted_dot(const double *U_d, const double *M_d, const double *lambda_d, int64_t rows,
+                     int rank, double *out_d, void *ws_d, size_t ws_bytes, skt_stream stream);
+
+/* ---------------------------------------------------------------- CP-ALS normal equations
+ * G = U^T U for a tall (rows x rank) factor (cp.py:146, ktensor.py:125).                 */
+SKT_API size_t skt_gram_workspace(int64_t rows, int rank);
+SKT_API int skt_gram(const double *U_d, int64_t rows, int rank, double *G_d, void *ws_d,
+             size_t ws_bytes, skt_stream stream);
+/* P = pinv( hadamard_{m != mode} G_m )  with scipy.linalg.pinv's cut-off
+ * rtol = rank * eps * sigma_max (cp.py:144-147).  G_d holds ndim (rank x rank) Grams.
+ * Computed by a cyclic Jacobi eigen-decomposition in one CTA.  info_d[0] receives the
+ * numerical rank kept, or -1 if Y held NaN/Inf (the reference raises ValueError there). */
+SKT_API int skt_hadamard_pinv(const double *G_d, int ndim, int rank, int mode, double *P_d,
+                      int *info_d, skt_stream stream);
+/* Phase A of the factor update: Unew = M P (cp.py:147) and the per-column statistic the
+ * normalisation needs: sum of squares when first_iter != 0 (cp.py:149-150), signed maximum
+ * otherwise (cp.py:151-152).  colstat_d: rank doubles.                                   */
+SKT_API size_t skt_solve_stats_workspace(int64_t rows, int rank);
+SKT_API int skt_solve_stats(const double *M_d, const double *P_d, int64_t rows, int rank,
+                    int first_iter, double *Unew_d, double *colstat_d, void *ws_d,
+                    size_t ws_bytes, skt_stream stream);
+/* Phase B: lambda = sqrt(colstat) (first_iter) or max(colstat, 1) (cp.py:150-153);
+ * U = Unew / lambda in place (cp.py:154); G = U^T U of the normalised factor; and, when
+ * Mip_d != NULL, ip_d[0] = sum_r lambda_r sum_i U[i,r] Mip[i,r]  (= <P,X> when Mip is the
+ * MTTKRP of the last mode; replaces ktensor.innerprod, ktensor.py:128-150).  A multi-GPU
+ * caller all-reduces colstat between the two phases and G / ip afterwards.              */
+SKT_API size_t skt_normalise_gram_workspace(int64_t rows, int rank);
+SKT_API int skt_normalise_gram(double *U_d, const double *colstat_d, int64_t rows, int rank,
+                       int first_iter, double *lambda_d, double *G_d, const double *Mip_d,
+                       double *ip_d, void *ws_d, size_t ws_bytes, skt_stream stream);
+/* fit = 1 - (normX2 + ||P||^2 - 2 ip) / normX2 with ||P||^2 = sum(lambda lambda^T *
+ * hadamard_m G_m) (cp.py:157-159, ktensor.py:113-126).  out_d[0] = fit, out_d[1] = ||P||^2. */
+SKT_API int skt_cp_fit(const double *G_d, int ndim, int rank, const double *lambda_d,
+               const double *ip_d, const double *normX2_d, double *out_d, skt_stream stream);
+
+/* ---------------------------------------------------------------- Tucker / HOOI
+ * Y = X x_mode V^T (transp != 0: V is I_mode x p) or X x_mode V (V is p x I_mode)
+ * (dtensor._ttm_compute, dtensor.py:58-76), without the transpose/reshape copies.        */
+SKT_API int skt_ttm_dense(const double *X_d, const int64_t *shape, int ndim, const double *V_d,
+                  int64_t p, int mode, int transp, double *Y_d, skt_stream stream);
+/* G = X_(mode) X_(mode)^T  (I_mode x I_mode), the Gram inside core.nvecs (core.py:279,285). */
+SKT_API size_t skt_unfold_gram_workspace(const int64_t *shape, int ndim, int mode);
+SKT_API int skt_unfold_gram(const double *X_d, const int64_t *shape, int ndim, int mode, double *G_d,
+                    void *ws_d, size_t ws_bytes, skt_stream stream);
+
+/* ---------------------------------------------------------------- measurement helpers
+ * Peak probes used by bench.py for the roofline denominators that MEASURED_PEAKS.json
+ * does not carry: FP64 DMMA (mma.sync m8n8k4) and FP64 FMA issue rate, in TFLOP/s.       */
+SKT_API int skt_probe_fp64_peaks(double *dmma_tflops, double *dfma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKTENSOR_B200_H */

@@ -1,0 +1,100 @@
+// Shared helpers for the sm_100a kernels of libsktensor_b200: error plumbing for the C ABI,
+// FP64 tensor-core MMA (DMMA.8x8x4), cp.async staging and deterministic reductions.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sktensor_b200.h"
+
+namespace skt {
+
+// ---------------------------------------------------------------------------------------------
+// error state (thread-local message behind skt_last_error)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SKT_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return skt::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define SKT_REQUIRE(cond, code, ...)                                           \
+    do {                                                                       \
+        if (!(cond)) {                                                         \
+            skt::set_error(__VA_ARGS__);                                       \
+            return (code);                                                     \
+        }                                                                      \
+    } while (0)
+
+// Launch-error check that does not synchronise.
+#define SKT_LAUNCH_CHECK() SKT_CUDA(cudaGetLastError())
+
+int sm_count();            // SMs of the current device (cached)
+size_t smem_optin_bytes(); // max opt-in dynamic shared memory per block (cached)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+// D(8x8) += A(8x4, row) * B(4x8, col) in FP64 on the tensor pipe (SASS: DMMA.8x8x4).
+// Fragment ownership (lane = 4*g + t):  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 16-byte async global->shared copy (LDGSTS); src_bytes < 16 zero-fills the remainder.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(src_bytes));
+}
+// 8-byte variant for shapes whose rows are not 16-byte aligned.
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// "Last block reduces": every block stores its partial, the block that takes the final ticket
+// sees all of them and finishes the reduction in a fixed order (deterministic, one launch).
+// `counter` must be zero on entry and is reset to zero by the last block.
+__device__ __forceinline__ bool last_block_ticket(unsigned int *counter, unsigned int nblocks) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(counter, 1u);
+        is_last = (t == nblocks - 1);
+        if (is_last) *counter = 0u;
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+}  // namespace skt

@@ -1,0 +1,557 @@
+// CP-ALS normal equations for sm_100a: tall-skinny Grams, Hadamard-of-Grams pseudo-inverse,
+// factor update + normalisation, Kruskal fit.  Reference: sktensor/cp.py:144-159 and
+// sktensor/ktensor.py:113-150.  Every reduction is ordered (partials + "last block reduces"),
+// so results are bitwise reproducible run to run.
+#include <algorithm>
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace skt {
+namespace {
+
+constexpr int ROWS = 64;        // factor rows staged per tile
+constexpr int NT = 256;         // 16 x 16 threads
+constexpr int MAXR = SKT_MAX_RANK;
+
+// Deterministic block-wide sum / max of one double per thread (NT threads). Result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    __syncthreads();
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Factor pass:  (optionally) U <- U / lambda,  G = U^T U,  ip = sum_r lambda_r sum_i U[i,r] Mip[i,r]
+// 16x16 threads; thread (ty,tx) owns G[ty+16a][tx+16b], a,b < TT = ceil(R/16).
+// ---------------------------------------------------------------------------------------------
+template <int TT>
+__global__ void __launch_bounds__(NT) factor_pass_kernel(double *U, const double *__restrict__ colstat, long long rows,
+                                                         int R, int normalise, int first_iter, double *lambda_out,
+                                                         double *G_out, const double *__restrict__ Mip, double *ip_out,
+                                                         double *partials, unsigned int *counter) {
+    __shared__ double Us[ROWS][16 * TT + 1];
+    __shared__ double lam[16 * TT];
+    __shared__ double red[NT / 32];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int nblk = gridDim.x;
+
+    if (tid < 16 * TT) {
+        double l = 1.0;
+        if (normalise && tid < R) {
+            const double c = colstat[tid];
+            l = first_iter ? sqrt(c) : (c < 1.0 ? 1.0 : c);  // cp.py:150 / cp.py:152-153
+        }
+        lam[tid] = l;
+        if (normalise && lambda_out && blockIdx.x == 0 && tid < R) lambda_out[tid] = l;
+    }
+    for (int e = tid; e < ROWS * (16 * TT + 1); e += NT) (&Us[0][0])[e] = 0.0;
+    __syncthreads();
+
+    double g[TT][TT];
+#pragma unroll
+    for (int a = 0; a < TT; ++a)
+#pragma unroll
+        for (int b = 0; b < TT; ++b) g[a][b] = 0.0;
+    double ip = 0.0;
+
+    const long long ntile = (rows + ROWS - 1) / ROWS;
+    for (long long tile = blockIdx.x; tile < ntile; tile += nblk) {
+        const long long r0 = tile * ROWS;
+        const int nr = (int)min((long long)ROWS, rows - r0);
+        // coalesced load of nr x R, divide, write back
+        for (int e = tid; e < ROWS * R; e += NT) {
+            const int i = e / R, c = e % R;
+            double v = 0.0;
+            if (i < nr) {
+                const long long gi = (r0 + i) * R + c;
+                v = U[gi];
+                if (normalise) {
+                    v = v / lam[c];
+                    U[gi] = v;
+                }
+                if (Mip) ip += lam[c] * v * Mip[gi];
+            }
+            Us[i][c] = v;
+        }
+        __syncthreads();
+        for (int i = 0; i < nr; ++i) {
+            double ua[TT], ub[TT];
+#pragma unroll
+            for (int a = 0; a < TT; ++a) ua[a] = Us[i][ty + 16 * a];
+#pragma unroll
+            for (int b = 0; b < TT; ++b) ub[b] = Us[i][tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < TT; ++a)
+#pragma unroll
+                for (int b = 0; b < TT; ++b) g[a][b] += ua[a] * ub[b];
+        }
+        __syncthreads();
+    }
+    double *mine = partials + (size_t)blockIdx.x * (MAXR * MAXR + 1);
+#pragma unroll
+    for (int a = 0; a < TT; ++a)
+#pragma unroll
+        for (int b = 0; b < TT; ++b) {
+            const int ra = ty + 16 * a, cb = tx + 16 * b;
+            if (ra < R && cb < R) mine[ra * R + cb] = g[a][b];
+        }
+    const double ipb = block_sum(ip, red);
+    if (tid == 0) mine[MAXR * MAXR] = ipb;
+
+    if (last_block_ticket(counter, nblk)) {
+        for (int e = tid; e < R * R; e += NT) {
+            double s = 0.0;
+            for (int b = 0; b < nblk; ++b) s += partials[(size_t)b * (MAXR * MAXR + 1) + e];
+            G_out[e] = s;
+        }
+        if (tid == 0 && ip_out) {
+            double s = 0.0;
+            for (int b = 0; b < nblk; ++b) s += partials[(size_t)b * (MAXR * MAXR + 1) + MAXR * MAXR];
+            ip_out[0] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Unew = M P  and per-column statistic (sum of squares or signed max).  cp.py:147-152
+// ---------------------------------------------------------------------------------------------
+template <int TT>
+__global__ void __launch_bounds__(NT) solve_stats_kernel(const double *__restrict__ M, const double *__restrict__ P,
+                                                         long long rows, int R, int first_iter, double *Unew,
+                                                         double *colstat, double *partials, unsigned int *counter) {
+    extern __shared__ double sm[];
+    double *Ps = sm;                         // [R][16*TT+1]
+    double *Ms = Ps + MAXR * (16 * TT + 1);  // [ROWS][R+1]
+    double *cs = Ms + ROWS * (MAXR + 1);     // [16][16*TT]
+    const int PL = 16 * TT + 1, ML = R + 1;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int nblk = gridDim.x;
+
+    for (int e = tid; e < R * 16 * TT; e += NT) {
+        const int k = e / (16 * TT), c = e % (16 * TT);
+        Ps[k * PL + c] = (c < R) ? P[k * R + c] : 0.0;
+    }
+    double stat[TT];
+#pragma unroll
+    for (int b = 0; b < TT; ++b) stat[b] = first_iter ? 0.0 : -DBL_MAX;
+    __syncthreads();
+
+    const long long ntile = (rows + ROWS - 1) / ROWS;
+    for (long long tile = blockIdx.x; tile < ntile; tile += nblk) {
+        const long long r0 = tile * ROWS;
+        const int nr = (int)min((long long)ROWS, rows - r0);
+        for (int e = tid; e < ROWS * R; e += NT) {
+            const int i = e / R, c = e % R;
+            Ms[i * ML + c] = (i < nr) ? M[(r0 + i) * R + c] : 0.0;
+        }
+        __syncthreads();
+        double acc[4][TT];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < TT; ++b) acc[a][b] = 0.0;
+        for (int k = 0; k < R; ++k) {
+            double m[4], pv[TT];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) m[a] = Ms[(ty + 16 * a) * ML + k];
+#pragma unroll
+            for (int b = 0; b < TT; ++b) pv[b] = Ps[k * PL + tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < TT; ++b) acc[a][b] += m[a] * pv[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ty + 16 * a;
+            if (i < nr) {
+#pragma unroll
+                for (int b = 0; b < TT; ++b) {
+                    const int c = tx + 16 * b;
+                    if (c < R) {
+                        Unew[(r0 + i) * R + c] = acc[a][b];
+                        if (first_iter) stat[b] += acc[a][b] * acc[a][b];
+                        else stat[b] = fmax(stat[b], acc[a][b]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // combine the 16 row-groups (ty) per column in a fixed order
+#pragma unroll
+    for (int b = 0; b < TT; ++b) cs[ty * 16 * TT + tx + 16 * b] = stat[b];
+    __syncthreads();
+    double *mine = partials + (size_t)blockIdx.x * MAXR;
+    if (tid < R) {
+        double s = first_iter ? 0.0 : -DBL_MAX;
+        for (int y = 0; y < 16; ++y) {
+            const double v = cs[y * 16 * TT + tid];
+            s = first_iter ? s + v : fmax(s, v);
+        }
+        mine[tid] = s;
+    }
+    if (last_block_ticket(counter, nblk)) {
+        if (tid < R) {
+            double s = first_iter ? 0.0 : -DBL_MAX;
+            for (int b = 0; b < nblk; ++b) {
+                const double v = partials[(size_t)b * MAXR + tid];
+                s = first_iter ? s + v : fmax(s, v);
+            }
+            colstat[tid] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// P = pinv( hadamard_{m != mode} G_m ),  scipy.linalg.pinv semantics (cp.py:144-147):
+// singular values <= R*eps*sigma_max are dropped.  One CTA, one warp per column pair, one-sided
+// (Hestenes) Jacobi with a round-robin ordering; symmetric Y so Y V = W with orthogonal columns,
+// sigma_j = |w_j| and pinv(Y) = sum_j v_j w_j^T / sigma_j^2.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) hadamard_pinv_kernel(const double *__restrict__ G, int ndim, int R, int mode,
+                                                             double *P, int *info) {
+    extern __shared__ double jsm[];
+    double (*W)[MAXR + 1] = reinterpret_cast<double (*)[MAXR + 1]>(jsm);                        // W[j][i]: column j of the working matrix
+    double (*V)[MAXR + 1] = reinterpret_cast<double (*)[MAXR + 1]>(jsm + MAXR * (MAXR + 1));    // V[j][i]: column j of the accumulated rotations
+    double *sig2 = jsm + 2 * MAXR * (MAXR + 1);
+    __shared__ int flag_rot, flag_bad;
+    __shared__ double smax2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x;
+    const int npairs = (R + 1) / 2;
+    const int m = 2 * npairs - 1;  // round-robin modulus (n' - 1), n' = R rounded up to even
+
+    if (tid == 0) { flag_bad = 0; flag_rot = 0; }
+    __syncthreads();
+    for (int e = tid; e < R * R; e += nthreads) {
+        const int a = e / R, b = e % R;
+        double y = 1.0;
+        for (int k = 0; k < ndim; ++k)
+            if (k != mode) y *= G[(size_t)k * R * R + e];
+        if (!isfinite(y)) flag_bad = 1;
+        W[b][a] = y;
+        V[b][a] = (a == b) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (flag_bad) {
+        for (int e = tid; e < R * R; e += nthreads) P[e] = nan("");
+        if (tid == 0) info[0] = -1;
+        return;
+    }
+    // scale reference for the "both columns negligible" skip
+    if (warp == 0) {
+        double mx = 0.0;
+        for (int j = lane; j < R; j += 32) {
+            double s = 0.0;
+            for (int i = 0; i < R; ++i) s += W[j][i] * W[j][i];
+            mx = fmax(mx, s);
+        }
+        mx = warp_max(mx);
+        if (lane == 0) smax2 = mx;
+    }
+    __syncthreads();
+    const double eps = DBL_EPSILON;
+    const double negl = smax2 * (R * eps) * (R * eps) * 1e-4;  // far below the pinv cut-off
+
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        for (int step = 0; step < m; ++step) {
+            if (warp < npairs) {
+                int p, q;
+                if (warp == 0) { p = m; q = step % m; }
+                else { p = (step + warp) % m; q = (step - warp + m) % m; }
+                if (p > q) { const int t = p; p = q; q = t; }
+                if (q < R) {
+                    double wp0 = (lane < R) ? W[p][lane] : 0.0, wq0 = (lane < R) ? W[q][lane] : 0.0;
+                    double wp1 = (lane + 32 < R) ? W[p][lane + 32] : 0.0, wq1 = (lane + 32 < R) ? W[q][lane + 32] : 0.0;
+                    const double alpha = warp_sum(wp0 * wp0 + wp1 * wp1);
+                    const double beta = warp_sum(wq0 * wq0 + wq1 * wq1);
+                    const double gamma = warp_sum(wp0 * wq0 + wp1 * wq1);
+                    const double lim = eps * sqrt(alpha * beta);
+                    const bool tiny = (alpha <= negl && beta <= negl);
+                    if (fabs(gamma) > lim && !tiny && alpha * beta > 0.0) {
+                        const double zeta = (beta - alpha) / (2.0 * gamma);
+                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                        if (lane < R) {
+                            W[p][lane] = c * wp0 - s * wq0;
+                            W[q][lane] = s * wp0 + c * wq0;
+                            const double vp = V[p][lane], vq = V[q][lane];
+                            V[p][lane] = c * vp - s * vq;
+                            V[q][lane] = s * vp + c * vq;
+                        }
+                        if (lane + 32 < R) {
+                            W[p][lane + 32] = c * wp1 - s * wq1;
+                            W[q][lane + 32] = s * wp1 + c * wq1;
+                            const double vp = V[p][lane + 32], vq = V[q][lane + 32];
+                            V[p][lane + 32] = c * vp - s * vq;
+                            V[q][lane + 32] = s * vp + c * vq;
+                        }
+                        if (lane == 0) flag_rot = 1;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int any = flag_rot;
+        __syncthreads();
+        if (tid == 0) flag_rot = 0;
+        __syncthreads();
+        if (!any) break;
+    }
+    // singular values and cut-off
+    for (int j = warp; j < R; j += (nthreads >> 5)) {
+        double s = 0.0;
+        for (int i = lane; i < R; i += 32) s += W[j][i] * W[j][i];
+        s = warp_sum(s);
+        if (lane == 0) sig2[j] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double mx = 0.0;
+        for (int j = 0; j < R; ++j) mx = fmax(mx, sig2[j]);
+        smax2 = mx;
+        const double cut = (double)R * eps * sqrt(mx);
+        int kept = 0;
+        for (int j = 0; j < R; ++j) {
+            if (sqrt(sig2[j]) > cut) ++kept;
+            else sig2[j] = 0.0;  // dropped
+        }
+        info[0] = kept;
+    }
+    __syncthreads();
+    for (int e = tid; e < R * R; e += nthreads) {
+        const int a = e / R, b = e % R;
+        double s = 0.0;
+        for (int j = 0; j < R; ++j)
+            if (sig2[j] > 0.0) s += V[j][a] * W[j][b] / sig2[j];
+        P[e] = s;
+    }
+}
+
+// fit (cp.py:157-159) with ||P||^2 from the Grams (ktensor.py:113-126)
+__global__ void cp_fit_kernel(const double *__restrict__ G, int ndim, int R, const double *__restrict__ lambda,
+                              const double *__restrict__ ip, const double *__restrict__ normX2, double *out) {
+    __shared__ double red[NT / 32];
+    double s = 0.0;
+    for (int e = threadIdx.x; e < R * R; e += NT) {
+        const int a = e / R, b = e % R;
+        double y = lambda[a] * lambda[b];
+        for (int k = 0; k < ndim; ++k) y *= G[(size_t)k * R * R + e];
+        s += y;
+    }
+    const double normP2 = block_sum(s, red);
+    if (threadIdx.x == 0) {
+        const double nx2 = normX2[0];
+        out[0] = 1.0 - (nx2 + normP2 - 2.0 * ip[0]) / nx2;
+        out[1] = normP2;
+    }
+}
+
+__global__ void __launch_bounds__(NT) sumsq_kernel(const double *__restrict__ x, long long n, double *out, double *partials,
+                                                   unsigned int *counter) {
+    __shared__ double red[NT / 32];
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+        const double v = x[i];
+        s += v * v;
+    }
+    const double b = block_sum(s, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
+    if (last_block_ticket(counter, gridDim.x)) {
+        double t = 0.0;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += NT) t += partials[k];
+        const double tot = block_sum(t, red);
+        if (threadIdx.x == 0) out[0] = tot;
+    }
+}
+
+// out = sum_i sum_r lambda_r U[i,r] M[i,r]   (<P,X> from the last-mode MTTKRP; ktensor.py:128-150)
+__global__ void __launch_bounds__(NT) weighted_dot_kernel(const double *__restrict__ U, const double *__restrict__ M,
+                                                          const double *__restrict__ lambda, long long n, int R,
+                                                          double *out, double *partials, unsigned int *counter) {
+    __shared__ double red[NT / 32];
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)NT + threadIdx.x; i < n; i += (long long)gridDim.x * NT) {
+        const double l = lambda ? lambda[i % R] : 1.0;
+        s += l * U[i] * M[i];
+    }
+    const double b = block_sum(s, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = b;
+    if (last_block_ticket(counter, gridDim.x)) {
+        double t = 0.0;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += NT) t += partials[k];
+        const double tot = block_sum(t, red);
+        if (threadIdx.x == 0) out[0] = tot;
+    }
+}
+
+int pass_blocks(long long rows) {
+    const long long ntile = (rows + ROWS - 1) / ROWS;
+    return (int)std::max<long long>(1, std::min<long long>(ntile, 2LL * sm_count()));
+}
+
+// workspace layout shared by the factor passes: [counter (256 B)] [partials]
+size_t pass_ws_bytes(long long rows, size_t per_block_doubles) {
+    return 256 + align_up((size_t)pass_blocks(rows) * per_block_doubles * sizeof(double), 256);
+}
+
+int check_rank(int rank) {
+    SKT_REQUIRE(rank >= 1 && rank <= MAXR, SKT_EUNSUPPORTED, "rank %d outside [1, %d] supported by the solve kernels", rank, MAXR);
+    return SKT_OK;
+}
+
+int launch_factor_pass(double *U, const double *colstat, long long rows, int R, int normalise, int first_iter,
+                       double *lambda, double *G, const double *Mip, double *ip, void *ws, size_t ws_bytes,
+                       cudaStream_t st) {
+    const size_t need = pass_ws_bytes(rows, MAXR * MAXR + 1);
+    SKT_REQUIRE(ws && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    unsigned int *counter = (unsigned int *)ws;
+    double *partials = (double *)((char *)ws + 256);
+    SKT_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    const int nb = pass_blocks(rows);
+    const int tt = (R + 15) / 16;
+#define FP(TT_) factor_pass_kernel<TT_><<<nb, NT, 0, st>>>(U, colstat, rows, R, normalise, first_iter, lambda, G, Mip, ip, partials, counter)
+    switch (tt) {
+        case 1: FP(1); break;
+        case 2: FP(2); break;
+        case 3: FP(3); break;
+        default: FP(4); break;
+    }
+#undef FP
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+}  // namespace
+}  // namespace skt
+
+using namespace skt;
+
+extern "C" size_t skt_gram_workspace(int64_t rows, int rank) { (void)rank; return pass_ws_bytes(rows, MAXR * MAXR + 1); }
+extern "C" size_t skt_normalise_gram_workspace(int64_t rows, int rank) { (void)rank; return pass_ws_bytes(rows, MAXR * MAXR + 1); }
+extern "C" size_t skt_solve_stats_workspace(int64_t rows, int rank) { (void)rank; return pass_ws_bytes(rows, MAXR); }
+extern "C" size_t skt_sumsq_workspace(int64_t n) {
+    (void)n;
+    return 256 + align_up((size_t)4 * sm_count() * sizeof(double), 256);
+}
+
+extern "C" int skt_gram(const double *U_d, int64_t rows, int rank, double *G_d, void *ws_d, size_t ws_bytes,
+                        skt_stream stream) {
+    SKT_REQUIRE(U_d && G_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
+    int rc = check_rank(rank);
+    if (rc) return rc;
+    return launch_factor_pass(const_cast<double *>(U_d), nullptr, rows, rank, 0, 0, nullptr, G_d, nullptr, nullptr, ws_d,
+                              ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int skt_normalise_gram(double *U_d, const double *colstat_d, int64_t rows, int rank, int first_iter,
+                                  double *lambda_d, double *G_d, const double *Mip_d, double *ip_d, void *ws_d,
+                                  size_t ws_bytes, skt_stream stream) {
+    SKT_REQUIRE(U_d && colstat_d && lambda_d && G_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
+    SKT_REQUIRE((Mip_d == nullptr) == (ip_d == nullptr), SKT_EINVAL, "Mip_d and ip_d must be given together");
+    int rc = check_rank(rank);
+    if (rc) return rc;
+    return launch_factor_pass(U_d, colstat_d, rows, rank, 1, first_iter, lambda_d, G_d, Mip_d, ip_d, ws_d, ws_bytes,
+                              (cudaStream_t)stream);
+}
+
+extern "C" int skt_solve_stats(const double *M_d, const double *P_d, int64_t rows, int rank, int first_iter,
+                               double *Unew_d, double *colstat_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    SKT_REQUIRE(M_d && P_d && Unew_d && colstat_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
+    int rc = check_rank(rank);
+    if (rc) return rc;
+    const size_t need = pass_ws_bytes(rows, MAXR);
+    SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int *counter = (unsigned int *)ws_d;
+    double *partials = (double *)((char *)ws_d + 256);
+    SKT_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    const int nb = pass_blocks(rows);
+    const int tt = (rank + 15) / 16;
+    const size_t smem = (size_t)(MAXR * (16 * tt + 1) + ROWS * (MAXR + 1) + 16 * 16 * tt) * sizeof(double);
+#define SS(TT_)                                                                                                   \
+    do {                                                                                                          \
+        static bool cfg = false;                                                                                  \
+        if (!cfg) {                                                                                               \
+            SKT_CUDA(cudaFuncSetAttribute(solve_stats_kernel<TT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            cfg = true;                                                                                           \
+        }                                                                                                         \
+        solve_stats_kernel<TT_><<<nb, NT, smem, st>>>(M_d, P_d, rows, rank, first_iter, Unew_d, colstat_d, partials, counter); \
+    } while (0)
+    switch (tt) {
+        case 1: SS(1); break;
+        case 2: SS(2); break;
+        case 3: SS(3); break;
+        default: SS(4); break;
+    }
+#undef SS
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" int skt_hadamard_pinv(const double *G_d, int ndim, int rank, int mode, double *P_d, int *info_d,
+                                 skt_stream stream) {
+    SKT_REQUIRE(G_d && P_d && info_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= -1 && mode < ndim, SKT_EINVAL, "bad ndim/mode");
+    int rc = check_rank(rank);
+    if (rc) return rc;
+    const int npairs = (rank + 1) / 2;
+    const int threads = std::max(64, 32 * npairs);
+    const size_t smem = (size_t)(2 * MAXR * (MAXR + 1) + MAXR) * sizeof(double);
+    static bool cfg = false;
+    if (!cfg) {
+        SKT_CUDA(cudaFuncSetAttribute(hadamard_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg = true;
+    }
+    hadamard_pinv_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(G_d, ndim, rank, mode, P_d, info_d);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" int skt_cp_fit(const double *G_d, int ndim, int rank, const double *lambda_d, const double *ip_d,
+                          const double *normX2_d, double *out_d, skt_stream stream) {
+    SKT_REQUIRE(G_d && lambda_d && ip_d && normX2_d && out_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "bad ndim");
+    int rc = check_rank(rank);
+    if (rc) return rc;
+    cp_fit_kernel<<<1, NT, 0, (cudaStream_t)stream>>>(G_d, ndim, rank, lambda_d, ip_d, normX2_d, out_d);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" int skt_sumsq(const double *x_d, int64_t n, double *out_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    SKT_REQUIRE(x_d && out_d && n >= 0, SKT_EINVAL, "NULL argument or negative length");
+    const size_t need = skt_sumsq_workspace(n);
+    SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int *counter = (unsigned int *)ws_d;
+    double *partials = (double *)((char *)ws_d + 256);
+    SKT_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    const int nb = (int)std::max<long long>(1, std::min<long long>((n + NT - 1) / NT, 4LL * sm_count()));
+    sumsq_kernel<<<nb, NT, 0, st>>>(x_d, n, out_d, partials, counter);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" int skt_weighted_dot(const double *U_d, const double *M_d, const double *lambda_d, int64_t rows, int rank,
+                                double *out_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    SKT_REQUIRE(U_d && M_d && out_d && rows >= 0 && rank >= 1, SKT_EINVAL, "NULL argument or bad size");
+    const long long n = (long long)rows * rank;
+    const size_t need = skt_sumsq_workspace(n);
+    SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int *counter = (unsigned int *)ws_d;
+    double *partials = (double *)((char *)ws_d + 256);
+    SKT_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    const int nb = (int)std::max<long long>(1, std::min<long long>((n + NT - 1) / NT, 4LL * sm_count()));
+    weighted_dot_kernel<<<nb, NT, 0, st>>>(U_d, M_d, lambda_d, n, rank, out_d, partials, counter);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}

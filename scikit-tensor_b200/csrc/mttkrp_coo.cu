@@ -1,0 +1,593 @@
+// Sparse (COO) FP64 MTTKRP for sm_100a -- the kernel behind sptensor.uttkrp
+// (reference: sktensor/sptensor.py:216-229, one ttv / _ttv_compute pass per rank column,
+// sptensor.py:153-177: gather-multiply, unique, searchsorted, bincount).
+//
+// Device format (built once per tensor by skt_coo_build): for every output mode n a copy of the
+// non-zeros stably radix-sorted by i_n -- int32 subscripts for all N modes plus the FP64 values,
+// 4N+8 bytes per non-zero, which is exactly the compulsory index/value traffic of one MTTKRP.
+//
+// Kernel: all R rank columns in ONE pass.  A group of GS lanes (GS = next power of two >= R,
+// at most 32, CPL columns per lane beyond that) walks S consecutive non-zeros; factor rows are
+// gathered 8 non-zeros at a time to keep loads in flight, and equal-row runs are accumulated in
+// registers.  Complete runs inside a group are stored straight to M; the first/last run of each
+// group is merged across the groups of the CTA in shared memory and across CTAs by a short
+// fix-up kernel, always in storage order -- a segmented reduction without a single atomic and
+// with a reproducible summation order.  Rows without non-zeros are zero (M is cleared first).
+#include <algorithm>
+#include <cstring>
+
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+struct skt_coo {
+    int ndim;
+    long long nnz;
+    long long shape[SKT_MAX_NDIM];
+    unsigned built_mask;
+    // sorted copy for output mode n: idx[n][m] (nnz int32 each) and vals[n]
+    int *idx[SKT_MAX_NDIM][SKT_MAX_NDIM];
+    double *vals[SKT_MAX_NDIM];
+    size_t bytes;
+};
+
+namespace skt {
+namespace {
+
+constexpr int CT = 256;  // threads per CTA
+constexpr int S = 256;   // non-zeros per lane group
+constexpr int B = 8;     // gather batch (non-zeros in flight per group)
+
+struct CooParams {
+    const int *rows;                  // sorted output-mode subscripts
+    const int *oidx[SKT_MAX_NDIM];    // subscripts of the other modes (same order)
+    const double *U[SKT_MAX_NDIM];    // their factors
+    const double *vals;
+    long long nnz;
+    int R;
+    int nother;
+    double *M;
+    int *carry_row;     // [2*nCTA]
+    double *carry_val;  // [2*nCTA][R]
+};
+
+template <int GS, int CPL, int NO>
+__global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ CooParams p) {
+    constexpr int NG = CT / GS;  // groups per CTA
+    extern __shared__ double csm[];
+    // per-CTA carry staging: 2 slots per group
+    int *crow = reinterpret_cast<int *>(csm);                 // [2*NG]
+    double *cval = csm + ((2 * NG * (int)sizeof(int) + 7) / 8);  // [2*NG][GS*CPL]
+    constexpr int RW = GS * CPL;
+
+    const int tid = threadIdx.x;
+    const int gl = tid % GS;   // lane within group
+    const int gi = tid / GS;   // group within CTA
+    const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << ((tid & 31) / GS * GS));
+    const int gbase = (tid & 31) / GS * GS;  // first warp lane of this group
+    const long long cta_start = (long long)blockIdx.x * (NG * S);
+    const long long start = cta_start + (long long)gi * S;
+    const long long end = min(start + (long long)S, p.nnz);
+    const int R = p.R;
+
+    double acc[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] = 0.0;
+    int cur_row = -1;
+    int nseg = 0;  // completed flushes of this group
+
+    auto flush = [&](bool is_tail) {
+        // first run of the group -> slot 2*gi ; last run (if not also the first) -> slot 2*gi+1 ; others -> M
+        if (nseg == 0 || is_tail) {
+            const int slot = 2 * gi + (nseg == 0 ? 0 : 1);
+            if (gl == 0) crow[slot] = cur_row;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) cval[slot * RW + gl + GS * c] = acc[c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int col = gl + GS * c;
+                if (col < R) p.M[(long long)cur_row * R + col] = acc[c];
+            }
+        }
+        ++nseg;
+    };
+
+    if (gl == 0) { crow[2 * gi] = -1; crow[2 * gi + 1] = -1; }
+    __syncwarp(gmask);
+
+    if (start < end) {
+        cur_row = p.rows[start];
+        for (long long base = start; base < end; base += GS) {
+            const long long my = base + gl;
+            const bool have = my < end;
+            const int my_row = have ? p.rows[my] : -1;
+            const double my_val = have ? p.vals[my] : 0.0;
+            int my_idx[NO];
+#pragma unroll
+            for (int m = 0; m < NO; ++m) my_idx[m] = (have && m < p.nother) ? p.oidx[m][my] : 0;
+            const int cnt = (int)min((long long)GS, end - base);
+            for (int j0 = 0; j0 < cnt; j0 += B) {
+                double contrib[B][CPL];
+                int rws[B];
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    const int j = j0 + b;
+                    const int src = gbase + (j < GS ? j : 0);
+                    const int row = __shfl_sync(gmask, my_row, src);
+                    const double v = __shfl_sync(gmask, my_val, src);
+                    const bool ok = j < cnt;
+                    rws[b] = ok ? row : -1;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) contrib[b][c] = ok ? v : 0.0;
+#pragma unroll
+                    for (int m = 0; m < NO; ++m) {
+                        const int im = __shfl_sync(gmask, my_idx[m], src);
+                        if (m < p.nother) {
+#pragma unroll
+                            for (int c = 0; c < CPL; ++c) {
+                                const int col = gl + GS * c;
+                                const double u = (ok && col < R) ? __ldg(p.U[m] + (long long)im * R + col) : 0.0;
+                                contrib[b][c] *= u;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    if (rws[b] >= 0) {
+                        if (rws[b] != cur_row) {
+                            flush(false);
+#pragma unroll
+                            for (int c = 0; c < CPL; ++c) acc[c] = 0.0;
+                            cur_row = rws[b];
+                        }
+#pragma unroll
+                        for (int c = 0; c < CPL; ++c) acc[c] += contrib[b][c];
+                    }
+                }
+            }
+        }
+        flush(true);
+    }
+    __syncthreads();
+
+    // ---- merge the 2*NG group carries of this CTA in slot order
+    // run starts are handled by the group that owns the slot; a run is written to M unless it
+    // contains the first or the last valid slot of the CTA (those go to the global carry list).
+    int last_valid = -1;
+    for (int k = 2 * NG - 1; k >= 0; --k)
+        if (crow[k] >= 0) { last_valid = k; break; }
+    if (last_valid < 0) {
+        if (tid == 0) { p.carry_row[2 * blockIdx.x] = -1; p.carry_row[2 * blockIdx.x + 1] = -1; }
+        return;
+    }
+    if (tid == 0) p.carry_row[2 * blockIdx.x + 1] = -1;  // overwritten below if a distinct tail run exists
+    __syncthreads();
+    for (int sl = 0; sl < 2; ++sl) {
+        const int k = 2 * gi + sl;
+        const int row = crow[k];
+        if (row < 0) continue;
+        int prev = k - 1;
+        while (prev >= 0 && crow[prev] < 0) --prev;
+        if (prev >= 0 && crow[prev] == row) continue;  // not a run start
+        double sum[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) sum[c] = 0.0;
+        int j = k, last = k;
+        while (j < 2 * NG && (crow[j] == row || crow[j] < 0)) {
+            if (crow[j] == row) {
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) sum[c] += cval[j * RW + gl + GS * c];
+                last = j;
+            }
+            ++j;
+        }
+        const bool is_head = (prev < 0);
+        const bool is_tail = (last == last_valid);
+        if (is_head || is_tail) {
+            const long long slot = 2LL * blockIdx.x + (is_head ? 0 : 1);
+            if (gl == 0) p.carry_row[slot] = row;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int col = gl + GS * c;
+                if (col < R) p.carry_val[slot * R + col] = sum[c];
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int col = gl + GS * c;
+                if (col < R) p.M[(long long)row * R + col] = sum[c];
+            }
+        }
+    }
+}
+
+// Merge the per-CTA carries (2 per CTA, in storage order) and write the finished rows.
+__global__ void coo_fixup_kernel(const int *__restrict__ carry_row, const double *__restrict__ carry_val,
+                                 long long nslots, int R, double *M) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long k = t / R;
+    const int col = (int)(t % R);
+    if (k >= nslots) return;
+    const int row = carry_row[k];
+    if (row < 0) return;
+    long long prev = k - 1;
+    while (prev >= 0 && carry_row[prev] < 0) --prev;
+    if (prev >= 0 && carry_row[prev] == row) return;
+    double sum = 0.0;
+    for (long long j = k; j < nslots; ++j) {
+        const int rj = carry_row[j];
+        if (rj < 0) continue;
+        if (rj != row) break;
+        sum += carry_val[j * R + col];
+    }
+    M[(long long)row * R + col] = sum;
+}
+
+// Independent check kernel: one thread per (non-zero, column), FP64 atomics on M.
+struct AtomicParams {
+    const int *idx[SKT_MAX_NDIM];
+    const double *U[SKT_MAX_NDIM];
+    const double *vals;
+    long long nnz;
+    int ndim, R, mode;
+    double *M;
+};
+__global__ void mttkrp_coo_atomic_kernel(const __grid_constant__ AtomicParams p) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long z = t / p.R;
+    const int r = (int)(t % p.R);
+    if (z >= p.nnz) return;
+    double v = p.vals[z];
+    for (int m = 0; m < p.ndim; ++m)
+        if (m != p.mode) v *= p.U[m][(long long)p.idx[m][z] * p.R + r];
+    atomicAdd(&p.M[(long long)p.idx[p.mode][z] * p.R + r], v);
+}
+
+// <P, X> partial sums: each thread owns (non-zero, column) pairs in a fixed stride pattern.
+struct InnerParams {
+    const int *idx[SKT_MAX_NDIM];
+    const double *U[SKT_MAX_NDIM];
+    const double *vals;
+    const double *lambda;
+    long long nnz;
+    int ndim, R;
+};
+__global__ void __launch_bounds__(CT) coo_innerprod_kernel(const __grid_constant__ InnerParams p, double *out,
+                                                           double *partials, unsigned int *counter) {
+    __shared__ double red[CT / 32];
+    const long long total = p.nnz * p.R;
+    double s = 0.0;
+    for (long long t = blockIdx.x * (long long)CT + threadIdx.x; t < total; t += (long long)gridDim.x * CT) {
+        const long long z = t / p.R;
+        const int r = (int)(t % p.R);
+        double v = p.vals[z] * p.lambda[r];
+        for (int m = 0; m < p.ndim; ++m) v *= p.U[m][(long long)p.idx[m][z] * p.R + r];
+        s += v;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+        for (int w = 0; w < CT / 32; ++w) b += red[w];
+        partials[blockIdx.x] = b;
+    }
+    if (last_block_ticket(counter, gridDim.x)) {
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (unsigned k = 0; k < gridDim.x; ++k) tot += partials[k];
+            out[0] = tot;
+        }
+    }
+}
+
+__global__ void coo_convert_kernel(const long long *__restrict__ src, long long n, long long dim, int *__restrict__ dst,
+                                   unsigned int *bad) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long v = src[i];
+        if (v < 0 || v >= dim) atomicAdd(bad, 1u);
+        dst[i] = (int)v;
+    }
+}
+__global__ void iota_kernel(unsigned int *p, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = (unsigned int)i;
+}
+template <typename T>
+__global__ void gather_kernel(const T *__restrict__ src, const unsigned int *__restrict__ perm, long long n,
+                              T *__restrict__ dst) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[perm[i]];
+}
+
+int stream_blocks(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 8LL * sm_count())); }
+
+int group_cfg(int R, int &gs, int &cpl) {
+    cpl = (R + 31) / 32;
+    SKT_REQUIRE(cpl <= 4, SKT_EUNSUPPORTED, "sparse MTTKRP supports rank <= 128, got %d", R);
+    const int per = (R + cpl - 1) / cpl;
+    gs = 4;
+    while (gs < per) gs *= 2;
+    return SKT_OK;
+}
+
+long long coo_nctas(const skt_coo *t, int R) {
+    int gs, cpl;
+    if (group_cfg(R, gs, cpl) != SKT_OK) return 0;
+    const long long per_cta = (long long)(CT / gs) * S;
+    return std::max<long long>(1, (t->nnz + per_cta - 1) / per_cta);
+}
+
+template <int GS, int CPL>
+int launch_coo_no(int nother, const CooParams &p, long long nctas, cudaStream_t st) {
+    constexpr int NG = CT / GS;
+    const size_t smem = (size_t)((2 * NG * sizeof(int) + 7) / 8 * 8) + (size_t)2 * NG * GS * CPL * sizeof(double);
+    const unsigned grid = (unsigned)nctas;
+    if (nother <= 1) mttkrp_coo_kernel<GS, CPL, 1><<<grid, CT, smem, st>>>(p);
+    else if (nother == 2) mttkrp_coo_kernel<GS, CPL, 2><<<grid, CT, smem, st>>>(p);
+    else if (nother == 3) mttkrp_coo_kernel<GS, CPL, 3><<<grid, CT, smem, st>>>(p);
+    else mttkrp_coo_kernel<GS, CPL, 7><<<grid, CT, smem, st>>>(p);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+int launch_coo(int gs, int cpl, int nother, const CooParams &p, long long nctas, cudaStream_t st) {
+    if (cpl == 1) {
+        switch (gs) {
+            case 4: return launch_coo_no<4, 1>(nother, p, nctas, st);
+            case 8: return launch_coo_no<8, 1>(nother, p, nctas, st);
+            case 16: return launch_coo_no<16, 1>(nother, p, nctas, st);
+            default: return launch_coo_no<32, 1>(nother, p, nctas, st);
+        }
+    }
+    if (cpl == 2) return launch_coo_no<32, 2>(nother, p, nctas, st);
+    if (cpl == 3) return launch_coo_no<32, 3>(nother, p, nctas, st);
+    return launch_coo_no<32, 4>(nother, p, nctas, st);
+}
+
+int first_built(const skt_coo *t) {
+    for (int n = 0; n < t->ndim; ++n)
+        if (t->built_mask & (1u << n)) return n;
+    return -1;
+}
+
+}  // namespace
+}  // namespace skt
+
+using namespace skt;
+
+extern "C" int skt_coo_destroy(skt_coo *t) {
+    if (!t) return SKT_OK;
+    for (int n = 0; n < SKT_MAX_NDIM; ++n) {
+        for (int m = 0; m < SKT_MAX_NDIM; ++m)
+            if (t->idx[n][m]) cudaFree(t->idx[n][m]);
+        if (t->vals[n]) cudaFree(t->vals[n]);
+    }
+    delete t;
+    return SKT_OK;
+}
+
+extern "C" int64_t skt_coo_nnz(const skt_coo *t) { return t ? t->nnz : 0; }
+extern "C" size_t skt_coo_device_bytes(const skt_coo *t) { return t ? t->bytes : 0; }
+
+extern "C" int skt_coo_build(const int64_t *const *subs_d, const double *vals_d, int64_t nnz, const int64_t *shape,
+                             int ndim, unsigned modes_mask, skt_stream stream, skt_coo **out) {
+    SKT_REQUIRE(subs_d && shape && out && (vals_d || nnz == 0), SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(ndim >= 2 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "ndim must be in [2, %d], got %d", SKT_MAX_NDIM, ndim);
+    SKT_REQUIRE(nnz >= 0 && nnz < (1LL << 31) - 1, SKT_ESHAPE, "nnz %lld outside [0, 2^31)", (long long)nnz);
+    for (int m = 0; m < ndim; ++m)
+        SKT_REQUIRE(shape[m] >= 1 && shape[m] < (1LL << 31), SKT_ESHAPE, "shape[%d] = %lld not in [1, 2^31)", m, (long long)shape[m]);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (modes_mask == 0) modes_mask = (1u << ndim) - 1u;
+
+    skt_coo *t = new skt_coo();
+    memset(t, 0, sizeof(*t));
+    t->ndim = ndim;
+    t->nnz = nnz;
+    for (int m = 0; m < ndim; ++m) t->shape[m] = shape[m];
+    *out = nullptr;
+
+    const size_t n = (size_t)std::max<int64_t>(nnz, 1);
+    int *base[SKT_MAX_NDIM] = {nullptr};
+    int *keys_out = nullptr;
+    unsigned int *perm_in = nullptr, *perm_out = nullptr, *bad = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int rc = SKT_OK;
+    auto cleanup = [&]() {
+        for (int m = 0; m < ndim; ++m) cudaFree(base[m]);
+        cudaFree(keys_out); cudaFree(perm_in); cudaFree(perm_out); cudaFree(bad); cudaFree(tmp);
+    };
+#define BUILD_TRY(call)                                                                \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            rc = cuda_fail(e__, #call, __FILE__, __LINE__);                            \
+            cleanup(); skt_coo_destroy(t);                                             \
+            return rc;                                                                 \
+        }                                                                              \
+    } while (0)
+    BUILD_TRY(cudaMalloc(&bad, sizeof(unsigned int)));
+    BUILD_TRY(cudaMemsetAsync(bad, 0, sizeof(unsigned int), st));
+    for (int m = 0; m < ndim; ++m) {
+        BUILD_TRY(cudaMalloc(&base[m], n * sizeof(int)));
+        if (nnz > 0) coo_convert_kernel<<<stream_blocks(nnz), 256, 0, st>>>((const long long *)subs_d[m], nnz, shape[m], base[m], bad);
+    }
+    unsigned int nbad = 0;
+    BUILD_TRY(cudaMemcpyAsync(&nbad, bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    BUILD_TRY(cudaStreamSynchronize(st));
+    if (nbad) {
+        cleanup(); skt_coo_destroy(t);
+        set_error("%u subscripts fall outside the tensor shape", nbad);
+        return SKT_EINVAL;
+    }
+    BUILD_TRY(cudaMalloc(&keys_out, n * sizeof(int)));
+    BUILD_TRY(cudaMalloc(&perm_in, n * sizeof(unsigned int)));
+    BUILD_TRY(cudaMalloc(&perm_out, n * sizeof(unsigned int)));
+    if (nnz > 0) iota_kernel<<<stream_blocks(nnz), 256, 0, st>>>(perm_in, nnz);
+    BUILD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const int *)base[0], keys_out, (const unsigned int *)perm_in,
+                                              perm_out, (int)std::min<int64_t>(nnz, INT32_MAX), 0, 32, st));
+    BUILD_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 256));
+
+    for (int nmode = 0; nmode < ndim; ++nmode) {
+        if (!(modes_mask & (1u << nmode))) continue;
+        int bits = 1;
+        while ((1LL << bits) < shape[nmode]) ++bits;
+        if (nnz > 0) {
+            BUILD_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const int *)base[nmode], keys_out,
+                                                      (const unsigned int *)perm_in, perm_out, (int)nnz, 0, bits, st));
+        }
+        for (int m = 0; m < ndim; ++m) {
+            BUILD_TRY(cudaMalloc(&t->idx[nmode][m], n * sizeof(int)));
+            t->bytes += n * sizeof(int);
+            if (nnz > 0) gather_kernel<int><<<stream_blocks(nnz), 256, 0, st>>>(base[m], perm_out, nnz, t->idx[nmode][m]);
+        }
+        BUILD_TRY(cudaMalloc(&t->vals[nmode], n * sizeof(double)));
+        t->bytes += n * sizeof(double);
+        if (nnz > 0) gather_kernel<double><<<stream_blocks(nnz), 256, 0, st>>>(vals_d, perm_out, nnz, t->vals[nmode]);
+        t->built_mask |= (1u << nmode);
+    }
+    BUILD_TRY(cudaGetLastError());
+    BUILD_TRY(cudaStreamSynchronize(st));
+#undef BUILD_TRY
+    cleanup();
+    *out = t;
+    return SKT_OK;
+}
+
+extern "C" int skt_coo_build_host(const int64_t *const *subs_h, const double *vals_h, int64_t nnz,
+                                  const int64_t *shape, int ndim, unsigned modes_mask, skt_coo **out) {
+    SKT_REQUIRE(subs_h && shape && out && (vals_h || nnz == 0), SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(ndim >= 2 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "ndim must be in [2, %d], got %d", SKT_MAX_NDIM, ndim);
+    SKT_REQUIRE(nnz >= 0, SKT_ESHAPE, "negative nnz");
+    const size_t n = (size_t)std::max<int64_t>(nnz, 1);
+    long long *subs_d[SKT_MAX_NDIM] = {nullptr};
+    double *vals_d = nullptr;
+    auto cleanup = [&]() {
+        for (int m = 0; m < ndim; ++m) cudaFree(subs_d[m]);
+        cudaFree(vals_d);
+    };
+    for (int m = 0; m < ndim; ++m) {
+        cudaError_t e = cudaMalloc(&subs_d[m], n * sizeof(long long));
+        if (e == cudaSuccess && nnz > 0) e = cudaMemcpy(subs_d[m], subs_h[m], (size_t)nnz * sizeof(long long), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "upload subscripts", __FILE__, __LINE__); }
+    }
+    cudaError_t e = cudaMalloc(&vals_d, n * sizeof(double));
+    if (e == cudaSuccess && nnz > 0) e = cudaMemcpy(vals_d, vals_h, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "upload values", __FILE__, __LINE__); }
+    const int rc = skt_coo_build((const int64_t *const *)subs_d, vals_d, nnz, shape, ndim, modes_mask, nullptr, out);
+    cleanup();
+    return rc;
+}
+
+extern "C" size_t skt_mttkrp_coo_workspace(const skt_coo *t, int rank, int mode) {
+    (void)mode;
+    if (!t || rank < 1) return 0;
+    const long long nctas = coo_nctas(t, rank);
+    return align_up((size_t)2 * nctas * sizeof(int), 256) + align_up((size_t)2 * nctas * rank * sizeof(double), 256);
+}
+
+extern "C" int skt_mttkrp_coo(const skt_coo *t, const double *const *U_d, int rank, int mode, double *M_d, void *ws_d,
+                              size_t ws_bytes, skt_stream stream) {
+    SKT_REQUIRE(t && U_d && M_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(mode >= 0 && mode < t->ndim, SKT_EINVAL, "mode %d out of range", mode);
+    SKT_REQUIRE(rank >= 1, SKT_EINVAL, "rank must be >= 1");
+    SKT_REQUIRE(t->built_mask & (1u << mode), SKT_EINVAL, "the sorted copy for mode %d was not built", mode);
+    int gs, cpl;
+    int rc = group_cfg(rank, gs, cpl);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t need = skt_mttkrp_coo_workspace(t, rank, mode);
+    SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    SKT_CUDA(cudaMemsetAsync(M_d, 0, (size_t)t->shape[mode] * rank * sizeof(double), st));
+    if (t->nnz == 0) return SKT_OK;
+    const long long nctas = coo_nctas(t, rank);
+    CooParams p;
+    p.rows = t->idx[mode][mode];
+    p.vals = t->vals[mode];
+    p.nnz = t->nnz;
+    p.R = rank;
+    p.M = M_d;
+    p.carry_row = (int *)ws_d;
+    p.carry_val = (double *)((char *)ws_d + align_up((size_t)2 * nctas * sizeof(int), 256));
+    int k = 0;
+    for (int m = 0; m < t->ndim; ++m) {
+        if (m == mode) continue;
+        SKT_REQUIRE(U_d[m] != nullptr, SKT_EINVAL, "U[%d] is NULL (only U[mode] may be)", m);
+        p.oidx[k] = t->idx[mode][m];
+        p.U[k] = U_d[m];
+        ++k;
+    }
+    p.nother = k;
+    for (; k < SKT_MAX_NDIM; ++k) { p.oidx[k] = p.oidx[0]; p.U[k] = p.U[0]; }
+    rc = launch_coo(gs, cpl, p.nother, p, nctas, st);
+    if (rc) return rc;
+    const long long nslots = 2 * nctas;
+    const long long threads = nslots * rank;
+    coo_fixup_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p.carry_row, p.carry_val, nslots, rank, M_d);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" int skt_mttkrp_coo_atomic(const skt_coo *t, const double *const *U_d, int rank, int mode, double *M_d,
+                                     skt_stream stream) {
+    SKT_REQUIRE(t && U_d && M_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(mode >= 0 && mode < t->ndim && rank >= 1, SKT_EINVAL, "bad mode/rank");
+    const int src = first_built(t);
+    SKT_REQUIRE(src >= 0, SKT_EINVAL, "no sorted copy was built");
+    cudaStream_t st = (cudaStream_t)stream;
+    SKT_CUDA(cudaMemsetAsync(M_d, 0, (size_t)t->shape[mode] * rank * sizeof(double), st));
+    if (t->nnz == 0) return SKT_OK;
+    AtomicParams p;
+    for (int m = 0; m < t->ndim; ++m) {
+        SKT_REQUIRE(m == mode || U_d[m] != nullptr, SKT_EINVAL, "U[%d] is NULL", m);
+        p.idx[m] = t->idx[src][m];
+        p.U[m] = U_d[m];
+    }
+    p.vals = t->vals[src];
+    p.nnz = t->nnz; p.ndim = t->ndim; p.R = rank; p.mode = mode; p.M = M_d;
+    const long long threads = t->nnz * rank;
+    mttkrp_coo_atomic_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" size_t skt_coo_innerprod_workspace(const skt_coo *t, int rank) {
+    (void)t; (void)rank;
+    return 256 + align_up((size_t)4 * sm_count() * sizeof(double), 256);
+}
+
+extern "C" int skt_coo_innerprod(const skt_coo *t, const double *const *U_d, const double *lambda_d, int rank,
+                                 double *out_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    SKT_REQUIRE(t && U_d && lambda_d && out_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(rank >= 1, SKT_EINVAL, "rank must be >= 1");
+    const int src = first_built(t);
+    SKT_REQUIRE(src >= 0, SKT_EINVAL, "no sorted copy was built");
+    const size_t need = skt_coo_innerprod_workspace(t, rank);
+    SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    InnerParams p;
+    for (int m = 0; m < t->ndim; ++m) {
+        SKT_REQUIRE(U_d[m] != nullptr, SKT_EINVAL, "U[%d] is NULL", m);
+        p.idx[m] = t->idx[src][m];
+        p.U[m] = U_d[m];
+    }
+    p.vals = t->vals[src]; p.lambda = lambda_d; p.nnz = t->nnz; p.ndim = t->ndim; p.R = rank;
+    unsigned int *counter = (unsigned int *)ws_d;
+    double *partials = (double *)((char *)ws_d + 256);
+    SKT_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    const long long total = std::max<long long>(1, t->nnz * rank);
+    const int nb = (int)std::max<long long>(1, std::min<long long>((total + CT - 1) / CT, 4LL * sm_count()));
+    coo_innerprod_kernel<<<nb, CT, 0, st>>>(p, out_d, partials, counter);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" int skt_coo_sumsq(const skt_coo *t, double *out_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    SKT_REQUIRE(t && out_d, SKT_EINVAL, "NULL argument");
+    const int src = first_built(t);
+    SKT_REQUIRE(src >= 0, SKT_EINVAL, "no sorted copy was built");
+    return skt_sumsq(t->vals[src], t->nnz, out_d, ws_d, ws_bytes, stream);
+}

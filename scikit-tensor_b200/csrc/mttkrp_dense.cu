@@ -1,0 +1,628 @@
+// Dense FP64 MTTKRP for sm_100a -- the kernel behind dtensor.uttkrp
+// (reference: sktensor/dtensor.py:163-167 = unfold (dtensor.py:103-150) . khatrirao (core.py:333-378)).
+//
+// Formulation (no unfolding, no Khatri-Rao matrix).  For output mode n pick the contraction
+// mode c = N-1 (c = 0 when n == N-1).  Every other index forms the "row space", viewed as
+// (l, i_n, t): l = the modes left of n, t = the modes between n and c.  Then
+//
+//     acc[row, r]  = sum_kc X[row, kc] * U_c[kc, r]                 (FP64 tensor-core GEMM)
+//     M[i_n, r]    = sum_{l,t} acc[(l,i_n,t), r] * prod_{m != n,c} U_m[i_m, r]   (epilogue)
+//
+// so the flop count stays 2*R*prod(I) and X is streamed exactly once.  A CTA owns a 128-row
+// tile (a power-of-two box bl x bi x bt in (l, i_n, t)), streams it in BK=32 slices through a
+// multi-stage cp.async ring, multiplies with DMMA.8x8x4, applies the Khatri-Rao weights to
+// the accumulators in registers at the end of each tile, and keeps a second register
+// accumulator across all tiles of its work item.  Rows of equal i_n are then summed through
+// shared memory in a fixed order and written either straight to M or to a per-split partial
+// slab that a second tiny kernel adds up -- no atomics, bitwise reproducible.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace skt {
+
+namespace {
+
+constexpr int BM = 128;        // rows per tile
+constexpr int BK = 32;         // contraction slice per pipeline stage
+constexpr int NTHREADS = 256;  // 8 warps, 16 tile rows each
+constexpr int XS_K = BK + 4;   // row stride (doubles) of a K-major X stage  (== 4 mod 16: conflict-free DMMA loads)
+constexpr int XS_M = BM + 4;   // row stride of an M-major X stage
+constexpr int ZS = 36;         // row stride of the flush staging tile (32 columns + 4)
+
+struct WeightMode {
+    const double *U;  // factor of a mode that is neither the output nor the contraction mode
+    int dim;          // its length
+    int div;          // index = (space_index / div) % dim
+    int space;        // 0: decomposes l, 1: decomposes t
+};
+
+struct DenseParams {
+    const double *X;
+    const double *Uc;   // factor of the contraction mode (Kc x ld), pre-offset to the first column of this pass
+    double *out;        // M (nsplit == 1) or the partial slabs [nsplit][In][ld]
+    long long out_split_stride;
+    long long NR;       // L*In*T = number of rows (the kc stride of an M-major X)
+    int R;              // columns handled by this pass (<= 8*NB)
+    int ld;             // row stride of every factor and of the output
+    int Kc, In, L, T;
+    int lg_bt, lg_bi, lg_bl;
+    int nit, ntt, nred;  // output-row tiles; t tiles; reduction tiles per output-row tile (= nlt*ntt)
+    int nsplit, chunk, nitems;
+    int nk;
+    int vecX, vecU;
+    int nw;
+    WeightMode w[SKT_MAX_NDIM];
+};
+
+template <int NB, bool MMAJOR>
+__global__ void __launch_bounds__(NTHREADS, 1) mttkrp_dense_kernel(const __grid_constant__ DenseParams p) {
+    constexpr int STAGES = (NB <= 4) ? 4 : 3;
+    constexpr int RS = 8 * NB + 4;
+    constexpr int XSTAGE = MMAJOR ? BK * XS_M : BM * XS_K;
+    constexpr int STAGE = XSTAGE + BK * RS;
+    constexpr int NROWOFF = MMAJOR ? 2 : 8;
+
+    extern __shared__ __align__(16) double smem[];
+    double *Z = smem + STAGES * STAGE;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int bt = 1 << p.lg_bt, bi = 1 << p.lg_bi, bl = 1 << p.lg_bl;
+
+    // slot q of tile (it, lt, tt) -> (l, i, t) and validity
+    auto decompose = [&](int q, int it, int lt, int tt, int &l, int &i, int &t) -> bool {
+        const int t_off = q & (bt - 1);
+        const int i_off = (q >> p.lg_bt) & (bi - 1);
+        const int l_off = q >> (p.lg_bt + p.lg_bi);
+        t = tt * bt + t_off;
+        i = it * bi + i_off;
+        l = lt * bl + l_off;
+        return (t < p.T) && (i < p.In) && (l < p.L);
+    };
+    auto item_range = [&](int item, int &t0, int &t1) {
+        const int s = item % p.nsplit;
+        t0 = s * p.chunk;
+        t1 = min(t0 + p.chunk, p.nred);
+    };
+
+    // ------------------------------------------------------------------ loader state
+    int l_item = blockIdx.x, l_tile = 0, l_tile_end = 0, l_ks = 0;
+    bool l_active = l_item < p.nitems;
+    long long rowoff[NROWOFF];  // element offset of each row this thread copies; -1 = padding row
+
+    auto setup_rows = [&]() {
+        const int it = l_item / p.nsplit;
+        const int lt = l_tile / p.ntt, tt = l_tile % p.ntt;
+#pragma unroll
+        for (int j = 0; j < NROWOFF; ++j) {
+            const int q = MMAJOR ? (2 * (tid & 63) + j) : ((tid >> 4) + 16 * j);
+            int l, i, t;
+            const bool ok = decompose(q, it, lt, tt, l, i, t);
+            const long long rho = ((long long)l * p.In + i) * p.T + t;
+            rowoff[j] = ok ? (MMAJOR ? rho : rho * p.Kc) : -1;
+        }
+    };
+    if (l_active) {
+        item_range(l_item, l_tile, l_tile_end);
+        setup_rows();
+    }
+
+    auto loader_issue = [&](int st) {
+        if (l_active) {
+            double *Xs = smem + st * STAGE;
+            double *Us = Xs + XSTAGE;
+            const int k0 = l_ks * BK;
+            if (!MMAJOR) {
+                const int col = 2 * (tid & 15);
+                const int kc = k0 + col;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int q = (tid >> 4) + 16 * j;
+                    double *dst = Xs + q * XS_K + col;
+                    const long long off = rowoff[j];
+                    if (p.vecX) {
+                        const bool ok = (off >= 0) && (kc < p.Kc);
+                        cp_async16(dst, p.X + (ok ? off + kc : 0), ok ? 16 : 0);
+                    } else {
+                        const bool ok0 = (off >= 0) && (kc < p.Kc);
+                        const bool ok1 = (off >= 0) && (kc + 1 < p.Kc);
+                        cp_async8(dst, p.X + (ok0 ? off + kc : 0), ok0 ? 8 : 0);
+                        cp_async8(dst + 1, p.X + (ok1 ? off + kc + 1 : 0), ok1 ? 8 : 0);
+                    }
+                }
+            } else {
+                const int q = 2 * (tid & 63);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int kr = (tid >> 6) + 4 * j;
+                    const int kc = k0 + kr;
+                    double *dst = Xs + kr * XS_M + q;
+                    const long long koff = (long long)kc * p.NR;
+                    if (p.vecX) {
+                        const bool ok = (rowoff[0] >= 0) && (kc < p.Kc);
+                        cp_async16(dst, p.X + (ok ? koff + rowoff[0] : 0), ok ? 16 : 0);
+                    } else {
+                        const bool ok0 = (rowoff[0] >= 0) && (kc < p.Kc);
+                        const bool ok1 = (rowoff[1] >= 0) && (kc < p.Kc);
+                        cp_async8(dst, p.X + (ok0 ? koff + rowoff[0] : 0), ok0 ? 8 : 0);
+                        cp_async8(dst + 1, p.X + (ok1 ? koff + rowoff[1] : 0), ok1 ? 8 : 0);
+                    }
+                }
+            }
+            // factor slice of the contraction mode: BK rows x 8*NB columns (zero beyond R / Kc)
+            for (int c = tid; c < BK * 4 * NB; c += NTHREADS) {
+                const int kr = c / (4 * NB);
+                const int col = 2 * (c % (4 * NB));
+                const int kc = k0 + kr;
+                double *dst = Us + kr * RS + col;
+                const double *src = p.Uc + (long long)kc * p.ld + col;
+                if (p.vecU) {
+                    const bool ok = (kc < p.Kc) && (col < p.R);
+                    cp_async16(dst, ok ? src : p.Uc, ok ? 16 : 0);
+                } else {
+                    const bool ok0 = (kc < p.Kc) && (col < p.R);
+                    const bool ok1 = (kc < p.Kc) && (col + 1 < p.R);
+                    cp_async8(dst, ok0 ? src : p.Uc, ok0 ? 8 : 0);
+                    cp_async8(dst + 1, ok1 ? src + 1 : p.Uc, ok1 ? 8 : 0);
+                }
+            }
+            // advance to the next (item, tile, k-slice) of this CTA's static schedule
+            if (++l_ks == p.nk) {
+                l_ks = 0;
+                if (++l_tile == l_tile_end) {
+                    l_item += gridDim.x;
+                    if (l_item < p.nitems) item_range(l_item, l_tile, l_tile_end);
+                    else l_active = false;
+                }
+                if (l_active) setup_rows();
+            }
+        }
+        cp_async_commit();
+    };
+
+    // ------------------------------------------------------------------ consumer state
+    double acc[2][NB][2], out[2][NB][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            acc[a][nb][0] = acc[a][nb][1] = 0.0;
+            out[a][nb][0] = out[a][nb][1] = 0.0;
+        }
+    int c_item = blockIdx.x, c_tile = 0, c_tile_end = 0, c_ks = 0;
+    if (c_item < p.nitems) item_range(c_item, c_tile, c_tile_end);
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) loader_issue(s);
+
+    int stage = 0;
+    while (c_item < p.nitems) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        loader_issue((stage + STAGES - 1) % STAGES);
+
+        // ---- 128 x 8NB x 32 FP64 tensor-core block product on the current stage
+        {
+            const double *Xs = smem + stage * STAGE;
+            const double *Us = Xs + XSTAGE;
+#pragma unroll
+            for (int kk = 0; kk < BK; kk += 4) {
+                double a0, a1;
+                if (MMAJOR) {
+                    a0 = Xs[(kk + t4) * XS_M + 16 * warp + g];
+                    a1 = Xs[(kk + t4) * XS_M + 16 * warp + 8 + g];
+                } else {
+                    a0 = Xs[(16 * warp + g) * XS_K + kk + t4];
+                    a1 = Xs[(16 * warp + 8 + g) * XS_K + kk + t4];
+                }
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const double b = Us[(kk + t4) * RS + 8 * nb + g];
+                    dmma884(acc[0][nb][0], acc[0][nb][1], a0, b);
+                    dmma884(acc[1][nb][0], acc[1][nb][1], a1, b);
+                }
+            }
+        }
+        stage = (stage + 1) % STAGES;
+
+        if (++c_ks == p.nk) {
+            c_ks = 0;
+            // ---- tile epilogue: out += acc * prod_m U_m[i_m(row), col]   (the Khatri-Rao rows, on the fly)
+            {
+                const int it = c_item / p.nsplit;
+                const int lt = c_tile / p.ntt, tt = c_tile % p.ntt;
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const int q = 16 * warp + 8 * a + g;
+                    int l, i, t;
+                    const bool ok = decompose(q, it, lt, tt, l, i, t);
+                    double wgt[NB][2];
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) wgt[nb][0] = wgt[nb][1] = ok ? 1.0 : 0.0;
+                    if (ok) {
+                        for (int m = 0; m < p.nw; ++m) {
+                            const int sp = p.w[m].space ? t : l;
+                            const int idx = (sp / p.w[m].div) % p.w[m].dim;
+                            const double *row = p.w[m].U + (long long)idx * p.ld;
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) {
+                                const int col = 8 * nb + 2 * t4;
+                                if (col < p.R) wgt[nb][0] *= __ldg(row + col);
+                                if (col + 1 < p.R) wgt[nb][1] *= __ldg(row + col + 1);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        out[a][nb][0] += ok ? wgt[nb][0] * acc[a][nb][0] : 0.0;
+                        out[a][nb][1] += ok ? wgt[nb][1] * acc[a][nb][1] : 0.0;
+                        acc[a][nb][0] = acc[a][nb][1] = 0.0;
+                    }
+                }
+            }
+            if (++c_tile == c_tile_end) {
+                // ---- item flush: sum rows of equal i_n in a fixed order, write bi x R outputs
+                const int it = c_item / p.nsplit, s = c_item % p.nsplit;
+                double *dst = p.out + (long long)s * p.out_split_stride;
+                constexpr int NH = (NB + 3) / 4;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const int q = 16 * warp + 8 * a + g;
+#pragma unroll
+                        for (int nn = 0; nn < 4; ++nn) {
+                            const int nb = 4 * h + nn;
+                            if (nb < NB) {
+                                Z[q * ZS + 8 * nn + 2 * t4] = out[a][nb][0];
+                                Z[q * ZS + 8 * nn + 2 * t4 + 1] = out[a][nb][1];
+                                out[a][nb][0] = out[a][nb][1] = 0.0;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    for (int o = tid; o < bi * 32; o += NTHREADS) {
+                        const int i_off = o >> 5, c = o & 31;
+                        const int col = 32 * h + c;
+                        const int i = it * bi + i_off;
+                        if (col < p.R && col < 8 * NB && i < p.In) {
+                            double sum = 0.0;
+                            for (int l_off = 0; l_off < bl; ++l_off)
+                                for (int t_off = 0; t_off < bt; ++t_off) {
+                                    const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
+                                    sum += Z[q * ZS + c];
+                                }
+                            dst[(long long)i * p.ld + col] = sum;
+                        }
+                    }
+                    __syncthreads();
+                }
+                c_item += gridDim.x;
+                if (c_item < p.nitems) item_range(c_item, c_tile, c_tile_end);
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// M[e] = sum_s P[s][e] in split order (deterministic)
+__global__ void reduce_splits_kernel(const double *__restrict__ P, int nsplit, long long n, double *__restrict__ M) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < nsplit; ++k) s += P[(long long)k * n + e];
+        M[e] = s;
+    }
+}
+
+struct NaiveParams {
+    const double *X;
+    const double *U[SKT_MAX_NDIM];
+    long long shape[SKT_MAX_NDIM];
+    long long stride[SKT_MAX_NDIM];
+    int ndim, R, mode;
+    long long nother;  // prod of the other dims
+};
+
+// One thread per output element, serial loop over the rest of the tensor.  Slow and obviously
+// correct: the independent on-device check used by the tests.
+__global__ void mttkrp_dense_naive_kernel(const __grid_constant__ NaiveParams p, double *__restrict__ M) {
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long In = p.shape[p.mode];
+    if (idx >= In * p.R) return;
+    const long long i = idx / p.R;
+    const int r = (int)(idx % p.R);
+    double sum = 0.0;
+    for (long long e = 0; e < p.nother; ++e) {
+        long long rem = e, off = i * p.stride[p.mode];
+        double w = 1.0;
+        for (int m = p.ndim - 1; m >= 0; --m) {
+            if (m == p.mode) continue;
+            const long long im = rem % p.shape[m];
+            rem /= p.shape[m];
+            off += im * p.stride[m];
+            w *= p.U[m][im * p.R + r];
+        }
+        sum += p.X[off] * w;
+    }
+    M[idx] = sum;
+}
+
+// ------------------------------------------------------------------ host-side planning
+struct DensePlan {
+    bool mmajor;
+    int c;  // contraction mode
+    int Kc, In, L, T;
+    int lg_bt, lg_bi, lg_bl;
+    int nit, nlt, ntt, nred;
+    int nsplit, chunk, nitems;
+    int nw;
+    int wmode[SKT_MAX_NDIM], wdim[SKT_MAX_NDIM], wdiv[SKT_MAX_NDIM], wspace[SKT_MAX_NDIM];
+    int grid;
+};
+
+int ilog2(int x) {
+    int l = 0;
+    while ((1 << l) < x) ++l;
+    return l;
+}
+
+int make_plan(const int64_t *shape, int ndim, int rank, int mode, DensePlan &pl) {
+    SKT_REQUIRE(shape != nullptr, SKT_EINVAL, "shape is NULL");
+    SKT_REQUIRE(ndim >= 2 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "ndim must be in [2, %d], got %d", SKT_MAX_NDIM, ndim);
+    SKT_REQUIRE(mode >= 0 && mode < ndim, SKT_EINVAL, "mode %d out of range for a %d-way tensor", mode, ndim);
+    SKT_REQUIRE(rank >= 1, SKT_EINVAL, "rank must be >= 1, got %d", rank);
+    for (int m = 0; m < ndim; ++m) SKT_REQUIRE(shape[m] >= 1, SKT_ESHAPE, "shape[%d] = %lld", m, (long long)shape[m]);
+    pl.mmajor = (mode == ndim - 1);
+    pl.c = pl.mmajor ? 0 : ndim - 1;
+    long long L = 1, T = 1;
+    pl.nw = 0;
+    const int lo = pl.mmajor ? 1 : 0;  // first mode of the l-space
+    // l-space: modes lo..mode-1 ; t-space: modes mode+1..(c-1) (empty when c == 0)
+    {
+        long long div = 1;
+        for (int m = mode - 1; m >= lo; --m) {
+            pl.wmode[pl.nw] = m; pl.wdim[pl.nw] = (int)shape[m]; pl.wdiv[pl.nw] = (int)div; pl.wspace[pl.nw] = 0;
+            ++pl.nw;
+            div *= shape[m];
+            SKT_REQUIRE(div < (1LL << 31), SKT_ESHAPE, "product of the modes left of mode %d exceeds 2^31", mode);
+        }
+        L = div;
+    }
+    if (!pl.mmajor) {
+        long long div = 1;
+        for (int m = ndim - 2; m > mode; --m) {
+            pl.wmode[pl.nw] = m; pl.wdim[pl.nw] = (int)shape[m]; pl.wdiv[pl.nw] = (int)div; pl.wspace[pl.nw] = 1;
+            ++pl.nw;
+            div *= shape[m];
+            SKT_REQUIRE(div < (1LL << 31), SKT_ESHAPE, "product of the modes right of mode %d exceeds 2^31", mode);
+        }
+        T = div;
+    }
+    SKT_REQUIRE(shape[mode] < (1LL << 31) && shape[pl.c] < (1LL << 31), SKT_ESHAPE, "mode length exceeds 2^31");
+    pl.L = (int)L; pl.T = (int)T; pl.In = (int)shape[mode]; pl.Kc = (int)shape[pl.c];
+
+    // tile box: the power-of-two (bl, bi, bt), bl*bi*bt = 128, that wastes the fewest padded rows;
+    // ties go to the longest contiguous run (bt for K-major, bi for M-major).
+    double best = 1e300;
+    int bbt = 0, bbi = 0, bbl = 0;
+    for (int lt = 0; lt <= 7; ++lt)
+        for (int li = 0; li + lt <= 7; ++li) {
+            const int ll = 7 - lt - li;
+            const long long bt = 1LL << lt, bi = 1LL << li, bl = 1LL << ll;
+            if (pl.mmajor && lt != 0) continue;
+            const double padded = (double)((T + bt - 1) / bt * bt) * (double)((pl.In + bi - 1) / bi * bi) *
+                                  (double)((L + bl - 1) / bl * bl);
+            // prefer (slightly) boxes whose inner run is long: fewer DRAM page switches
+            const double score = padded * (1.0 + 1e-3 * (pl.mmajor ? (7 - li) : (7 - lt)) + 1e-5 * ll);
+            if (score < best) { best = score; bbt = lt; bbi = li; bbl = ll; }
+        }
+    pl.lg_bt = bbt; pl.lg_bi = bbi; pl.lg_bl = bbl;
+    const long long nit = (pl.In + (1 << bbi) - 1) >> bbi;
+    const long long nlt = (L + (1 << bbl) - 1) >> bbl;
+    const long long ntt = (T + (1 << bbt) - 1) >> bbt;
+    SKT_REQUIRE(nlt * ntt < (1LL << 31) && nit * nlt * ntt < (1LL << 40), SKT_ESHAPE, "tensor too large for the tile scheduler");
+    pl.nit = (int)nit; pl.nlt = (int)nlt; pl.ntt = (int)ntt; pl.nred = (int)(nlt * ntt);
+
+    // split the reduction space so that the static round-robin schedule over the SMs is balanced
+    // without drowning the memory system in partial slabs.
+    const int G = sm_count();
+    const double tile_cost = (double)BM * pl.Kc * G;          // elements streamed, in chip-bandwidth units
+    const double slab_cost = 2.0 * (double)pl.In * rank;      // write + re-read of one partial slab
+    double best_cost = 1e300;
+    int best_ns = 1;
+    const int ns_max = (int)std::min<long long>(pl.nred, std::max<long long>(1, (8LL * G + nit - 1) / nit));
+    for (int ns = 1; ns <= ns_max; ++ns) {
+        const int chunk = (pl.nred + ns - 1) / ns;
+        const int ns_eff = (pl.nred + chunk - 1) / chunk;
+        if (ns_eff != ns) continue;
+        const long long nitems = nit * ns;
+        const int last = pl.nred - (ns - 1) * chunk;
+        // makespan of the round-robin schedule: CTA b takes items b, b+G, ...
+        // items are (it-major, split-minor); the short item of each row-tile is split ns-1.
+        long long worst = 0;
+        if (nitems <= 4096LL * G) {
+            const int gcnt = (int)std::min<long long>(G, nitems);
+            for (int b = 0; b < gcnt; ++b) {
+                long long tiles = 0;
+                for (long long it = b; it < nitems; it += G) tiles += ((it % ns) == ns - 1) ? last : chunk;
+                worst = std::max(worst, tiles);
+            }
+        } else {
+            worst = (nitems + G - 1) / G * chunk;
+        }
+        const double cost = (double)worst * tile_cost + (ns > 1 ? ns * slab_cost : 0.0);
+        if (cost < best_cost) { best_cost = cost; best_ns = ns; }
+    }
+    pl.nsplit = best_ns;
+    pl.chunk = (pl.nred + best_ns - 1) / best_ns;
+    const long long nitems = nit * best_ns;
+    SKT_REQUIRE(nitems < (1LL << 31), SKT_ESHAPE, "too many work items");
+    pl.nitems = (int)nitems;
+    pl.grid = (int)std::min<long long>(G, nitems);
+    return SKT_OK;
+}
+
+template <int NB, bool MMAJOR>
+int launch_dense(const DenseParams &p, int grid, cudaStream_t st) {
+    constexpr int STAGES = (NB <= 4) ? 4 : 3;
+    constexpr int RS = 8 * NB + 4;
+    constexpr int XSTAGE = MMAJOR ? BK * XS_M : BM * XS_K;
+    constexpr int STAGE = XSTAGE + BK * RS;
+    const size_t smem = (size_t)(STAGES * STAGE + BM * ZS) * sizeof(double);
+    static bool configured = false;  // per template instance
+    if (!configured) {
+        SKT_CUDA(cudaFuncSetAttribute(mttkrp_dense_kernel<NB, MMAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    mttkrp_dense_kernel<NB, MMAJOR><<<grid, NTHREADS, smem, st>>>(p);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+template <bool MMAJOR>
+int launch_dense_nb(int nb, const DenseParams &p, int grid, cudaStream_t st) {
+    switch (nb) {
+        case 1: return launch_dense<1, MMAJOR>(p, grid, st);
+        case 2: return launch_dense<2, MMAJOR>(p, grid, st);
+        case 3: return launch_dense<3, MMAJOR>(p, grid, st);
+        case 4: return launch_dense<4, MMAJOR>(p, grid, st);
+        case 5: return launch_dense<5, MMAJOR>(p, grid, st);
+        case 6: return launch_dense<6, MMAJOR>(p, grid, st);
+        case 7: return launch_dense<7, MMAJOR>(p, grid, st);
+        default: return launch_dense<8, MMAJOR>(p, grid, st);
+    }
+}
+
+}  // namespace
+}  // namespace skt
+
+using namespace skt;
+
+extern "C" size_t skt_mttkrp_dense_workspace(const int64_t *shape, int ndim, int rank, int mode) {
+    DensePlan pl;
+    if (make_plan(shape, ndim, rank, mode, pl) != SKT_OK) return 0;
+    if (pl.nsplit <= 1) return 256;
+    return align_up((size_t)pl.nsplit * pl.In * rank * sizeof(double), 256);
+}
+
+extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndim, const double *const *U_d, int rank,
+                                int mode, double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    DensePlan pl;
+    int rc = make_plan(shape, ndim, rank, mode, pl);
+    if (rc != SKT_OK) return rc;
+    SKT_REQUIRE(X_d && U_d && M_d, SKT_EINVAL, "NULL tensor / factor list / output");
+    for (int m = 0; m < ndim; ++m)
+        SKT_REQUIRE(m == mode || U_d[m] != nullptr, SKT_EINVAL, "U[%d] is NULL (only U[mode] may be)", m);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t need = (pl.nsplit > 1) ? (size_t)pl.nsplit * pl.In * rank * sizeof(double) : 0;
+    SKT_REQUIRE(ws_bytes >= need && (need == 0 || ws_d != nullptr), SKT_EWORKSPACE,
+                "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+
+    DenseParams p;
+    p.X = X_d;
+    p.ld = rank;
+    p.Kc = pl.Kc; p.In = pl.In; p.L = pl.L; p.T = pl.T;
+    p.NR = (long long)pl.L * pl.In * pl.T;
+    p.lg_bt = pl.lg_bt; p.lg_bi = pl.lg_bi; p.lg_bl = pl.lg_bl;
+    p.nit = pl.nit; p.ntt = pl.ntt; p.nred = pl.nred;
+    p.nsplit = pl.nsplit; p.chunk = pl.chunk; p.nitems = pl.nitems;
+    p.nk = (pl.Kc + BK - 1) / BK;
+    p.nw = pl.nw;
+    p.out_split_stride = (pl.nsplit > 1) ? (long long)pl.In * rank : 0;
+    double *outbase = (pl.nsplit > 1) ? (double *)ws_d : M_d;
+    const bool xalign = (((uintptr_t)X_d) & 15) == 0;
+    if (pl.mmajor) p.vecX = xalign && (pl.In % 2 == 0) && (pl.lg_bi >= 1);
+    else p.vecX = xalign && (pl.Kc % 2 == 0);
+
+    // rank > 64 runs in column passes of 64 (X is re-streamed once per pass)
+    for (int c0 = 0; c0 < rank; c0 += 64) {
+        const int ncol = std::min(64, rank - c0);
+        p.R = ncol;
+        p.Uc = U_d[pl.c] + c0;
+        p.out = outbase + c0;
+        for (int m = 0; m < pl.nw; ++m) {
+            p.w[m].U = U_d[pl.wmode[m]] + c0;
+            p.w[m].dim = pl.wdim[m]; p.w[m].div = pl.wdiv[m]; p.w[m].space = pl.wspace[m];
+        }
+        p.vecU = ((((uintptr_t)p.Uc) & 15) == 0) && (rank % 2 == 0) && (ncol % 2 == 0);
+        const int nb = (ncol + 7) / 8;
+        rc = pl.mmajor ? launch_dense_nb<true>(nb, p, pl.grid, st) : launch_dense_nb<false>(nb, p, pl.grid, st);
+        if (rc != SKT_OK) return rc;
+    }
+    if (pl.nsplit > 1) {
+        const long long n = (long long)pl.In * rank;
+        const int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * sm_count());
+        reduce_splits_kernel<<<blocks, 256, 0, st>>>((const double *)ws_d, pl.nsplit, n, M_d);
+        SKT_LAUNCH_CHECK();
+    }
+    return SKT_OK;
+}
+
+extern "C" int skt_mttkrp_dense_naive(const double *X_d, const int64_t *shape, int ndim, const double *const *U_d,
+                                      int rank, int mode, double *M_d, skt_stream stream) {
+    SKT_REQUIRE(X_d && shape && U_d && M_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= 0 && mode < ndim && rank >= 1, SKT_EINVAL, "bad ndim/mode/rank");
+    NaiveParams p;
+    p.X = X_d; p.ndim = ndim; p.R = rank; p.mode = mode;
+    long long stride = 1, nother = 1;
+    for (int m = ndim - 1; m >= 0; --m) {
+        p.shape[m] = shape[m];
+        p.stride[m] = stride;
+        stride *= shape[m];
+        p.U[m] = U_d[m];
+        if (m != mode) nother *= shape[m];
+        SKT_REQUIRE(m == mode || U_d[m] != nullptr, SKT_EINVAL, "U[%d] is NULL", m);
+    }
+    p.nother = nother;
+    const long long n = shape[mode] * rank;
+    mttkrp_dense_naive_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p, M_d);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" int skt_mttkrp_dense_host(const double *X_h, const int64_t *shape, int ndim, const double *const *U_h,
+                                     int rank, int mode, double *M_h) {
+    SKT_REQUIRE(X_h && shape && U_h && M_h, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(ndim >= 2 && ndim <= SKT_MAX_NDIM && mode >= 0 && mode < ndim && rank >= 1, SKT_EINVAL, "bad ndim/mode/rank");
+    size_t nelem = 1;
+    for (int m = 0; m < ndim; ++m) nelem *= (size_t)shape[m];
+    double *X_d = nullptr, *M_d = nullptr;
+    double *U_d[SKT_MAX_NDIM] = {nullptr};
+    void *ws = nullptr;
+    int rc = SKT_OK;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(X_d); cudaFree(M_d); cudaFree(ws);
+        for (int m = 0; m < ndim; ++m) cudaFree(U_d[m]);
+        if (st) cudaStreamDestroy(st);
+    };
+#define HOST_TRY(call)                                                             \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) { cleanup(); return cuda_fail(e__, #call, __FILE__, __LINE__); } \
+    } while (0)
+    HOST_TRY(cudaStreamCreate(&st));
+    HOST_TRY(cudaMalloc(&X_d, nelem * sizeof(double)));
+    HOST_TRY(cudaMemcpyAsync(X_d, X_h, nelem * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (int m = 0; m < ndim; ++m) {
+        if (m == mode) continue;
+        if (!U_h[m]) { cleanup(); set_error("U[%d] is NULL", m); return SKT_EINVAL; }
+        const size_t b = (size_t)shape[m] * rank * sizeof(double);
+        HOST_TRY(cudaMalloc(&U_d[m], b));
+        HOST_TRY(cudaMemcpyAsync(U_d[m], U_h[m], b, cudaMemcpyHostToDevice, st));
+    }
+    const size_t mb = (size_t)shape[mode] * rank * sizeof(double);
+    HOST_TRY(cudaMalloc(&M_d, mb));
+    const size_t wsb = skt_mttkrp_dense_workspace(shape, ndim, rank, mode);
+    HOST_TRY(cudaMalloc(&ws, wsb ? wsb : 256));
+    rc = skt_mttkrp_dense(X_d, shape, ndim, U_d, rank, mode, M_d, ws, wsb, st);
+    if (rc != SKT_OK) { cleanup(); return rc; }
+    HOST_TRY(cudaMemcpyAsync(M_h, M_d, mb, cudaMemcpyDeviceToHost, st));
+    HOST_TRY(cudaStreamSynchronize(st));
+#undef HOST_TRY
+    cleanup();
+    return SKT_OK;
+}

@@ -1,0 +1,226 @@
+"""Thin Python wrappers: device tensors in, one C-ABI call each, device tensors out.
+
+Everything here enqueues work on the current CUDA stream and returns without
+synchronising.  Argument checking beyond what the ABI does itself is left to callers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _device as dev
+from . import _lib
+
+
+def _factor_ptrs(U, skip=None):
+    return _lib.ptr_array([None if (u is None or m == skip) else u.data_ptr() for m, u in enumerate(U)])
+
+
+# ------------------------------------------------------------------ dense MTTKRP
+def mttkrp_dense(Xd, shape, U, rank, mode, out=None, naive=False):
+    """``dtensor.uttkrp`` on device tensors (dtensor.py:163-167). ``U[mode]`` may be None."""
+    lib = _lib.load()
+    shp = _lib.shape_array(shape)
+    nd = len(shape)
+    if out is None:
+        out = dev.empty((shape[mode], rank))
+    ptrs = _factor_ptrs(U, mode)
+    if naive:
+        _lib.check(lib.skt_mttkrp_dense_naive(dev.ptr(Xd), shp, nd, ptrs, rank, mode, dev.ptr(out), dev.stream_ptr()))
+        return out
+    need = lib.skt_mttkrp_dense_workspace(shp, nd, rank, mode)
+    if need == 0:      # the plan was rejected; the reason is in skt_last_error()
+        _lib.check(-2)
+    ws, wsz = dev.workspace('mttkrp').get(need)
+    _lib.check(lib.skt_mttkrp_dense(dev.ptr(Xd), shp, nd, ptrs, rank, mode, dev.ptr(out), ws, wsz, dev.stream_ptr()))
+    return out
+
+
+def mttkrp_dense_host(X, U, rank, mode):
+    """Host-buffer entry point (uploads, computes, downloads inside the C call)."""
+    lib = _lib.load()
+    dev.require_cuda()
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    Uh = [None if (u is None or m == mode) else np.ascontiguousarray(u, dtype=np.float64) for m, u in enumerate(U)]
+    M = np.empty((X.shape[mode], rank))
+    ptrs = _lib.ptr_array([None if u is None else u.ctypes.data for u in Uh])
+    _lib.check(lib.skt_mttkrp_dense_host(C.c_void_p(X.ctypes.data), _lib.shape_array(X.shape), X.ndim, ptrs,
+                                         rank, mode, C.c_void_p(M.ctypes.data)))
+    return M
+
+
+# ------------------------------------------------------------------ sparse
+class CooHandle(object):
+    """Owner of a device-resident sorted COO tensor (``skt_coo*``)."""
+
+    def __init__(self, subs, vals, shape, modes_mask=0):
+        lib = _lib.load()
+        dev.require_cuda()
+        self.shape = tuple(int(s) for s in shape)
+        self.ndim = len(self.shape)
+        self._subs = [np.ascontiguousarray(s, dtype=np.int64) for s in subs]
+        self._vals = np.ascontiguousarray(vals, dtype=np.float64)
+        self.nnz = int(self._vals.shape[0])
+        h = C.c_void_p()
+        ptrs = _lib.ptr_array([s.ctypes.data if self.nnz else None for s in self._subs])
+        _lib.check(lib.skt_coo_build_host(ptrs, C.c_void_p(self._vals.ctypes.data) if self.nnz else None,
+                                          self.nnz, _lib.shape_array(self.shape), self.ndim, modes_mask,
+                                          C.byref(h)))
+        self.h = h
+        self._subs = self._vals = None   # host copies are not retained
+
+    def device_bytes(self):
+        return int(_lib.load().skt_coo_device_bytes(self.h))
+
+    def close(self):
+        if getattr(self, 'h', None):
+            _lib.load().skt_coo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def mttkrp_coo(coo, U, rank, mode, out=None, atomic=False):
+    """``sptensor.uttkrp`` on device factors (sptensor.py:216-229)."""
+    lib = _lib.load()
+    if out is None:
+        out = dev.empty((coo.shape[mode], rank))
+    ptrs = _factor_ptrs(U, mode)
+    if atomic:
+        _lib.check(lib.skt_mttkrp_coo_atomic(coo.h, ptrs, rank, mode, dev.ptr(out), dev.stream_ptr()))
+        return out
+    need = lib.skt_mttkrp_coo_workspace(coo.h, rank, mode)
+    ws, wsz = dev.workspace('mttkrp').get(need)
+    _lib.check(lib.skt_mttkrp_coo(coo.h, ptrs, rank, mode, dev.ptr(out), ws, wsz, dev.stream_ptr()))
+    return out
+
+
+def coo_innerprod(coo, U, lam, rank):
+    lib = _lib.load()
+    out = dev.empty((1,))
+    ws, wsz = dev.workspace('reduce').get(lib.skt_coo_innerprod_workspace(coo.h, rank))
+    _lib.check(lib.skt_coo_innerprod(coo.h, _factor_ptrs(U), dev.ptr(lam), rank, dev.ptr(out), ws, wsz,
+                                     dev.stream_ptr()))
+    return out
+
+
+def coo_sumsq(coo):
+    lib = _lib.load()
+    out = dev.empty((1,))
+    ws, wsz = dev.workspace('reduce').get(lib.skt_sumsq_workspace(coo.nnz))
+    _lib.check(lib.skt_coo_sumsq(coo.h, dev.ptr(out), ws, wsz, dev.stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------ reductions / normal equations
+def sumsq(x):
+    lib = _lib.load()
+    out = dev.empty((1,))
+    n = x.numel()
+    ws, wsz = dev.workspace('reduce').get(lib.skt_sumsq_workspace(n))
+    _lib.check(lib.skt_sumsq(dev.ptr(x), n, dev.ptr(out), ws, wsz, dev.stream_ptr()))
+    return out
+
+
+def weighted_dot(U, M, lam=None):
+    """``sum_i sum_r lam_r U[i,r] M[i,r]`` -> 1-element device tensor."""
+    lib = _lib.load()
+    rows, R = U.shape
+    out = dev.empty((1,))
+    ws, wsz = dev.workspace('reduce').get(lib.skt_sumsq_workspace(rows * R))
+    _lib.check(lib.skt_weighted_dot(dev.ptr(U), dev.ptr(M), dev.ptr(lam), rows, R, dev.ptr(out), ws, wsz,
+                                    dev.stream_ptr()))
+    return out
+
+
+def gram(U, out=None):
+    lib = _lib.load()
+    rows, R = U.shape
+    if out is None:
+        out = dev.empty((R, R))
+    ws, wsz = dev.workspace('pass').get(lib.skt_gram_workspace(rows, R))
+    _lib.check(lib.skt_gram(dev.ptr(U), rows, R, dev.ptr(out), ws, wsz, dev.stream_ptr()))
+    return out
+
+
+def hadamard_pinv(G, mode, P=None, info=None):
+    """``pinv(hadamard_{m != mode} G[m])`` (cp.py:144-147); ``G`` is (ndim, R, R)."""
+    lib = _lib.load()
+    nd, R = int(G.shape[0]), int(G.shape[1])
+    if P is None:
+        P = dev.empty((R, R))
+    if info is None:
+        info = dev.empty((1,), np.int32)
+    _lib.check(lib.skt_hadamard_pinv(dev.ptr(G), nd, R, mode, dev.ptr(P), dev.ptr(info), dev.stream_ptr()))
+    return P, info
+
+
+def solve_stats(M, P, first_iter, Unew=None, colstat=None):
+    lib = _lib.load()
+    rows, R = M.shape
+    if Unew is None:
+        Unew = dev.empty((rows, R))
+    if colstat is None:
+        colstat = dev.empty((R,))
+    ws, wsz = dev.workspace('pass').get(lib.skt_solve_stats_workspace(rows, R))
+    _lib.check(lib.skt_solve_stats(dev.ptr(M), dev.ptr(P), rows, R, 1 if first_iter else 0, dev.ptr(Unew),
+                                   dev.ptr(colstat), ws, wsz, dev.stream_ptr()))
+    return Unew, colstat
+
+
+def normalise_gram(U, colstat, first_iter, lam=None, G=None, Mip=None, ip=None):
+    lib = _lib.load()
+    rows, R = U.shape
+    if lam is None:
+        lam = dev.empty((R,))
+    if G is None:
+        G = dev.empty((R, R))
+    if Mip is not None and ip is None:
+        ip = dev.empty((1,))
+    ws, wsz = dev.workspace('pass').get(lib.skt_normalise_gram_workspace(rows, R))
+    _lib.check(lib.skt_normalise_gram(dev.ptr(U), dev.ptr(colstat), rows, R, 1 if first_iter else 0, dev.ptr(lam),
+                                      dev.ptr(G), dev.ptr(Mip), dev.ptr(ip) if Mip is not None else None,
+                                      ws, wsz, dev.stream_ptr()))
+    return lam, G, ip
+
+
+def cp_fit(G, lam, ip, normX2, out=None):
+    lib = _lib.load()
+    if out is None:
+        out = dev.empty((2,))
+    _lib.check(lib.skt_cp_fit(dev.ptr(G), int(G.shape[0]), int(G.shape[1]), dev.ptr(lam), dev.ptr(ip),
+                              dev.ptr(normX2), dev.ptr(out), dev.stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------ HOOI pieces
+def ttm_dense(Xd, shape, V, mode, transp):
+    lib = _lib.load()
+    p = int(V.shape[1] if transp else V.shape[0])
+    oshape = list(shape)
+    oshape[mode] = p
+    Y = dev.empty(oshape)
+    _lib.check(lib.skt_ttm_dense(dev.ptr(Xd), _lib.shape_array(shape), len(shape), dev.ptr(V), p, mode,
+                                 1 if transp else 0, dev.ptr(Y), dev.stream_ptr()))
+    return Y, tuple(oshape)
+
+
+def unfold_gram(Xd, shape, mode):
+    lib = _lib.load()
+    n = int(shape[mode])
+    G = dev.empty((n, n))
+    shp = _lib.shape_array(shape)
+    ws, wsz = dev.workspace('reduce').get(lib.skt_unfold_gram_workspace(shp, len(shape), mode))
+    _lib.check(lib.skt_unfold_gram(dev.ptr(Xd), shp, len(shape), mode, dev.ptr(G), ws, wsz, dev.stream_ptr()))
+    return G
+
+
+def probe_fp64_peaks():
+    lib = _lib.load()
+    dev.require_cuda()
+    a, b = C.c_double(), C.c_double()
+    _lib.check(lib.skt_probe_fp64_peaks(C.byref(a), C.byref(b)))
+    return a.value, b.value

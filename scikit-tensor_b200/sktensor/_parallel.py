@@ -1,0 +1,300 @@
+"""The CP-ALS sweep engine: device-resident state, kernel choreography, and mode sharding.
+
+One process drives one GPU.  With ``torch.distributed`` initialised (world size > 1) the
+tensor is cut along its largest mode ``s`` into contiguous index ranges -- equal rows for
+dense tensors, equal non-zeros for sparse ones -- and each rank keeps its slab, its rows
+of ``U_s`` and a replica of every other factor:
+
+  * mode ``s``: the MTTKRP output rows are local; only the R-vector of column statistics
+    and the R x R Gram of the updated rows are all-reduced;
+  * mode ``n != s``: every rank produces a full-height partial MTTKRP from its slab, the
+    partials are summed with one all-reduce, and the (small, replicated) solve is repeated
+    on every rank, which leaves the replicas bitwise identical.
+
+The collectives are issued through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU
+tests); nothing else in this file touches PyTorch.  The numerical kernels are reached
+through a backend object so that the CPU test-suite can drive the same choreography with a
+NumPy stand-in (``tests/fake_backend.py``); the shipped default is the CUDA library and
+there is no automatic fallback.
+"""
+import numpy as np
+
+from .dtensor import dtensor
+from .sptensor import sptensor
+
+
+# ---------------------------------------------------------------------------------------------
+# partitioning (pure host logic)
+# ---------------------------------------------------------------------------------------------
+def split_rows(n, world):
+    """``world + 1`` offsets cutting ``range(n)`` into contiguous, nearly equal ranges."""
+    base, extra = divmod(int(n), int(world))
+    sizes = [base + (1 if r < extra else 0) for r in range(world)]
+    return np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+
+
+def split_nnz(idx, dim, world):
+    """Offsets on ``range(dim)`` such that each range holds about ``nnz / world`` entries of ``idx``.
+
+    Power-law tensors put most non-zeros on few rows: equal-row cuts would leave one rank
+    with nearly all the work, so the cuts follow the cumulative non-zero count instead.
+    Cuts never split a row (a row's non-zeros stay on one rank).
+    """
+    counts = np.bincount(np.asarray(idx, dtype=np.int64), minlength=int(dim))
+    cum = np.cumsum(counts)
+    total = int(cum[-1]) if len(cum) else 0
+    offs = [0]
+    for r in range(1, world):
+        target = total * r / float(world)
+        cut = int(np.searchsorted(cum, target, side='left')) + 1 if total else 0
+        cut = min(max(cut, offs[-1]), int(dim))
+        offs.append(cut)
+    offs.append(int(dim))
+    return np.array(offs, dtype=np.int64)
+
+
+def shard_mode(shape):
+    """The mode to cut: the largest one (first on ties)."""
+    return int(np.argmax(np.asarray(shape)))
+
+
+class LocalShard(object):
+    """A rank's slab of a tensor that is already partitioned along ``mode``.
+
+    ``tensor`` is the local ``dtensor`` / ``sptensor`` (sparse subscripts along ``mode`` are
+    LOCAL, i.e. already shifted by ``-offset``); ``global_shape`` is the full shape and
+    ``offsets`` the ``world + 1`` cut points along ``mode``.
+    """
+
+    def __init__(self, tensor, mode, global_shape, offsets):
+        self.tensor = tensor
+        self.mode = int(mode)
+        self.shape = tuple(int(s) for s in global_shape)
+        self.ndim = len(self.shape)
+        self.offsets = np.asarray(offsets, dtype=np.int64)
+
+
+# ---------------------------------------------------------------------------------------------
+# backends
+# ---------------------------------------------------------------------------------------------
+class CudaBackend(object):
+    """The product backend: libsktensor_b200 kernels on the current CUDA device."""
+
+    def __init__(self):
+        from . import _device as dev
+        from . import _kernels as K
+        dev.require_cuda()
+        self.dev, self.K = dev, K
+
+    # memory
+    def to_device(self, a): return self.dev.to_device(a)
+    def to_host(self, x): return self.dev.to_host(x)
+    def empty(self, shape, dtype=np.float64): return self.dev.empty(shape, dtype)
+    def zeros(self, shape, dtype=np.float64): return self.dev.zeros(shape, dtype)
+    # tensors
+    def upload_dense(self, X): return self.dev.to_device(np.asarray(X))
+    def upload_coo(self, subs, vals, shape): return self.K.CooHandle(subs, vals, shape)
+    # kernels
+    def mttkrp_dense(self, Xd, shape, U, R, n, out): return self.K.mttkrp_dense(Xd, shape, U, R, n, out=out)
+    def mttkrp_coo(self, coo, U, R, n, out): return self.K.mttkrp_coo(coo, U, R, n, out=out)
+    def sumsq(self, x): return self.K.sumsq(x)
+    def coo_sumsq(self, coo): return self.K.coo_sumsq(coo)
+    def gram(self, U, out): return self.K.gram(U, out=out)
+    def hadamard_pinv(self, G, n, P, info): return self.K.hadamard_pinv(G, n, P=P, info=info)
+    def solve_stats(self, M, P, first, Unew, colstat): return self.K.solve_stats(M, P, first, Unew=Unew, colstat=colstat)
+    def normalise_gram(self, U, colstat, first, lam, G, Mip, ip):
+        return self.K.normalise_gram(U, colstat, first, lam=lam, G=G, Mip=Mip, ip=ip)
+    def cp_fit(self, G, lam, ip, normX2, out): return self.K.cp_fit(G, lam, ip, normX2, out=out)
+
+
+_backend_factory = CudaBackend
+
+
+def set_backend_factory(factory):
+    """Replace the kernel backend constructor (test hook; the default is ``CudaBackend``)."""
+    global _backend_factory
+    _backend_factory = factory if factory is not None else CudaBackend
+
+
+class _Comm(object):
+    """torch.distributed wrapper; a no-op object when running on a single rank."""
+
+    def __init__(self):
+        self.rank, self.world, self.dist = 0, 1, None
+        try:
+            import torch.distributed as dist
+        except Exception:      # torch missing is caught later by the backend
+            return
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self.dist = dist
+            self.rank = dist.get_rank()
+            self.world = dist.get_world_size()
+
+    @property
+    def active(self):
+        return self.dist is not None
+
+    def allreduce_sum(self, x):
+        if self.active:
+            self.dist.all_reduce(x, op=self.dist.ReduceOp.SUM)
+
+    def allreduce_max(self, x):
+        if self.active:
+            self.dist.all_reduce(x, op=self.dist.ReduceOp.MAX)
+
+    def allgather_rows(self, local, offsets, backend):
+        """Concatenate the ranks' row blocks (sizes from ``offsets``) into one host array."""
+        if not self.active:
+            return backend.to_host(local)
+        sizes = np.diff(offsets)
+        maxr = int(sizes.max())
+        pad = backend.zeros((maxr, local.shape[1]))
+        pad[:local.shape[0]] = local
+        bufs = [backend.empty((maxr, local.shape[1])) for _ in range(self.world)]
+        self.dist.all_gather(bufs, pad)
+        return np.concatenate([backend.to_host(b)[:int(sizes[r])] for r, b in enumerate(bufs)], axis=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# the engine
+# ---------------------------------------------------------------------------------------------
+class CpAlsEngine(object):
+    """Device-resident CP-ALS state; ``sweep`` runs one iteration of cp.py:142-159."""
+
+    def __init__(self, X, rank, U, backend=None, comm=None):
+        self.be = backend if backend is not None else _backend_factory()
+        self.comm = comm if comm is not None else _Comm()
+        be, comm = self.be, self.comm
+        self.R = R = int(rank)
+        if R < 1:
+            raise ValueError('rank must be a positive integer')
+
+        # ---- which slab is ours
+        if isinstance(X, LocalShard):
+            self.shape, self.s, self.offsets = X.shape, X.mode, X.offsets
+            local = X.tensor
+        else:
+            self.shape = tuple(int(d) for d in X.shape)
+            self.s = shard_mode(self.shape) if comm.active else -1
+            local = X
+            if comm.active:
+                local, self.offsets = self._cut(X, self.s, comm)
+            else:
+                self.offsets = None
+        self.N = N = len(self.shape)
+        self.sparse = isinstance(local, sptensor)
+        if not self.sparse and not isinstance(local, dtensor):
+            raise ValueError('cp_als needs a dtensor or sptensor (got %s)' % type(local))
+        self.lshape = tuple(int(d) for d in local.shape)
+        lo = int(self.offsets[comm.rank]) if comm.active else 0
+        hi = int(self.offsets[comm.rank + 1]) if comm.active else 0
+        self.row_lo, self.row_hi = lo, hi
+
+        # ---- tensor to the device, ||X||^2
+        if self.sparse:
+            self.Xd = be.upload_coo([np.asarray(s_) for s_ in local.subs], local.vals, self.lshape)
+            self.normX2 = be.coo_sumsq(self.Xd) if len(local.vals) else be.zeros((1,))
+        else:
+            self.Xd = be.upload_dense(local)
+            self.normX2 = be.sumsq(self.Xd)
+        comm.allreduce_sum(self.normX2)
+
+        # ---- factors (local rows for the sharded mode), Grams, scratch
+        self.Ud = [None] * N
+        self.G = be.zeros((N, R, R))
+        for m in range(N):
+            if U[m] is None:
+                continue
+            Um = np.asarray(U[m], dtype=np.float64)
+            if Um.ndim != 2 or Um.shape != (self.shape[m], R):
+                raise ValueError('Dimension mismatch of factor matrices')
+            if m == self.s:
+                Um = Um[lo:hi]
+            self.Ud[m] = be.to_device(Um)
+            be.gram(self.Ud[m], self.G[m])
+            if m == self.s:
+                comm.allreduce_sum(self.G[m])
+        for m in range(N):
+            if self.Ud[m] is None:
+                self.Ud[m] = be.zeros((self.lshape[m], R))
+        self.missing = [m for m in range(N) if U[m] is None]
+        self.M = [be.empty((self.lshape[m], R)) for m in range(N)]
+        self.P = be.empty((R, R))
+        self.info = be.zeros((N,), np.int32)
+        self.colstat = be.empty((R,))
+        self.lam = be.empty((R,))
+        self.ip = be.zeros((1,))
+        self.fitout = be.zeros((2,))
+
+    @staticmethod
+    def _cut(X, s, comm):
+        """Slice a full tensor down to this rank's slab along mode ``s``."""
+        if isinstance(X, sptensor):
+            offs = split_nnz(X.subs[s], X.shape[s], comm.world)
+            lo, hi = int(offs[comm.rank]), int(offs[comm.rank + 1])
+            idx = np.asarray(X.subs[s])
+            keep = (idx >= lo) & (idx < hi)
+            subs = tuple((np.asarray(sm)[keep] - (lo if m == s else 0)).astype(np.int64)
+                         for m, sm in enumerate(X.subs))
+            shape = list(X.shape)
+            shape[s] = hi - lo
+            return sptensor(subs, np.asarray(X.vals)[keep], shape=shape), offs
+        offs = split_rows(X.shape[s], comm.world)
+        lo, hi = int(offs[comm.rank]), int(offs[comm.rank + 1])
+        sl = [slice(None)] * X.ndim
+        sl[s] = slice(lo, hi)
+        return dtensor(np.ascontiguousarray(np.asarray(X)[tuple(sl)])), offs
+
+    # ------------------------------------------------------------------ one ALS iteration
+    def mttkrp(self, n):
+        """Local MTTKRP for mode ``n`` into ``self.M[n]`` (partial sums reduced across ranks)."""
+        be = self.be
+        # the reference ignores U[n]; on the first sweep the not-yet-computed factors are never read
+        if self.sparse:
+            be.mttkrp_coo(self.Xd, self.Ud, self.R, n, self.M[n])
+        else:
+            be.mttkrp_dense(self.Xd, self.lshape, self.Ud, self.R, n, self.M[n])
+        if self.comm.active and n != self.s:
+            self.comm.allreduce_sum(self.M[n])
+        return self.M[n]
+
+    def sweep(self, first_iter, want_fit=True):
+        be, comm, N = self.be, self.comm, self.N
+        for n in range(N):
+            M = self.mttkrp(n)
+            be.hadamard_pinv(self.G, n, self.P, self.info[n:n + 1])
+            be.solve_stats(M, self.P, first_iter, self.Ud[n], self.colstat)
+            if comm.active and n == self.s:
+                if first_iter:
+                    comm.allreduce_sum(self.colstat)
+                else:
+                    comm.allreduce_max(self.colstat)
+            last = (n == N - 1) and want_fit
+            be.normalise_gram(self.Ud[n], self.colstat, first_iter, self.lam, self.G[n],
+                              M if last else None, self.ip if last else None)
+            if comm.active and n == self.s:
+                comm.allreduce_sum(self.G[n])
+                if last:
+                    comm.allreduce_sum(self.ip)
+        if want_fit:
+            be.cp_fit(self.G, self.lam, self.ip, self.normX2, self.fitout)
+
+    def check_status(self):
+        info = self.be.to_host(self.info)
+        if (info < 0).any():
+            # scipy.linalg.pinv raises exactly this on a non-finite Gram product (cp.py:147)
+            raise ValueError('array must not contain infs or NaNs')
+
+    def read_fit(self):
+        fit = float(self.be.to_host(self.fitout)[0])
+        self.check_status()
+        return fit
+
+    def download(self, U):
+        """Write the factors into the caller's list (in place) and return lambda."""
+        for m in range(self.N):
+            if self.comm.active and m == self.s:
+                U[m] = self.comm.allgather_rows(self.Ud[m], self.offsets, self.be)
+            else:
+                U[m] = self.be.to_host(self.Ud[m])
+        return self.be.to_host(self.lam)

@@ -1,0 +1,50 @@
+"""Worker for tests/test_distributed_gloo.py: one rank of a world_size-N gloo job on CPU."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, 'scikit-tensor_b200'), ROOT, os.path.join(ROOT, 'tests')):
+    sys.path.insert(0, p)
+
+import torch.distributed as dist  # noqa: E402
+
+from fake_backend import NumpyBackend  # noqa: E402
+from sktensor import _parallel, cp_als, dtensor, sptensor  # noqa: E402
+from sktensor.sptensor import fromarray  # noqa: E402
+
+
+def main():
+    out_path = sys.argv[1]
+    dist.init_process_group('gloo')
+    rank = dist.get_rank()
+    _parallel.set_backend_factory(NumpyBackend)
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden.npz'))
+    res = {}
+
+    def run(key, X, R, seed, **kw):
+        np.random.seed(seed)
+        P, fit, itr, _ = cp_als(X, R, **kw)
+        res[key] = {'fit': float(fit), 'itr': int(itr), 'lmbda': np.asarray(P.lmbda).tolist(),
+                    'U': [np.asarray(u).tolist() for u in P.U]}
+
+    X1 = g['cfg1_X']
+    run('cp_cfg1_s42', dtensor(X1), 3, 42, init='random')                       # sharded on mode 1 (11)
+    run('cp_cfg1_s42_it5', dtensor(X1), 3, 42, init='random', max_iter=5, conv=0)
+    run('cp_kat3_s42', fromarray(X1 * (X1 > 0.7)), 3, 42, init='random')        # sparse
+    run('cp_d4_s3', dtensor(g['cp4_X']), 4, 3, init='random', max_iter=30)      # 4-way, sharded on the last mode
+    subs = tuple(g['cpsp_sub%d' % m] for m in range(3))
+    run('cp_sp_s1', sptensor(subs, g['cpsp_vals'], shape=(60, 50, 40)), 5, 1, init='random', max_iter=25)
+    np.random.seed(42)
+    _, fit, itr, _ = cp_als(dtensor(X1), 3, init='random', fit_method=None, max_iter=4)
+    res['nofit'] = {'fit': float(fit), 'itr': int(itr)}
+    with open('%s.%d' % (out_path, rank), 'w') as f:
+        json.dump(res, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

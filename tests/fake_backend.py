@@ -1,0 +1,102 @@
+"""NumPy stand-in for the CUDA kernel backend -- TEST DOUBLE ONLY.
+
+It lets the CPU test-suite drive ``sktensor._parallel.CpAlsEngine`` (sharding, collective
+placement, status handling) under ``gloo`` with world_size > 1, where no GPU exists.  Storage
+is CPU ``torch`` tensors so ``torch.distributed`` can reduce them; arithmetic comes from the
+oracle.  Nothing in the shipped package imports this file.
+"""
+import numpy as np
+import torch
+from scipy.linalg import pinv
+
+from oracle import sktensor_oracle as orc
+
+
+class NumpyBackend(object):
+    def to_device(self, a):
+        return torch.from_numpy(np.array(a, dtype=np.float64, order='C', copy=True))
+
+    def to_host(self, x):
+        return x.detach().numpy().copy()
+
+    def empty(self, shape, dtype=np.float64):
+        return torch.zeros(tuple(int(s) for s in shape), dtype=getattr(torch, np.dtype(dtype).name))
+
+    zeros = empty
+
+    def upload_dense(self, X):
+        return np.array(X, dtype=np.float64, order='C', copy=True)
+
+    def upload_coo(self, subs, vals, shape):
+        return (tuple(np.asarray(s, dtype=np.int64) for s in subs), np.asarray(vals, dtype=np.float64), tuple(shape))
+
+    @staticmethod
+    def _np(U):
+        return [None if u is None else u.numpy() for u in U]
+
+    def mttkrp_dense(self, Xd, shape, U, R, n, out):
+        Un = self._np(U)
+        out.copy_(torch.from_numpy(orc.mttkrp_dense(Xd, Un, n)))
+        return out
+
+    def mttkrp_coo(self, coo, U, R, n, out):
+        subs, vals, shape = coo
+        out.copy_(torch.from_numpy(orc.mttkrp_coo(subs, vals, shape, self._np(U), n)))
+        return out
+
+    def sumsq(self, x):
+        return torch.tensor([float((np.asarray(x) ** 2).sum())], dtype=torch.float64)
+
+    def coo_sumsq(self, coo):
+        return torch.tensor([float((coo[1] ** 2).sum())], dtype=torch.float64)
+
+    def gram(self, U, out):
+        u = U.numpy()
+        out.copy_(torch.from_numpy(u.T.dot(u)))
+        return out
+
+    def hadamard_pinv(self, G, n, P, info):
+        g = G.numpy()
+        Y = np.ones(g.shape[1:])
+        for m in range(g.shape[0]):
+            if m != n:
+                Y = Y * g[m]
+        if not np.isfinite(Y).all():
+            info[0] = -1
+            P.fill_(float('nan'))
+        else:
+            P.copy_(torch.from_numpy(pinv(Y)))
+            info[0] = int(np.linalg.matrix_rank(Y))
+        return P, info
+
+    def solve_stats(self, M, P, first, Unew, colstat):
+        u = M.numpy().dot(P.numpy())
+        Unew.copy_(torch.from_numpy(u))
+        if u.shape[0] == 0:
+            stat = np.zeros(u.shape[1]) if first else np.full(u.shape[1], -np.finfo(float).max)
+        else:
+            stat = (u ** 2).sum(axis=0) if first else u.max(axis=0)
+        colstat.copy_(torch.from_numpy(stat))
+        return Unew, colstat
+
+    def normalise_gram(self, U, colstat, first, lam, G, Mip, ip):
+        c = colstat.numpy()
+        l = np.sqrt(c) if first else np.where(c < 1, 1.0, c)
+        lam.copy_(torch.from_numpy(l))
+        u = U.numpy() / l
+        U.copy_(torch.from_numpy(u))
+        G.copy_(torch.from_numpy(u.T.dot(u)))
+        if Mip is not None:
+            ip[0] = float((l * u * Mip.numpy()).sum())
+        return lam, G, ip
+
+    def cp_fit(self, G, lam, ip, normX2, out):
+        l = lam.numpy()
+        coef = np.outer(l, l)
+        for g in G.numpy():
+            coef = coef * g
+        normP2 = coef.sum()
+        nx2 = float(normX2[0])
+        out[0] = 1.0 - (nx2 + normP2 - 2.0 * float(ip[0])) / nx2
+        out[1] = normP2
+        return out

@@ -1,0 +1,68 @@
+"""The C-ABI library loads on a CPU-only box and exports exactly what include/sktensor_b200.h
+declares and what the ctypes binding expects (no compute calls here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, 'include', 'sktensor_b200.h')
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'SKT_API[^;(]*?\b(skt_\w+)\s*\(', src)))
+
+
+def test_header_declares_the_path():
+    names = declared_symbols()
+    for must in ('skt_mttkrp_dense', 'skt_mttkrp_coo', 'skt_coo_build_host', 'skt_hadamard_pinv',
+                 'skt_solve_stats', 'skt_normalise_gram', 'skt_cp_fit', 'skt_ttm_dense', 'skt_gram',
+                 'skt_mttkrp_dense_host', 'skt_last_error'):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from sktensor import _lib
+    assert os.path.exists(_lib.LIB_PATH), 'build the library first: make -C scikit-tensor_b200'
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r' T (skt_\w+)', out))
+    assert exported == set(declared_symbols())
+
+
+def test_ctypes_prototypes_match_header():
+    from sktensor import _lib
+    assert sorted(_lib.PROTOTYPES) == declared_symbols()
+    lib = _lib.load()
+    assert lib.skt_version() >= 100
+    # argument counts agree with the header
+    src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _lib.PROTOTYPES.items():
+        m = re.search(r'\b%s\s*\(([^;]*?)\)\s*;' % name, src, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ('', 'void') else params.count(',') + 1
+        assert n == len(args), (name, n, len(args))
+
+
+def test_argument_errors_without_a_gpu():
+    """Pure argument validation returns SKT_E* codes and a message; nothing touches the device."""
+    from sktensor import _lib
+    lib = _lib.load()
+    shp = _lib.shape_array((4, 5, 6))
+    assert lib.skt_mttkrp_dense_workspace(shp, 3, 8, 7) == 0          # mode out of range
+    assert b'mode' in lib.skt_last_error()
+    assert lib.skt_mttkrp_dense_workspace(shp, 3, 8, 1) >= 256
+    rc = lib.skt_mttkrp_dense(None, shp, 3, None, 8, 0, None, None, 0, None)
+    assert rc == -1
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+    assert lib.skt_gram(None, 10, 4, None, None, 0, None) == -1
+    assert lib.skt_hadamard_pinv(None, 3, 200, 0, None, None, None) == -1

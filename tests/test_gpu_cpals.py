@@ -1,0 +1,253 @@
+"""GPU parity tests for the normal-equation kernels and the cp_als / tucker_hooi drivers,
+against golden vectors of the unmodified reference (fit within north_star's 1e-6, itr exact)."""
+import numpy as np
+import pytest
+from scipy.linalg import pinv
+
+from conftest import relerr
+from oracle import sktensor_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def K():
+    from sktensor import _device as dev, _kernels as K
+    dev.require_cuda()
+    return K
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from sktensor import _device as dev
+    return dev
+
+
+@pytest.mark.parametrize('rows,R', [(1, 1), (10, 3), (64, 16), (65, 17), (1000, 32), (5000, 33), (3000, 64), (100000, 16)])
+def test_gram_and_sumsq(K, dev, rows, R):
+    rng = np.random.RandomState(rows + R)
+    U = rng.rand(rows, R) - 0.4
+    G = dev.to_host(K.gram(dev.to_device(U)))
+    assert relerr(G, U.T.dot(U)) < 1e-13
+    assert abs(dev.to_host(K.sumsq(dev.to_device(U)))[0] - (U ** 2).sum()) < 1e-12 * (U ** 2).sum()
+
+
+def test_hadamard_pinv_matches_scipy(K, dev, golden):
+    for name in golden.j['solve_cases']:
+        F = [golden['slv_%s_F0' % name], golden['slv_%s_F1' % name]]
+        R = F[0].shape[1]
+        G = np.zeros((3, R, R))
+        G[1], G[2] = F[0].T.dot(F[0]), F[1].T.dot(F[1])
+        Y = golden['slv_%s_Y' % name]
+        P, info = K.hadamard_pinv(dev.to_device(G), 0)
+        P, info = dev.to_host(P), int(dev.to_host(info)[0])
+        ref = pinv(Y)
+        assert info == np.linalg.matrix_rank(Y, tol=R * np.finfo(float).eps * np.linalg.norm(Y, 2)), name
+        # compare through the product the path needs: M pinv(Y)
+        M = golden['slv_%s_M' % name]
+        assert relerr(M.dot(P), golden['slv_%s_Unew' % name]) < 1e-9, name
+        assert relerr(P, ref) < 1e-8, name
+    # non-finite Gram -> status -1 (the reference raises ValueError in pinv)
+    G = np.ones((3, 4, 4))
+    G[1, 2, 2] = np.nan
+    _, info = K.hadamard_pinv(dev.to_device(G), 0)
+    assert int(dev.to_host(info)[0]) == -1
+    # all-zero Gram -> zero pseudo-inverse, rank 0
+    P, info = K.hadamard_pinv(dev.to_device(np.zeros((3, 5, 5))), 1)
+    assert int(dev.to_host(info)[0]) == 0 and (dev.to_host(P) == 0).all()
+
+
+@pytest.mark.parametrize('R', [2, 7, 16, 32, 48, 64])
+def test_hadamard_pinv_random_conditioning(K, dev, R):
+    rng = np.random.RandomState(R)
+    for cond in (1e2, 1e8, 1e13):
+        Q, _ = np.linalg.qr(rng.randn(R, R))
+        s = np.logspace(0, -np.log10(cond), R)
+        Y = (Q * s).dot(Q.T)
+        Y = (Y + Y.T) / 2
+        G = np.ones((2, R, R))
+        G[1] = Y
+        P, info = K.hadamard_pinv(dev.to_device(G), 0)
+        P = dev.to_host(P)
+        ref = pinv(Y)
+        assert relerr(P, ref) < 1e-6 * max(1.0, cond * 1e-10), (R, cond)
+        assert relerr(Y.dot(P).dot(Y), Y) < 1e-10
+
+
+def test_solve_normalise_golden(K, dev, golden):
+    for name in golden.j['solve_cases']:
+        M, Y = golden['slv_%s_M' % name], golden['slv_%s_Y' % name]
+        R = M.shape[1]
+        F = [golden['slv_%s_F0' % name], golden['slv_%s_F1' % name]]
+        G = np.zeros((3, R, R))
+        G[1], G[2] = F[0].T.dot(F[0]), F[1].T.dot(F[1])
+        P, _ = K.hadamard_pinv(dev.to_device(G), 0)
+        for itr in (0, 1):
+            Md = dev.to_device(M)
+            Unew, colstat = K.solve_stats(Md, P, itr == 0)
+            lam, Gn, ip = K.normalise_gram(Unew, colstat, itr == 0, Mip=Md)
+            U = dev.to_host(Unew)
+            assert relerr(U, golden['slv_%s_U%d' % (name, itr)]) < 1e-8, (name, itr)
+            assert relerr(dev.to_host(lam), golden['slv_%s_lam%d' % (name, itr)]) < 1e-9, (name, itr)
+            assert relerr(dev.to_host(Gn), U.T.dot(U)) < 1e-12
+            l = dev.to_host(lam)
+            assert abs(dev.to_host(ip)[0] - (l * U * M).sum()) < 1e-10 * abs((l * U * M).sum())
+
+
+def test_solve_tall_factor(K, dev):
+    rng = np.random.RandomState(5)
+    M = rng.rand(100003, 16) * 3 - 1
+    P = rng.rand(16, 16)
+    for first in (True, False):
+        Unew, colstat = K.solve_stats(dev.to_device(M), dev.to_device(P), first)
+        ref = M.dot(P)
+        assert relerr(dev.to_host(Unew), ref) < 1e-13
+        stat = (ref ** 2).sum(0) if first else ref.max(0)
+        assert relerr(dev.to_host(colstat), stat) < 1e-12
+
+
+def test_kruskal_norm_innerprod(K, dev, golden):
+    from sktensor import dtensor, ktensor
+    from sktensor.sptensor import fromarray
+    P = ktensor(golden.factors('kt', 3), golden['kt_lmbda'])
+    assert abs(P.norm() - golden.j['kt_norm']) < 1e-11
+    assert abs(P.innerprod(dtensor(golden['kt_X'])) - golden.j['kt_innerprod_dense']) < 1e-10
+    assert abs(P.innerprod(fromarray(golden['kt_Xs'])) - golden.j['kt_innerprod_sparse']) < 1e-10
+    assert relerr(P.toarray(), golden['kt_toarray']) < 1e-14
+
+
+def _check_cp(golden, key, P, fit, itr, tol=1e-7):
+    assert itr == golden.j[key]['itr'], (key, itr)
+    assert abs(float(fit) - golden.j[key]['fit']) < 1e-6, key          # north_star tolerance
+    assert abs(float(fit) - golden.j[key]['fit']) < 1e-9, key          # what we actually reach
+    assert relerr(P.lmbda, golden['%s_lmbda' % key]) < tol
+    for m in range(P.ndim):
+        assert relerr(P.U[m], golden['%s_U%d' % (key, m)]) < tol, (key, m)
+
+
+def test_cp_als_cfg1_golden(golden):
+    """BASELINE config 1: dense 10x11x8, rank 3, random init (KAT-2)."""
+    from sktensor import cp_als, dtensor, ktensor
+    X = golden['cfg1_X']
+    for seed in (42, 7, 0):
+        np.random.seed(seed)
+        P, fit, itr, ex = cp_als(dtensor(X), 3, init='random')
+        assert isinstance(P, ktensor) and len(ex) == itr + 1
+        _check_cp(golden, 'cp_cfg1_s%d' % seed, P, fit, itr)
+    np.random.seed(42)
+    _check_cp(golden, 'cp_cfg1_s42_it5', *cp_als(dtensor(X), 3, init='random', max_iter=5, conv=0)[:3])
+    np.random.seed(42)
+    _check_cp(golden, 'cp_cfg1_s42_F', *cp_als(dtensor(np.asfortranarray(X)), 3, init='random')[:3])
+    np.random.seed(42)
+    P, fit, itr, _ = cp_als(dtensor(X), 3, init='random', fit_method=None, max_iter=10)
+    assert fit == 9 and itr == 9
+    _check_cp(golden, 'cp_cfg1_nvecs', *cp_als(dtensor(X), 3)[:3], tol=1e-6)      # default init='nvecs'
+    with pytest.raises(ValueError, match='Unknown keywords'):
+        cp_als(dtensor(X), 3, maxiter=5)
+
+
+def test_cp_als_trace_matches_reference(golden):
+    from sktensor import cp_als, dtensor
+    X = golden['cfg1_X']
+    ref = golden.j['cp_cfg1_s42_trace']
+    for k in (1, 2, 3, 10, 22):
+        np.random.seed(42)
+        _, fit, itr, _ = cp_als(dtensor(X), 3, init='random', max_iter=k, conv=0)
+        assert itr == k - 1 and abs(fit - ref[k - 1]) < 1e-10
+
+
+def test_cp_als_sparse_and_singular(golden):
+    from sktensor import cp_als, dtensor, sptensor
+    from sktensor.sptensor import fromarray
+    X = golden['cfg1_X']
+    S = fromarray(X * (X > 0.7))
+    assert abs(S.norm() - golden.j['kat3_norm']) < 1e-12
+    np.random.seed(42)
+    _check_cp(golden, 'cp_kat3_s42', *cp_als(S, 3, init='random')[:3])
+    np.random.seed(42)
+    _check_cp(golden, 'cp_kat3_dense_s42', *cp_als(dtensor(S.toarray()), 3, init='random')[:3])
+    # KAT-5: singular normal equations, list init mutated in place
+    init = [None, golden['kat5_init1'].copy(), golden['kat5_init2'].copy()]
+    P, fit, itr, _ = cp_als(dtensor(X), 3, init=init, max_iter=50)
+    _check_cp(golden, 'cp_kat5', P, fit, itr, tol=1e-5)
+    assert init[0] is not None and init[1] is P.U[1]
+    assert all(np.isfinite(u).all() for u in P.U)
+    np.random.seed(3)
+    _check_cp(golden, 'cp_d4_s3', *cp_als(dtensor(golden['cp4_X']), 4, init='random', max_iter=30)[:3])
+    np.random.seed(1)
+    _check_cp(golden, 'cp_planted_s1', *cp_als(dtensor(golden['cppl_X']), 3, init='random', max_iter=60)[:3], tol=1e-6)
+    subs = tuple(golden['cpsp_sub%d' % m] for m in range(3))
+    np.random.seed(1)
+    _check_cp(golden, 'cp_sp_s1', *cp_als(sptensor(subs, golden['cpsp_vals'], shape=(60, 50, 40)), 5,
+                                          init='random', max_iter=25)[:3])
+    # all-zero init: 0/0 on the first sweep, then the reference's pinv raises ValueError (App. A.17)
+    with pytest.raises(ValueError):
+        cp_als(dtensor(X), 3, init=[None, np.zeros((11, 3)), np.zeros((8, 3))], max_iter=3)
+
+
+def test_cp_als_midsize_vs_oracle():
+    """64x48x56 rank 16 and a rank-32 4-way run: same trajectory as the oracle."""
+    from sktensor import cp_als, dtensor
+    rng = np.random.RandomState(2)
+    for shape, R in (((64, 48, 56), 16), ((20, 24, 16, 18), 32)):
+        X = rng.rand(*shape)
+        np.random.seed(9)
+        Uo, lo, fo, io, _ = orc.cp_als(X, R, init='random', max_iter=8, conv=0)
+        np.random.seed(9)
+        P, fit, itr, _ = cp_als(dtensor(X), R, init='random', max_iter=8, conv=0)
+        assert itr == io and abs(fit - float(np.ravel(fo)[0])) < 1e-9
+        for a, b in zip(P.U, Uo):
+            assert relerr(a, b) < 1e-6
+
+
+def test_ttm_ttv_nvecs(golden):
+    from sktensor import dtensor, nvecs, ttm
+    from sktensor.sptensor import fromarray
+    T = golden['kat1_T']
+    Y2 = dtensor(T).ttm(golden['ttm_V'], 0)                  # test_base.py:77-81
+    assert Y2.shape == (2, 4, 2) and (np.asarray(Y2) == golden['ttm_Y0']).all()
+    X = golden['ttm_X']
+    V = [golden['ttm_V%d' % m] for m in range(3)]
+    for m in range(3):
+        assert relerr(dtensor(X).ttm(V[m], m, transp=True), golden['ttm_single%d' % m]) < 1e-13
+        assert relerr(ttm(dtensor(X), V, m, transp=True, without=True), golden['ttm_without%d' % m]) < 1e-13
+        got, ref = nvecs(dtensor(X), m, 3), golden['nvecs_%d' % m]
+        assert relerr(got, ref) < 1e-8
+    assert relerr(dtensor(X).ttm(V, transp=True), golden['ttm_all']) < 1e-13
+    # ttv: dense and sparse (test_sptensor.py:103-133)
+    v = np.array([1., 2, 3, 4])
+    assert (np.asarray(dtensor(T).ttv(v, 1)) == [[70, 190], [80, 200], [90, 210]]).all()
+    Xv = fromarray(T).ttv(v, 1)
+    assert Xv.shape == (3, 2) and (Xv == np.array([[70, 190], [80, 200], [90, 210]]))
+    from sktensor import sptensor
+    S = sptensor((np.array([0, 1, 0, 5, 7, 8]), np.array([2, 0, 4, 5, 3, 9]), np.array([0, 1, 2, 2, 1, 0])),
+                 np.array([1, 1, 1, 1, 1, 1]), shape=[10, 10, 3])
+    sttv = S.ttv((np.zeros(10), np.zeros(10)), modes=[0, 1])
+    assert type(sttv) == sptensor and len(sttv.vals) == 0 and sttv.shape == (3,)
+    w = S.ttv((np.arange(10.), np.arange(10.) + 1), modes=[0, 1])
+    dense = np.einsum('ijk,i,j->k', S.toarray(), np.arange(10.), np.arange(10.) + 1)
+    out = np.zeros(3)
+    out[w.subs[0]] = w.vals
+    assert np.allclose(out, dense)
+    full = dtensor(X).ttv((np.ones(7), np.ones(6), np.ones(5)))
+    assert abs(float(np.ravel(full)[0]) - X.sum()) < 1e-10
+
+
+def test_tucker_hooi_golden(golden):
+    from sktensor import dtensor, tucker_hooi
+    X = golden['cfg1_X']
+    core, U = tucker_hooi(dtensor(X), [3, 4, 2], init='nvecs')
+    assert abs(np.linalg.norm(core) - golden.j['hooi_cfg1']['core_norm']) < 1e-9
+    assert relerr(np.abs(core), np.abs(golden['hooi_cfg1_core'])) < 1e-6
+    for m in range(3):
+        assert relerr(U[m].T.dot(U[m]), np.eye(U[m].shape[1])) < 1e-12
+        assert relerr(U[m], golden['hooi_cfg1_U%d' % m]) < 1e-6
+    np.random.seed(3)
+    core, U = tucker_hooi(dtensor(X), [3, 4, 2], init='random')
+    normres = np.sqrt(np.linalg.norm(X) ** 2 - np.linalg.norm(core) ** 2)
+    assert abs((1 - normres / np.linalg.norm(X)) - golden.j['hooi_cfg1_rand3']['fit']) < 1e-6
+    core, U = tucker_hooi(dtensor(golden['hooi_b_X']), [4, 5, 3], init='nvecs', maxIter=6, conv=0)
+    assert abs(np.linalg.norm(core) - golden.j['hooi_b']['core_norm']) < 1e-9
+    assert relerr(np.abs(core), np.abs(golden['hooi_b_core'])) < 1e-6
+    core, U = tucker_hooi(dtensor(X), 2, init='random', maxIter=3)           # scalar rank (tucker.py:90-91)
+    assert core.shape == (2, 2, 2)

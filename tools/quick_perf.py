@@ -1,0 +1,90 @@
+"""Quick device-side timings (CUDA events) of the hot kernels; development aid, not the bench."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'scikit-tensor_b200'))
+import torch  # noqa: E402
+from sktensor import _device as dev, _kernels as K  # noqa: E402
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    print('fp64 peaks (dmma, dfma) TFLOP/s:', K.probe_fp64_peaks())
+    a = torch.rand(8192, 8192, dtype=torch.float64, device='cuda')
+    b = torch.rand(8192, 8192, dtype=torch.float64, device='cuda')
+    med, best = timeit(lambda: torch.matmul(a, b), reps=5, warm=2)
+    print('cuBLAS dgemm 8192^3: %.2f ms -> %.1f TFLOP/s' % (best, 2 * 8192 ** 3 / best / 1e9))
+    del a, b
+    which = sys.argv[1:] or ['cfg2', 'cfg5', 'sparse']
+    if 'cfg2' in which:
+        for shape, R in (((512, 512, 512), 32), ((512, 512, 512), 16), ((512, 512, 512), 64)):
+            X = torch.rand(*shape, dtype=torch.float64, device='cuda')
+            U = [torch.rand(s, R, dtype=torch.float64, device='cuda') for s in shape]
+            nbytes = 8 * (X.numel() + R * sum(shape))
+            for n in range(len(shape)):
+                out = dev.empty((shape[n], R))
+                med, best = timeit(lambda: K.mttkrp_dense(X, shape, U, R, n, out=out))
+                print('dense %s R=%d mode %d: median %.3f ms best %.3f ms  %.0f GB/s  %.1f TFLOP/s' %
+                      (shape, R, n, med, best, nbytes / med / 1e6, 2.0 * R * X.numel() / med / 1e9))
+            del X
+    if 'cfg5' in which:
+        shape, R = (160, 160, 160, 160), 64
+        X = torch.rand(*shape, dtype=torch.float64, device='cuda')
+        U = [torch.rand(s, R, dtype=torch.float64, device='cuda') for s in shape]
+        nbytes = 8 * (X.numel() + R * sum(shape))
+        for n in range(4):
+            out = dev.empty((shape[n], R))
+            med, best = timeit(lambda: K.mttkrp_dense(X, shape, U, R, n, out=out), reps=5)
+            print('dense %s R=%d mode %d: median %.3f ms best %.3f ms  %.0f GB/s  %.1f TFLOP/s' %
+                  (shape, R, n, med, best, nbytes / med / 1e6, 2.0 * R * X.numel() / med / 1e9))
+        del X
+    if 'sparse' in which:
+        shape = (10000000, 1000000, 100000)
+        nnz = int(os.environ.get('NNZ', 20000000))
+        R = 16
+        rng = np.random.default_rng(0)
+        subs = [np.minimum((I * rng.random(nnz) ** 3.0).astype(np.int64), I - 1) for I in shape]
+        vals = rng.random(nnz)
+        t0 = time.perf_counter()
+        coo = K.CooHandle(subs, vals, shape)
+        torch.cuda.synchronize()
+        print('coo build (%d nnz): %.2f s, %.2f GB on device' % (nnz, time.perf_counter() - t0, coo.device_bytes() / 1e9))
+        U = [torch.rand(s, R, dtype=torch.float64, device='cuda') for s in shape]
+        for n in range(3):
+            out = dev.empty((shape[n], R))
+            med, best = timeit(lambda: K.mttkrp_coo(coo, U, R, n, out=out), reps=5)
+            nbytes = nnz * (4 * 3 + 8) + 8 * R * sum(shape)
+            print('sparse nnz=%d R=%d mode %d: median %.3f ms best %.3f ms  %.0f GB/s (algorithmic)  %.1f Mnnz/s' %
+                  (nnz, R, n, med, best, nbytes / med / 1e6, nnz / med / 1e3))
+    if 'als' in which:
+        from sktensor import _parallel, dtensor
+        X = np.random.RandomState(0).rand(512, 512, 512)
+        np.random.seed(1)
+        U = [None] + [np.random.rand(512, 32) for _ in range(2)]
+        eng = _parallel.CpAlsEngine(dtensor(X), 32, U)
+        eng.sweep(True)
+        eng.read_fit()
+        med, best = timeit(lambda: (eng.sweep(False), eng.read_fit()), reps=10, warm=2)
+        print('cp_als 512^3 R=32 iteration: median %.3f ms best %.3f ms -> %.1f it/s' % (med, best, 1e3 / med))
+
+
+if __name__ == '__main__':
+    main()
