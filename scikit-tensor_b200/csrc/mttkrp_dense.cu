@@ -16,6 +16,9 @@
 // shared memory in a fixed order and written either straight to M or to a per-split partial
 // slab that a second tiny kernel adds up -- no atomics, bitwise reproducible.
 #include <algorithm>
+#include <cstdlib>
+
+#include <cuda.h>
 
 #include "common.cuh"
 
@@ -307,6 +310,261 @@ __global__ void __launch_bounds__(NTHREADS, 1) mttkrp_dense_kernel(const __grid_
     cp_async_wait<0>();
 }
 
+// =============================================================================================
+// TMA variant (the production path whenever the tensor's rows are 16-byte aligned).
+//
+// X tiles are fetched by the TMA engine (cp.async.bulk.tensor, SASS UTMALDG) from a tiled
+// tensor map with 128-byte swizzle; one elected thread issues 2 (K-major) or 8 (M-major) bulk
+// tensor copies per 32 KB stage and an mbarrier counts the bytes in, so the 8 compute warps
+// spend their issue slots on LDS + DMMA only.  The hardware zero-fills out-of-range box
+// elements, which removes every bounds predicate from the hot loop.
+//
+//   K-major (contraction mode last):  map dims (k, t, i_n, l), box (16, bt, bi, bl), two boxes
+//     per stage (k halves).  Shared layout: 128 rows x 128 B, 16-byte chunk c of row q stored at
+//     chunk c ^ (q & 7).  Warp rows are visited in the order perm(g) = 2*(g&3) + (g>>2) so that
+//     the 16 lanes of a 64-bit shared-load phase touch 8 distinct chunks x 2 halves: conflict-free.
+//   M-major (contraction mode first): map dims (i_n, l, k), box (16, 1, 32), eight boxes per
+//     stage (one per warp).  Shared layout per warp: 32 k-rows x 128 B, swizzled by k & 7; the four
+//     k-slots of one DMMA are k = 8j + 2*t + h so the swizzle again spreads them over all banks.
+// The factor slice of the contraction mode (BK x R, a few KB) still arrives by cp.async into a
+// padded layout; its rows are stored in the matching k order.
+// =============================================================================================
+constexpr int XSTAGE_BYTES = BM * BK * 8;  // 32 KB
+
+template <int NB, bool MMAJOR>
+__global__ void __launch_bounds__(NTHREADS, 1)
+    mttkrp_dense_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ DenseParams p) {
+    constexpr int STAGES = (NB <= 4) ? 4 : 3;
+    constexpr int RS = 8 * NB + 4;
+    constexpr int USTAGE_BYTES = (BK * RS * 8 + 1023) / 1024 * 1024;
+    constexpr int STAGE_BYTES = XSTAGE_BYTES + USTAGE_BYTES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1 KB alignment
+    double *Z = reinterpret_cast<double *>(base + STAGES * STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(Z + BM * ZS);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int bt = 1 << p.lg_bt, bi = 1 << p.lg_bi, bl = 1 << p.lg_bl;
+    const int pg = MMAJOR ? g : (2 * (g & 3) + (g >> 2));  // tile row (within a group of 8) owned by fragment row g
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmX);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto decompose = [&](int q, int it, int lt, int tt, int &l, int &i, int &t) -> bool {
+        const int t_off = q & (bt - 1);
+        const int i_off = (q >> p.lg_bt) & (bi - 1);
+        const int l_off = q >> (p.lg_bt + p.lg_bi);
+        t = tt * bt + t_off;
+        i = it * bi + i_off;
+        l = lt * bl + l_off;
+        return (t < p.T) && (i < p.In) && (l < p.L);
+    };
+    auto item_range = [&](int item, int &t0, int &t1) {
+        const int s = item % p.nsplit;
+        t0 = s * p.chunk;
+        t1 = min(t0 + p.chunk, p.nred);
+    };
+
+    // ------------------------------------------------------------------ loader
+    int l_item = blockIdx.x, l_tile = 0, l_tile_end = 0, l_ks = 0;
+    bool l_active = l_item < p.nitems;
+    if (l_active) item_range(l_item, l_tile, l_tile_end);
+
+    auto loader_issue = [&](int st) {
+        if (l_active) {
+            uint8_t *sb = base + st * STAGE_BYTES;
+            double *Us = reinterpret_cast<double *>(sb + XSTAGE_BYTES);
+            const int k0 = l_ks * BK;
+            for (int c = tid; c < BK * 4 * NB; c += NTHREADS) {
+                const int kr = c / (4 * NB);
+                const int col = 2 * (c % (4 * NB));
+                const int kc = k0 + kr;
+                const int dr = MMAJOR ? ((kr & ~7) + 4 * (kr & 1) + ((kr & 7) >> 1)) : kr;
+                double *dst = Us + dr * RS + col;
+                const double *src = p.Uc + (long long)kc * p.ld + col;
+                if (p.vecU) {
+                    const bool ok = (kc < p.Kc) && (col < p.R);
+                    cp_async16(dst, ok ? src : p.Uc, ok ? 16 : 0);
+                } else {
+                    const bool ok0 = (kc < p.Kc) && (col < p.R);
+                    const bool ok1 = (kc < p.Kc) && (col + 1 < p.R);
+                    cp_async8(dst, ok0 ? src : p.Uc, ok0 ? 8 : 0);
+                    cp_async8(dst + 1, ok1 ? src + 1 : p.Uc, ok1 ? 8 : 0);
+                }
+            }
+            if (tid == 0) {
+                const int it = l_item / p.nsplit;
+                const int lt = l_tile / p.ntt, tt = l_tile % p.ntt;
+                mbar_arrive_expect_tx(&full[st], XSTAGE_BYTES);
+                if (!MMAJOR) {
+                    tma_load_4d(sb, &tmX, &full[st], k0, tt * bt, it * bi, lt * bl);
+                    tma_load_4d(sb + XSTAGE_BYTES / 2, &tmX, &full[st], k0 + 16, tt * bt, it * bi, lt * bl);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        tma_load_3d(sb + j * (XSTAGE_BYTES / 8), &tmX, &full[st], it * 16, lt * 8 + j, k0);
+                }
+            }
+            if (++l_ks == p.nk) {
+                l_ks = 0;
+                if (++l_tile == l_tile_end) {
+                    l_item += gridDim.x;
+                    if (l_item < p.nitems) item_range(l_item, l_tile, l_tile_end);
+                    else l_active = false;
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    // ------------------------------------------------------------------ consumer
+    double acc[2][NB][2], out[2][NB][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            acc[a][nb][0] = acc[a][nb][1] = 0.0;
+            out[a][nb][0] = out[a][nb][1] = 0.0;
+        }
+    int c_item = blockIdx.x, c_tile = 0, c_tile_end = 0, c_ks = 0;
+    if (c_item < p.nitems) item_range(c_item, c_tile, c_tile_end);
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) loader_issue(s);
+
+    // per-thread constant parts of the swizzled A-fragment addresses
+    const int a_row0 = MMAJOR ? (warp * 4096 + (((g >> 1)) << 4) + (g & 1) * 8)        // a = 0: i_off = g
+                              : ((16 * warp + pg) * 128 + (t4 & 1) * 8);
+    const int tp = MMAJOR ? 0 : ((t4 >> 1) ^ pg);
+
+    int stage = 0;
+    uint32_t phase = 0;
+    while (c_item < p.nitems) {
+        cp_async_wait<STAGES - 2>();
+        mbar_wait(&full[stage], phase);
+        __syncthreads();
+        loader_issue((stage + STAGES - 1) % STAGES);
+
+        {
+            const uint8_t *Xb = base + stage * STAGE_BYTES;
+            const double *Us = reinterpret_cast<const double *>(Xb + XSTAGE_BYTES);
+#pragma unroll
+            for (int s8 = 0; s8 < BK / 4; ++s8) {
+                double a0, a1;
+                int brow;
+                if (MMAJOR) {
+                    const int kk8 = 8 * (s8 >> 1), h = s8 & 1;
+                    const int k = kk8 + 2 * t4 + h;      // k & 7 == 2*t4 + h
+                    const int x = 2 * t4 + h;
+                    // element (l_off = warp, k, i_off = 8a + g): chunk (4a + (g>>1)) ^ x
+                    const int c0 = ((g >> 1) ^ x) << 4;
+                    const int c1 = ((4 + (g >> 1)) ^ x) << 4;
+                    a0 = *reinterpret_cast<const double *>(Xb + warp * 4096 + k * 128 + c0 + (g & 1) * 8);
+                    a1 = *reinterpret_cast<const double *>(Xb + warp * 4096 + k * 128 + c1 + (g & 1) * 8);
+                    brow = kk8 + 4 * h + t4;
+                } else {
+                    const int kk = 4 * s8;
+                    const int off = (kk >> 4) * (XSTAGE_BYTES / 2) + ((((kk & 15) >> 1) ^ tp) << 4);
+                    a0 = *reinterpret_cast<const double *>(Xb + a_row0 + off);
+                    a1 = *reinterpret_cast<const double *>(Xb + a_row0 + 8 * 128 + off);
+                    brow = kk + t4;
+                }
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const double b = Us[brow * RS + 8 * nb + g];
+                    dmma884(acc[0][nb][0], acc[0][nb][1], a0, b);
+                    dmma884(acc[1][nb][0], acc[1][nb][1], a1, b);
+                }
+            }
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+
+        if (++c_ks == p.nk) {
+            c_ks = 0;
+            {
+                const int it = c_item / p.nsplit;
+                const int lt = c_tile / p.ntt, tt = c_tile % p.ntt;
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const int q = 16 * warp + 8 * a + pg;
+                    int l, i, t;
+                    const bool ok = decompose(q, it, lt, tt, l, i, t);
+                    double wgt[NB][2];
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) wgt[nb][0] = wgt[nb][1] = ok ? 1.0 : 0.0;
+                    if (ok) {
+                        for (int m = 0; m < p.nw; ++m) {
+                            const int sp = p.w[m].space ? t : l;
+                            const int idx = (sp / p.w[m].div) % p.w[m].dim;
+                            const double *row = p.w[m].U + (long long)idx * p.ld;
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) {
+                                const int col = 8 * nb + 2 * t4;
+                                if (col < p.R) wgt[nb][0] *= __ldg(row + col);
+                                if (col + 1 < p.R) wgt[nb][1] *= __ldg(row + col + 1);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        out[a][nb][0] += ok ? wgt[nb][0] * acc[a][nb][0] : 0.0;
+                        out[a][nb][1] += ok ? wgt[nb][1] * acc[a][nb][1] : 0.0;
+                        acc[a][nb][0] = acc[a][nb][1] = 0.0;
+                    }
+                }
+            }
+            if (++c_tile == c_tile_end) {
+                const int it = c_item / p.nsplit, s = c_item % p.nsplit;
+                double *dst = p.out + (long long)s * p.out_split_stride;
+                constexpr int NH = (NB + 3) / 4;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const int q = 16 * warp + 8 * a + pg;
+#pragma unroll
+                        for (int nn = 0; nn < 4; ++nn) {
+                            const int nb = 4 * h + nn;
+                            if (nb < NB) {
+                                Z[q * ZS + 8 * nn + 2 * t4] = out[a][nb][0];
+                                Z[q * ZS + 8 * nn + 2 * t4 + 1] = out[a][nb][1];
+                                out[a][nb][0] = out[a][nb][1] = 0.0;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    for (int o = tid; o < bi * 32; o += NTHREADS) {
+                        const int i_off = o >> 5, c = o & 31;
+                        const int col = 32 * h + c;
+                        const int i = it * bi + i_off;
+                        if (col < p.R && col < 8 * NB && i < p.In) {
+                            double sum = 0.0;
+                            for (int l_off = 0; l_off < bl; ++l_off)
+                                for (int t_off = 0; t_off < bt; ++t_off) {
+                                    const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
+                                    sum += Z[q * ZS + c];
+                                }
+                            dst[(long long)i * p.ld + col] = sum;
+                        }
+                    }
+                    __syncthreads();
+                }
+                c_item += gridDim.x;
+                if (c_item < p.nitems) item_range(c_item, c_tile, c_tile_end);
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // M[e] = sum_s P[s][e] in split order (deterministic)
 __global__ void reduce_splits_kernel(const double *__restrict__ P, int nsplit, long long n, double *__restrict__ M) {
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
@@ -369,7 +627,7 @@ int ilog2(int x) {
     return l;
 }
 
-int make_plan(const int64_t *shape, int ndim, int rank, int mode, DensePlan &pl) {
+int make_plan(const int64_t *shape, int ndim, int rank, int mode, bool tma, DensePlan &pl) {
     SKT_REQUIRE(shape != nullptr, SKT_EINVAL, "shape is NULL");
     SKT_REQUIRE(ndim >= 2 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "ndim must be in [2, %d], got %d", SKT_MAX_NDIM, ndim);
     SKT_REQUIRE(mode >= 0 && mode < ndim, SKT_EINVAL, "mode %d out of range for a %d-way tensor", mode, ndim);
@@ -413,6 +671,7 @@ int make_plan(const int64_t *shape, int ndim, int rank, int mode, DensePlan &pl)
             const int ll = 7 - lt - li;
             const long long bt = 1LL << lt, bi = 1LL << li, bl = 1LL << ll;
             if (pl.mmajor && lt != 0) continue;
+            if (pl.mmajor && tma && !(li == 4 && ll == 3)) continue;  // the M-major TMA box is fixed: 16 i x 8 l
             const double padded = (double)((T + bt - 1) / bt * bt) * (double)((pl.In + bi - 1) / bi * bi) *
                                   (double)((L + bl - 1) / bl * bl);
             // prefer (slightly) boxes whose inner run is long: fewer DRAM page switches
@@ -482,6 +741,89 @@ int launch_dense(const DenseParams &p, int grid, cudaStream_t st) {
     return SKT_OK;
 }
 
+// ---- TMA path -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+bool tma_eligible(const double *X, const DensePlan &pl) {
+    const char *off = getenv("SKT_DENSE_NO_TMA");
+    if (off && off[0] == '1') return false;
+    if ((((uintptr_t)X) & 15) != 0) return false;
+    return pl.mmajor ? (pl.In % 2 == 0) : (pl.Kc % 2 == 0);
+}
+
+int make_tensor_map(const double *X, const DensePlan &pl, CUtensorMap &tm) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    SKT_REQUIRE(enc != nullptr, SKT_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], estr[4] = {1, 1, 1, 1};
+    cuuint32_t rank;
+    if (!pl.mmajor) {
+        rank = 4;
+        dims[0] = pl.Kc; dims[1] = pl.T; dims[2] = pl.In; dims[3] = pl.L;
+        strides[0] = (cuuint64_t)pl.Kc * 8;
+        strides[1] = strides[0] * pl.T;
+        strides[2] = strides[1] * pl.In;
+        box[0] = 16; box[1] = 1u << pl.lg_bt; box[2] = 1u << pl.lg_bi; box[3] = 1u << pl.lg_bl;
+    } else {
+        rank = 3;
+        dims[0] = pl.In; dims[1] = pl.L; dims[2] = pl.Kc;
+        strides[0] = (cuuint64_t)pl.In * 8;
+        strides[1] = strides[0] * pl.L;
+        box[0] = 16; box[1] = 1; box[2] = BK;
+    }
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<double *>(X), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SKT_REQUIRE(r == CUDA_SUCCESS, SKT_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SKT_OK;
+}
+
+template <int NB, bool MMAJOR>
+int launch_dense_tma(const CUtensorMap &tm, const DenseParams &p, int grid, cudaStream_t st) {
+    constexpr int STAGES = (NB <= 4) ? 4 : 3;
+    constexpr int RS = 8 * NB + 4;
+    constexpr int USTAGE_BYTES = (BK * RS * 8 + 1023) / 1024 * 1024;
+    const size_t smem = (size_t)STAGES * (XSTAGE_BYTES + USTAGE_BYTES) + (size_t)BM * ZS * 8 + STAGES * 8 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        SKT_CUDA(cudaFuncSetAttribute(mttkrp_dense_tma_kernel<NB, MMAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    mttkrp_dense_tma_kernel<NB, MMAJOR><<<grid, NTHREADS, smem, st>>>(tm, p);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+template <bool MMAJOR>
+int launch_dense_tma_nb(int nb, const CUtensorMap &tm, const DenseParams &p, int grid, cudaStream_t st) {
+    switch (nb) {
+        case 1: return launch_dense_tma<1, MMAJOR>(tm, p, grid, st);
+        case 2: return launch_dense_tma<2, MMAJOR>(tm, p, grid, st);
+        case 3: return launch_dense_tma<3, MMAJOR>(tm, p, grid, st);
+        case 4: return launch_dense_tma<4, MMAJOR>(tm, p, grid, st);
+        case 5: return launch_dense_tma<5, MMAJOR>(tm, p, grid, st);
+        case 6: return launch_dense_tma<6, MMAJOR>(tm, p, grid, st);
+        case 7: return launch_dense_tma<7, MMAJOR>(tm, p, grid, st);
+        default: return launch_dense_tma<8, MMAJOR>(tm, p, grid, st);
+    }
+}
+
 template <bool MMAJOR>
 int launch_dense_nb(int nb, const DenseParams &p, int grid, cudaStream_t st) {
     switch (nb) {
@@ -502,18 +844,30 @@ int launch_dense_nb(int nb, const DenseParams &p, int grid, cudaStream_t st) {
 using namespace skt;
 
 extern "C" size_t skt_mttkrp_dense_workspace(const int64_t *shape, int ndim, int rank, int mode) {
-    DensePlan pl;
-    if (make_plan(shape, ndim, rank, mode, pl) != SKT_OK) return 0;
-    if (pl.nsplit <= 1) return 256;
-    return align_up((size_t)pl.nsplit * pl.In * rank * sizeof(double), 256);
+    // the kernel variant (TMA or cp.async) is chosen at launch from the pointer alignment: cover both plans
+    size_t need = 256;
+    for (int tma = 0; tma < 2; ++tma) {
+        DensePlan pl;
+        if (make_plan(shape, ndim, rank, mode, tma != 0, pl) != SKT_OK) return 0;
+        if (pl.nsplit > 1) need = std::max(need, align_up((size_t)pl.nsplit * pl.In * rank * sizeof(double), 256));
+    }
+    return need;
 }
 
 extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndim, const double *const *U_d, int rank,
                                 int mode, double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
-    DensePlan pl;
-    int rc = make_plan(shape, ndim, rank, mode, pl);
-    if (rc != SKT_OK) return rc;
     SKT_REQUIRE(X_d && U_d && M_d, SKT_EINVAL, "NULL tensor / factor list / output");
+    DensePlan pl;
+    int rc = make_plan(shape, ndim, rank, mode, false, pl);
+    if (rc != SKT_OK) return rc;
+    const bool use_tma = tma_eligible(X_d, pl);
+    CUtensorMap tm;
+    if (use_tma) {
+        rc = make_plan(shape, ndim, rank, mode, true, pl);
+        if (rc != SKT_OK) return rc;
+        rc = make_tensor_map(X_d, pl, tm);
+        if (rc != SKT_OK) return rc;
+    }
     for (int m = 0; m < ndim; ++m)
         SKT_REQUIRE(m == mode || U_d[m] != nullptr, SKT_EINVAL, "U[%d] is NULL (only U[mode] may be)", m);
     cudaStream_t st = (cudaStream_t)stream;
@@ -549,7 +903,10 @@ extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndi
         }
         p.vecU = ((((uintptr_t)p.Uc) & 15) == 0) && (rank % 2 == 0) && (ncol % 2 == 0);
         const int nb = (ncol + 7) / 8;
-        rc = pl.mmajor ? launch_dense_nb<true>(nb, p, pl.grid, st) : launch_dense_nb<false>(nb, p, pl.grid, st);
+        if (use_tma)
+            rc = pl.mmajor ? launch_dense_tma_nb<true>(nb, tm, p, pl.grid, st) : launch_dense_tma_nb<false>(nb, tm, p, pl.grid, st);
+        else
+            rc = pl.mmajor ? launch_dense_nb<true>(nb, p, pl.grid, st) : launch_dense_nb<false>(nb, p, pl.grid, st);
         if (rc != SKT_OK) return rc;
     }
     if (pl.nsplit > 1) {

@@ -25,6 +25,16 @@ def dev():
     return dev
 
 
+@pytest.fixture(params=['tma', 'cpasync'])
+def dense_path(request):
+    """Run a test on both dense kernels: TMA-staged (default) and the cp.async one used for
+    tensors whose rows are not 16-byte aligned (forced here through SKT_DENSE_NO_TMA)."""
+    import os
+    os.environ['SKT_DENSE_NO_TMA'] = '1' if request.param == 'cpasync' else '0'
+    yield request.param
+    os.environ['SKT_DENSE_NO_TMA'] = '0'
+
+
 def gpu_mttkrp_dense(K, dev, X, U, n, naive=False):
     R = next(u for m, u in enumerate(U) if m != n and u is not None).shape[1]
     Ud = [None if (u is None or m == n) else dev.to_device(u) for m, u in enumerate(U)]
@@ -42,7 +52,7 @@ def test_native_library_is_loaded(K):
     assert major.value == 10 and sm.value >= 100 and smem.value >= 227 * 1024
 
 
-def test_kat1_exact_integers(K, dev, golden):
+def test_kat1_exact_integers(K, dev, golden, dense_path):
     T = golden['kat1_T']
     U = golden.factors('kat1', 3)
     for n in range(3):
@@ -50,7 +60,7 @@ def test_kat1_exact_integers(K, dev, golden):
         assert (gpu_mttkrp_dense(K, dev, T, U, n, naive=True) == golden['kat1_M%d' % n]).all()
 
 
-def test_dense_golden_all_modes(K, dev, golden):
+def test_dense_golden_all_modes(K, dev, golden, dense_path):
     for name, c in golden.j['dense_cases'].items():
         N = len(c['shape'])
         X = golden['mtd_%s_X' % name]
@@ -68,8 +78,9 @@ def test_dense_golden_all_modes(K, dev, golden):
     ((129, 20, 34), 33), ((20, 130, 66), 64), ((24, 18, 20), 65), ((12, 14, 16), 100),
     ((6, 7, 8, 9), 5), ((16, 12, 10, 14), 32), ((5, 4, 6, 3, 7), 4), ((300, 2), 6), ((2, 300), 6),
     ((1, 50, 40), 4), ((50, 1, 40), 4), ((50, 40, 1), 4), ((3, 3, 3, 3, 3, 3), 2),
+    ((130, 70, 36), 32), ((36, 130, 70), 16), ((18, 22, 14, 20), 64), ((160, 12, 6, 40), 24),
 ])
-def test_dense_random_shapes_vs_oracle(K, dev, shape, R):
+def test_dense_random_shapes_vs_oracle(K, dev, shape, R, dense_path):
     rng = np.random.RandomState(hash((shape, R)) % (2 ** 31))
     X = rng.rand(*shape) - 0.3
     U = [rng.rand(s, R) - 0.5 for s in shape]
@@ -128,7 +139,7 @@ def test_dense_host_buffer_abi(K, golden):
         assert relerr(K.mttkrp_dense_host(X, U, 32, n), golden['mtd_d3b_M%d' % n]) < TOL
 
 
-def test_dense_deterministic_and_linear(K, dev):
+def test_dense_deterministic_and_linear(K, dev, dense_path):
     """Size-independent properties at a size the oracle still checks in seconds (256^3, R=32)."""
     rng = np.random.RandomState(11)
     X = rng.rand(256, 256, 256)
