@@ -314,76 +314,101 @@ __global__ void __launch_bounds__(NTHREADS, 1) mttkrp_dense_kernel(const __grid_
 // TMA variant (the production path whenever the tensor's rows are 16-byte aligned).
 //
 // X tiles are fetched by the TMA engine (cp.async.bulk.tensor, SASS UTMALDG) from a tiled
-// tensor map with 128-byte swizzle; one elected thread issues 2 (K-major) or 8 (M-major) bulk
-// tensor copies per 32 KB stage and an mbarrier counts the bytes in, so the 8 compute warps
-// spend their issue slots on LDS + DMMA only.  The hardware zero-fills out-of-range box
-// elements, which removes every bounds predicate from the hot loop.
+// tensor map with 128-byte swizzle; one elected thread issues the bulk tensor copies of a
+// stage and an mbarrier counts the bytes in, so the compute warps spend their issue slots on
+// LDS + DMMA only.  The hardware zero-fills out-of-range box elements, which removes every
+// bounds predicate from the hot loop.  16 warps (4 per scheduler) keep the FP64 tensor pipe fed
+// while other warps wait on shared loads or the stage barrier; every warp owns a 16-row x
+// 32-column accumulator block:  rank <= 32: 16 row groups (256-row tiles);  rank 33..64:
+// 8 row groups x 2 column groups (128-row tiles).
 //
-//   K-major (contraction mode last):  map dims (k, t, i_n, l), box (16, bt, bi, bl), two boxes
-//     per stage (k halves).  Shared layout: 128 rows x 128 B, 16-byte chunk c of row q stored at
-//     chunk c ^ (q & 7).  Warp rows are visited in the order perm(g) = 2*(g&3) + (g>>2) so that
-//     the 16 lanes of a 64-bit shared-load phase touch 8 distinct chunks x 2 halves: conflict-free.
-//   M-major (contraction mode first): map dims (i_n, l, k), box (16, 1, 32), eight boxes per
-//     stage (one per warp).  Shared layout per warp: 32 k-rows x 128 B, swizzled by k & 7; the four
-//     k-slots of one DMMA are k = 8j + 2*t + h so the swizzle again spreads them over all banks.
-// The factor slice of the contraction mode (BK x R, a few KB) still arrives by cp.async into a
+//   K-major (contraction mode last):  map dims (k, t, i_n, l), box (16, bt, bi, bl), one box per
+//     stage.  Shared layout: rows of 128 B, 16-byte chunk c of row q stored at chunk c ^ (q & 7).
+//     Warp rows are visited in the order perm(g) = 2*(g&3) + (g>>2) so that the 16 lanes of a
+//     64-bit shared-load phase touch 8 distinct chunks x 2 halves: conflict-free.
+//   M-major (contraction mode first): map dims (i_n, l, k), box (16, 1, 16), one box per row group.
+//     Shared layout per row group: 16 k-rows x 128 B, swizzled by k & 7; the four k-slots of one
+//     DMMA are k = 8j + 2*t + h so the swizzle again spreads them over all banks.
+// The factor slice of the contraction mode (16 x R, a few KB) still arrives by cp.async into a
 // padded layout; its rows are stored in the matching k order.
 // =============================================================================================
-constexpr int XSTAGE_BYTES = BM * BK * 8;  // 32 KB
+constexpr int TK = 16;            // contraction slice per stage of the TMA kernel (one 128-byte swizzle row)
+constexpr int TCONS = 512;        // 16 consumer (DMMA) warps
+constexpr int TTHREADS = 544;     // + 1 producer warp (TMA + cp.async issue)
+
+template <int NB>
+struct TmaCfg {
+    static constexpr int CG = (NB > 4) ? 2 : 1;          // column groups of 32
+    static constexpr int RG = 16 / CG;                   // row groups of 16
+    static constexpr int BMT = 16 * RG;                  // rows per tile
+    static constexpr int RS = 8 * NB + 4;                // padded row stride of the factor slice
+    static constexpr int XBYTES = BMT * TK * 8;          // 32 KB / 16 KB
+    static constexpr int UBYTES = (TK * RS * 8 + 1023) / 1024 * 1024;
+    static constexpr int STAGE_BYTES = XBYTES + UBYTES;
+    static constexpr int ZC = 32 * CG;                   // staged columns at flush time
+    static constexpr int ZSTR = ZC + 2;
+    static constexpr int ZBYTES = BMT * ZSTR * 8;
+    static constexpr int STAGES = (CG == 1) ? 4 : 6;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + ZBYTES + 2 * STAGES * 8 + 1024;
+};
+
+// Work schedule shared by the producer and the consumers: CTA b owns items b, b+grid, ...; an item is
+// (output-row tile, split) and covers reduction tiles [t0, t1); every tile is nk k-slices.
+struct StepState {
+    int item, tile, tile_end, ks;
+    __device__ __forceinline__ void init(const DenseParams &p) {
+        item = blockIdx.x;
+        tile = tile_end = 0;
+        ks = 0;
+        if (item < p.nitems) range(p);
+    }
+    __device__ __forceinline__ void range(const DenseParams &p) {
+        const int s = item % p.nsplit;
+        tile = s * p.chunk;
+        tile_end = min(tile + p.chunk, p.nred);
+    }
+    __device__ __forceinline__ bool active(const DenseParams &p) const { return item < p.nitems; }
+};
 
 template <int NB, bool MMAJOR>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(TTHREADS, 1)
     mttkrp_dense_tma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ DenseParams p) {
-    constexpr int STAGES = (NB <= 4) ? 4 : 3;
-    constexpr int RS = 8 * NB + 4;
-    constexpr int USTAGE_BYTES = (BK * RS * 8 + 1023) / 1024 * 1024;
-    constexpr int STAGE_BYTES = XSTAGE_BYTES + USTAGE_BYTES;
+    using C = TmaCfg<NB>;
+    constexpr int STAGES = C::STAGES, RS = C::RS, RG = C::RG;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1 KB alignment
-    double *Z = reinterpret_cast<double *>(base + STAGES * STAGE_BYTES);
-    uint64_t *full = reinterpret_cast<uint64_t *>(Z + BM * ZS);
+    double *Z = reinterpret_cast<double *>(base + STAGES * C::STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + STAGES * C::STAGE_BYTES + C::ZBYTES);
+    uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int g = lane >> 2, t4 = lane & 3;
     const int bt = 1 << p.lg_bt, bi = 1 << p.lg_bi, bl = 1 << p.lg_bl;
-    const int pg = MMAJOR ? g : (2 * (g & 3) + (g >> 2));  // tile row (within a group of 8) owned by fragment row g
 
     if (tid == 0) {
         tma_prefetch_desc(&tmX);
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 33);    // 32 cp.async completions (producer lanes) + the TMA expect_tx arrival
+            mbar_init(&empty[s], 16);   // one arrival per consumer warp
+        }
         fence_barrier_init();
     }
     __syncthreads();
 
-    auto decompose = [&](int q, int it, int lt, int tt, int &l, int &i, int &t) -> bool {
-        const int t_off = q & (bt - 1);
-        const int i_off = (q >> p.lg_bt) & (bi - 1);
-        const int l_off = q >> (p.lg_bt + p.lg_bi);
-        t = tt * bt + t_off;
-        i = it * bi + i_off;
-        l = lt * bl + l_off;
-        return (t < p.T) && (i < p.In) && (l < p.L);
-    };
-    auto item_range = [&](int item, int &t0, int &t1) {
-        const int s = item % p.nsplit;
-        t0 = s * p.chunk;
-        t1 = min(t0 + p.chunk, p.nred);
-    };
-
-    // ------------------------------------------------------------------ loader
-    int l_item = blockIdx.x, l_tile = 0, l_tile_end = 0, l_ks = 0;
-    bool l_active = l_item < p.nitems;
-    if (l_active) item_range(l_item, l_tile, l_tile_end);
-
-    auto loader_issue = [&](int st) {
-        if (l_active) {
-            uint8_t *sb = base + st * STAGE_BYTES;
-            double *Us = reinterpret_cast<double *>(sb + XSTAGE_BYTES);
-            const int k0 = l_ks * BK;
-            for (int c = tid; c < BK * 4 * NB; c += NTHREADS) {
+    if (warp == 16) {
+        // ================================================================== producer warp
+        StepState st;
+        st.init(p);
+        int stage = 0;
+        uint32_t use = 0;   // how many times the current stage slot has been filled before
+        while (st.active(p)) {
+            if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1u);
+            uint8_t *sb = base + stage * C::STAGE_BYTES;
+            double *Us = reinterpret_cast<double *>(sb + C::XBYTES);
+            const int k0 = st.ks * TK;
+            for (int c = lane; c < TK * 4 * NB; c += 32) {
                 const int kr = c / (4 * NB);
                 const int col = 2 * (c % (4 * NB));
                 const int kc = k0 + kr;
@@ -400,169 +425,178 @@ __global__ void __launch_bounds__(NTHREADS, 1)
                     cp_async8(dst + 1, ok1 ? src + 1 : p.Uc, ok1 ? 8 : 0);
                 }
             }
-            if (tid == 0) {
-                const int it = l_item / p.nsplit;
-                const int lt = l_tile / p.ntt, tt = l_tile % p.ntt;
-                mbar_arrive_expect_tx(&full[st], XSTAGE_BYTES);
+            cp_async_mbar_arrive_noinc(&full[stage]);
+            if (lane == 0) {
+                const int it = st.item / p.nsplit;
+                const int lt = st.tile / p.ntt, tt = st.tile % p.ntt;
+                mbar_arrive_expect_tx(&full[stage], C::XBYTES);
                 if (!MMAJOR) {
-                    tma_load_4d(sb, &tmX, &full[st], k0, tt * bt, it * bi, lt * bl);
-                    tma_load_4d(sb + XSTAGE_BYTES / 2, &tmX, &full[st], k0 + 16, tt * bt, it * bi, lt * bl);
+                    tma_load_4d(sb, &tmX, &full[stage], k0, tt * bt, it * bi, lt * bl);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        tma_load_3d(sb + j * (XSTAGE_BYTES / 8), &tmX, &full[st], it * 16, lt * 8 + j, k0);
+                    for (int j = 0; j < RG; ++j)
+                        tma_load_3d(sb + j * (TK * 128), &tmX, &full[stage], it * 16, lt * RG + j, k0);
                 }
             }
-            if (++l_ks == p.nk) {
-                l_ks = 0;
-                if (++l_tile == l_tile_end) {
-                    l_item += gridDim.x;
-                    if (l_item < p.nitems) item_range(l_item, l_tile, l_tile_end);
-                    else l_active = false;
+            if (++st.ks == p.nk) {
+                st.ks = 0;
+                if (++st.tile == st.tile_end) {
+                    st.item += gridDim.x;
+                    if (st.active(p)) st.range(p);
                 }
             }
+            if (++stage == STAGES) { stage = 0; ++use; }
         }
-        cp_async_commit();
+        cp_async_wait<0>();
+        return;
+    }
+
+    // ====================================================================== consumer warps
+    const int rg = warp % RG, cg = warp / RG;   // row group / column group of this warp
+    const int g = lane >> 2, t4 = lane & 3;
+    const int pg = MMAJOR ? g : (2 * (g & 3) + (g >> 2));  // tile row (within a group of 8) owned by fragment row g
+    const int nbw = (C::CG == 1) ? (NB < 4 ? NB : 4) : min(4, NB - 4 * cg);  // 8-column blocks this warp computes
+
+    auto decompose = [&](int q, int it, int lt, int tt, int &l, int &i, int &t) -> bool {
+        const int t_off = q & (bt - 1);
+        const int i_off = (q >> p.lg_bt) & (bi - 1);
+        const int l_off = q >> (p.lg_bt + p.lg_bi);
+        t = tt * bt + t_off;
+        i = it * bi + i_off;
+        l = lt * bl + l_off;
+        return (t < p.T) && (i < p.In) && (l < p.L);
     };
 
-    // ------------------------------------------------------------------ consumer
-    double acc[2][NB][2], out[2][NB][2];
+    // acc: the running GEMM block of the current tile (registers).  The weighted sums over the tiles of a
+    // work item live in shared memory (Z): each thread owns 16 private slots there, so no synchronisation
+    // is needed until the item is flushed -- and 32 registers are freed for the DMMA pipeline.
+    double acc[2][4][2];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-            acc[a][nb][0] = acc[a][nb][1] = 0.0;
-            out[a][nb][0] = out[a][nb][1] = 0.0;
-        }
-    int c_item = blockIdx.x, c_tile = 0, c_tile_end = 0, c_ks = 0;
-    if (c_item < p.nitems) item_range(c_item, c_tile, c_tile_end);
-
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) loader_issue(s);
+        for (int nn = 0; nn < 4; ++nn) acc[a][nn][0] = acc[a][nn][1] = 0.0;
+    StepState cs;
+    cs.init(p);
 
     // per-thread constant parts of the swizzled A-fragment addresses
-    const int a_row0 = MMAJOR ? (warp * 4096 + (((g >> 1)) << 4) + (g & 1) * 8)        // a = 0: i_off = g
-                              : ((16 * warp + pg) * 128 + (t4 & 1) * 8);
-    const int tp = MMAJOR ? 0 : ((t4 >> 1) ^ pg);
+    const int a_base = MMAJOR ? (rg * (TK * 128) + (g & 1) * 8) : ((16 * rg + pg) * 128 + (t4 & 1) * 8);
+    const int tp = (t4 >> 1) ^ pg;
+    const int colbase = 32 * cg;   // first column of this warp's block
+    double *zrow0 = Z + (16 * rg + pg) * C::ZSTR + colbase + 2 * t4;   // this thread's slots: rows q, q+8; 4 column pairs
+    double *zrow1 = zrow0 + 8 * C::ZSTR;
+#pragma unroll
+    for (int nn = 0; nn < 4; ++nn) {
+        zrow0[8 * nn] = zrow0[8 * nn + 1] = 0.0;
+        zrow1[8 * nn] = zrow1[8 * nn + 1] = 0.0;
+    }
 
     int stage = 0;
     uint32_t phase = 0;
-    while (c_item < p.nitems) {
-        cp_async_wait<STAGES - 2>();
+    while (cs.active(p)) {
         mbar_wait(&full[stage], phase);
-        __syncthreads();
-        loader_issue((stage + STAGES - 1) % STAGES);
-
         {
-            const uint8_t *Xb = base + stage * STAGE_BYTES;
-            const double *Us = reinterpret_cast<const double *>(Xb + XSTAGE_BYTES);
+            const uint8_t *Xb = base + stage * C::STAGE_BYTES;
+            const double *Us = reinterpret_cast<const double *>(Xb + C::XBYTES) + colbase;
 #pragma unroll
-            for (int s8 = 0; s8 < BK / 4; ++s8) {
+            for (int s4 = 0; s4 < TK / 4; ++s4) {
                 double a0, a1;
                 int brow;
                 if (MMAJOR) {
-                    const int kk8 = 8 * (s8 >> 1), h = s8 & 1;
-                    const int k = kk8 + 2 * t4 + h;      // k & 7 == 2*t4 + h
-                    const int x = 2 * t4 + h;
-                    // element (l_off = warp, k, i_off = 8a + g): chunk (4a + (g>>1)) ^ x
-                    const int c0 = ((g >> 1) ^ x) << 4;
-                    const int c1 = ((4 + (g >> 1)) ^ x) << 4;
-                    a0 = *reinterpret_cast<const double *>(Xb + warp * 4096 + k * 128 + c0 + (g & 1) * 8);
-                    a1 = *reinterpret_cast<const double *>(Xb + warp * 4096 + k * 128 + c1 + (g & 1) * 8);
+                    const int kk8 = 8 * (s4 >> 1), h = s4 & 1;
+                    const int x = 2 * t4 + h;            // == k & 7
+                    const int k = kk8 + x;
+                    // element (row group rg, k, i_off = 8a + g): chunk (4a + (g>>1)) ^ x
+                    a0 = *reinterpret_cast<const double *>(Xb + a_base + k * 128 + (((g >> 1) ^ x) << 4));
+                    a1 = *reinterpret_cast<const double *>(Xb + a_base + k * 128 + (((4 + (g >> 1)) ^ x) << 4));
                     brow = kk8 + 4 * h + t4;
                 } else {
-                    const int kk = 4 * s8;
-                    const int off = (kk >> 4) * (XSTAGE_BYTES / 2) + ((((kk & 15) >> 1) ^ tp) << 4);
-                    a0 = *reinterpret_cast<const double *>(Xb + a_row0 + off);
-                    a1 = *reinterpret_cast<const double *>(Xb + a_row0 + 8 * 128 + off);
+                    const int kk = 4 * s4;
+                    const int off = ((kk >> 1) ^ tp) << 4;
+                    a0 = *reinterpret_cast<const double *>(Xb + a_base + off);
+                    a1 = *reinterpret_cast<const double *>(Xb + a_base + 8 * 128 + off);
                     brow = kk + t4;
                 }
 #pragma unroll
-                for (int nb = 0; nb < NB; ++nb) {
-                    const double b = Us[brow * RS + 8 * nb + g];
-                    dmma884(acc[0][nb][0], acc[0][nb][1], a0, b);
-                    dmma884(acc[1][nb][0], acc[1][nb][1], a1, b);
+                for (int nn = 0; nn < 4; ++nn) {
+                    if (nn < nbw) {
+                        const double b = Us[brow * RS + 8 * nn + g];
+                        dmma884(acc[0][nn][0], acc[0][nn][1], a0, b);
+                        dmma884(acc[1][nn][0], acc[1][nn][1], a1, b);
+                    }
                 }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);   // this warp is done reading the slot
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
 
-        if (++c_ks == p.nk) {
-            c_ks = 0;
+        if (++cs.ks == p.nk) {
+            cs.ks = 0;
             {
-                const int it = c_item / p.nsplit;
-                const int lt = c_tile / p.ntt, tt = c_tile % p.ntt;
+                // ---- tile epilogue: out += acc * prod_m U_m[i_m(row), col]   (the Khatri-Rao rows, on the fly)
+                const int it = cs.item / p.nsplit;
+                const int lt = cs.tile / p.ntt, tt = cs.tile % p.ntt;
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
-                    const int q = 16 * warp + 8 * a + pg;
+                    const int q = 16 * rg + 8 * a + pg;
                     int l, i, t;
                     const bool ok = decompose(q, it, lt, tt, l, i, t);
-                    double wgt[NB][2];
+                    double wgt[4][2];
 #pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) wgt[nb][0] = wgt[nb][1] = ok ? 1.0 : 0.0;
+                    for (int nn = 0; nn < 4; ++nn) wgt[nn][0] = wgt[nn][1] = ok ? 1.0 : 0.0;
                     if (ok) {
                         for (int m = 0; m < p.nw; ++m) {
                             const int sp = p.w[m].space ? t : l;
                             const int idx = (sp / p.w[m].div) % p.w[m].dim;
-                            const double *row = p.w[m].U + (long long)idx * p.ld;
+                            const double *row = p.w[m].U + (long long)idx * p.ld + colbase;
 #pragma unroll
-                            for (int nb = 0; nb < NB; ++nb) {
-                                const int col = 8 * nb + 2 * t4;
-                                if (col < p.R) wgt[nb][0] *= __ldg(row + col);
-                                if (col + 1 < p.R) wgt[nb][1] *= __ldg(row + col + 1);
+                            for (int nn = 0; nn < 4; ++nn) {
+                                const int col = colbase + 8 * nn + 2 * t4;
+                                if (col < p.R) wgt[nn][0] *= __ldg(row + 8 * nn + 2 * t4);
+                                if (col + 1 < p.R) wgt[nn][1] *= __ldg(row + 8 * nn + 2 * t4 + 1);
                             }
                         }
                     }
+                    double *zr = a ? zrow1 : zrow0;
 #pragma unroll
-                    for (int nb = 0; nb < NB; ++nb) {
-                        out[a][nb][0] += ok ? wgt[nb][0] * acc[a][nb][0] : 0.0;
-                        out[a][nb][1] += ok ? wgt[nb][1] * acc[a][nb][1] : 0.0;
-                        acc[a][nb][0] = acc[a][nb][1] = 0.0;
+                    for (int nn = 0; nn < 4; ++nn) {
+                        if (ok) {
+                            zr[8 * nn] += wgt[nn][0] * acc[a][nn][0];
+                            zr[8 * nn + 1] += wgt[nn][1] * acc[a][nn][1];
+                        }
+                        acc[a][nn][0] = acc[a][nn][1] = 0.0;
                     }
                 }
             }
-            if (++c_tile == c_tile_end) {
-                const int it = c_item / p.nsplit, s = c_item % p.nsplit;
+            if (++cs.tile == cs.tile_end) {
+                // ---- item flush: sum rows of equal i_n in a fixed order, write bi x R outputs
+                const int it = cs.item / p.nsplit, s = cs.item % p.nsplit;
                 double *dst = p.out + (long long)s * p.out_split_stride;
-                constexpr int NH = (NB + 3) / 4;
-#pragma unroll
-                for (int h = 0; h < NH; ++h) {
-#pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        const int q = 16 * warp + 8 * a + pg;
-#pragma unroll
-                        for (int nn = 0; nn < 4; ++nn) {
-                            const int nb = 4 * h + nn;
-                            if (nb < NB) {
-                                Z[q * ZS + 8 * nn + 2 * t4] = out[a][nb][0];
-                                Z[q * ZS + 8 * nn + 2 * t4 + 1] = out[a][nb][1];
-                                out[a][nb][0] = out[a][nb][1] = 0.0;
+                named_bar_sync(1, TCONS);
+                for (int o = tid; o < bi * C::ZC; o += TCONS) {
+                    const int i_off = o / C::ZC, col = o % C::ZC;
+                    const int i = it * bi + i_off;
+                    if (col < p.R && i < p.In) {
+                        double sum = 0.0;
+                        for (int l_off = 0; l_off < bl; ++l_off)
+                            for (int t_off = 0; t_off < bt; ++t_off) {
+                                const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
+                                sum += Z[q * C::ZSTR + col];
                             }
-                        }
+                        dst[(long long)i * p.ld + col] = sum;
                     }
-                    __syncthreads();
-                    for (int o = tid; o < bi * 32; o += NTHREADS) {
-                        const int i_off = o >> 5, c = o & 31;
-                        const int col = 32 * h + c;
-                        const int i = it * bi + i_off;
-                        if (col < p.R && col < 8 * NB && i < p.In) {
-                            double sum = 0.0;
-                            for (int l_off = 0; l_off < bl; ++l_off)
-                                for (int t_off = 0; t_off < bt; ++t_off) {
-                                    const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
-                                    sum += Z[q * ZS + c];
-                                }
-                            dst[(long long)i * p.ld + col] = sum;
-                        }
-                    }
-                    __syncthreads();
                 }
-                c_item += gridDim.x;
-                if (c_item < p.nitems) item_range(c_item, c_tile, c_tile_end);
+                named_bar_sync(1, TCONS);
+#pragma unroll
+                for (int nn = 0; nn < 4; ++nn) {
+                    zrow0[8 * nn] = zrow0[8 * nn + 1] = 0.0;
+                    zrow1[8 * nn] = zrow1[8 * nn + 1] = 0.0;
+                }
+                cs.item += gridDim.x;
+                if (cs.active(p)) cs.range(p);
             }
         }
     }
-    cp_async_wait<0>();
 }
 
 // M[e] = sum_s P[s][e] in split order (deterministic)
@@ -619,6 +653,7 @@ struct DensePlan {
     int nw;
     int wmode[SKT_MAX_NDIM], wdim[SKT_MAX_NDIM], wdiv[SKT_MAX_NDIM], wspace[SKT_MAX_NDIM];
     int grid;
+    int bm;  // rows per tile
 };
 
 int ilog2(int x) {
@@ -628,6 +663,11 @@ int ilog2(int x) {
 }
 
 int make_plan(const int64_t *shape, int ndim, int rank, int mode, bool tma, DensePlan &pl) {
+    // rows per tile: 128 for the cp.async kernel; the TMA kernel uses 256 (rank <= 32 per pass) or 128
+    const int ncol = std::min(rank, 64);
+    const int lgbm = tma ? ((ncol <= 32) ? 8 : 7) : 7;
+    const int bm = 1 << lgbm;
+    pl.bm = bm;
     SKT_REQUIRE(shape != nullptr, SKT_EINVAL, "shape is NULL");
     SKT_REQUIRE(ndim >= 2 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "ndim must be in [2, %d], got %d", SKT_MAX_NDIM, ndim);
     SKT_REQUIRE(mode >= 0 && mode < ndim, SKT_EINVAL, "mode %d out of range for a %d-way tensor", mode, ndim);
@@ -666,16 +706,16 @@ int make_plan(const int64_t *shape, int ndim, int rank, int mode, bool tma, Dens
     // ties go to the longest contiguous run (bt for K-major, bi for M-major).
     double best = 1e300;
     int bbt = 0, bbi = 0, bbl = 0;
-    for (int lt = 0; lt <= 7; ++lt)
-        for (int li = 0; li + lt <= 7; ++li) {
-            const int ll = 7 - lt - li;
+    for (int lt = 0; lt <= lgbm; ++lt)
+        for (int li = 0; li + lt <= lgbm; ++li) {
+            const int ll = lgbm - lt - li;
             const long long bt = 1LL << lt, bi = 1LL << li, bl = 1LL << ll;
             if (pl.mmajor && lt != 0) continue;
-            if (pl.mmajor && tma && !(li == 4 && ll == 3)) continue;  // the M-major TMA box is fixed: 16 i x 8 l
+            if (pl.mmajor && tma && li != 4) continue;  // the M-major TMA box is fixed: 16 i per row group
             const double padded = (double)((T + bt - 1) / bt * bt) * (double)((pl.In + bi - 1) / bi * bi) *
                                   (double)((L + bl - 1) / bl * bl);
             // prefer (slightly) boxes whose inner run is long: fewer DRAM page switches
-            const double score = padded * (1.0 + 1e-3 * (pl.mmajor ? (7 - li) : (7 - lt)) + 1e-5 * ll);
+            const double score = padded * (1.0 + 1e-3 * (pl.mmajor ? (lgbm - li) : (lgbm - lt)) + 1e-5 * ll);
             if (score < best) { best = score; bbt = lt; bbi = li; bbl = ll; }
         }
     pl.lg_bt = bbt; pl.lg_bi = bbi; pl.lg_bl = bbl;
@@ -688,7 +728,7 @@ int make_plan(const int64_t *shape, int ndim, int rank, int mode, bool tma, Dens
     // split the reduction space so that the static round-robin schedule over the SMs is balanced
     // without drowning the memory system in partial slabs.
     const int G = sm_count();
-    const double tile_cost = (double)BM * pl.Kc * G;          // elements streamed, in chip-bandwidth units
+    const double tile_cost = (double)bm * pl.Kc * G;          // elements streamed, in chip-bandwidth units
     const double slab_cost = 2.0 * (double)pl.In * rank;      // write + re-read of one partial slab
     double best_cost = 1e300;
     int best_ns = 1;
@@ -785,7 +825,7 @@ int make_tensor_map(const double *X, const DensePlan &pl, CUtensorMap &tm) {
         dims[0] = pl.In; dims[1] = pl.L; dims[2] = pl.Kc;
         strides[0] = (cuuint64_t)pl.In * 8;
         strides[1] = strides[0] * pl.L;
-        box[0] = 16; box[1] = 1; box[2] = BK;
+        box[0] = 16; box[1] = 1; box[2] = TK;
     }
     const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<double *>(X), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -796,16 +836,13 @@ int make_tensor_map(const double *X, const DensePlan &pl, CUtensorMap &tm) {
 
 template <int NB, bool MMAJOR>
 int launch_dense_tma(const CUtensorMap &tm, const DenseParams &p, int grid, cudaStream_t st) {
-    constexpr int STAGES = (NB <= 4) ? 4 : 3;
-    constexpr int RS = 8 * NB + 4;
-    constexpr int USTAGE_BYTES = (BK * RS * 8 + 1023) / 1024 * 1024;
-    const size_t smem = (size_t)STAGES * (XSTAGE_BYTES + USTAGE_BYTES) + (size_t)BM * ZS * 8 + STAGES * 8 + 1024;
+    const size_t smem = TmaCfg<NB>::SMEM;
     static bool configured = false;
     if (!configured) {
         SKT_CUDA(cudaFuncSetAttribute(mttkrp_dense_tma_kernel<NB, MMAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    mttkrp_dense_tma_kernel<NB, MMAJOR><<<grid, NTHREADS, smem, st>>>(tm, p);
+    mttkrp_dense_tma_kernel<NB, MMAJOR><<<grid, TTHREADS, smem, st>>>(tm, p);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
 }
@@ -883,7 +920,7 @@ extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndi
     p.lg_bt = pl.lg_bt; p.lg_bi = pl.lg_bi; p.lg_bl = pl.lg_bl;
     p.nit = pl.nit; p.ntt = pl.ntt; p.nred = pl.nred;
     p.nsplit = pl.nsplit; p.chunk = pl.chunk; p.nitems = pl.nitems;
-    p.nk = (pl.Kc + BK - 1) / BK;
+    p.nk = use_tma ? (pl.Kc + TK - 1) / TK : (pl.Kc + BK - 1) / BK;
     p.nw = pl.nw;
     p.out_split_stride = (pl.nsplit > 1) ? (long long)pl.In * rank : 0;
     double *outbase = (pl.nsplit > 1) ? (double *)ws_d : M_d;
@@ -903,8 +940,11 @@ extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndi
         }
         p.vecU = ((((uintptr_t)p.Uc) & 15) == 0) && (rank % 2 == 0) && (ncol % 2 == 0);
         const int nb = (ncol + 7) / 8;
-        if (use_tma)
-            rc = pl.mmajor ? launch_dense_tma_nb<true>(nb, tm, p, pl.grid, st) : launch_dense_tma_nb<false>(nb, tm, p, pl.grid, st);
+        if (use_tma) {
+            // the tile height is fixed by the plan: 128-row tiles always run the two-column-group kernels
+            const int nbk = (pl.bm == 128) ? std::max(nb, 5) : nb;
+            rc = pl.mmajor ? launch_dense_tma_nb<true>(nbk, tm, p, pl.grid, st) : launch_dense_tma_nb<false>(nbk, tm, p, pl.grid, st);
+        }
         else
             rc = pl.mmajor ? launch_dense_nb<true>(nb, p, pl.grid, st) : launch_dense_nb<false>(nb, p, pl.grid, st);
         if (rc != SKT_OK) return rc;
