@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Benchmark of the CP-ALS hot path (BASELINE.json: "MTTKRP GB/s (% HBM roofline) and CP-ALS
+iters/sec at 1/2/4/8 B200").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload dense|sparse]
+
+One "step" is one full CP-ALS iteration on the workload -- for every mode the fused MTTKRP,
+the Hadamard-of-Grams pseudo-inverse, the factor update/normalisation, and the fit -- i.e. the
+loop body of the reference's cp.als (sktensor/cp.py:138-169).
+
+Workload at N = 1: BASELINE.json configs[1], "cp_als dense 3-way 512x512x512 rank 32, FP64".
+For N > 1 (launched by torch.distributed.run, one rank per GPU, NCCL) the tensor is
+(512 N) x 512 x 512, cut along mode 0 so that every GPU keeps a 512^3 slab: weak scaling.
+
+`value` (GB/s) = algorithmic MTTKRP bytes of one iteration, sum over modes of
+8 (prod I + R sum I), summed over all ranks' slabs, divided by the time of the WHOLE iteration
+(solves and fit included), tensor resident in HBM.  `als_iters_per_sec` is the same clock.
+`e2e` is the same metric through the public API, cp_als(dtensor(host ndarray), ...): host
+tensor upload, initial factor upload, per-iteration fit read-back and final factor download
+all inside the timed region.  `roofline` describes the dominant kernel (the dense MTTKRP),
+timed with CUDA events around each of its launches inside the timed iterations.
+
+`--impl reference` times the reference's own algorithm (the NumPy restatement in oracle/, the
+reference being pure Python that cannot travel to the GPU box) on the host cores, on a
+bounded 256^3 sub-cube of the same workload, reported in the same unit.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, 'scikit-tensor_b200'), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = 'cp_als_mttkrp_GBps'
+UNIT = 'GB/s'
+SIDE, RANK = 512, 32                       # BASELINE.json configs[1]
+SAMPLE_SIDE = 256                          # CPU sample: 1/8 of the tensor
+SPARSE_SHAPE = (10000000, 1000000, 100000)  # BASELINE.json configs[2]
+
+
+def alg_bytes_dense(shape, R):
+    """Algorithmic bytes of one dense MTTKRP: X once + the N-1 factors + the output."""
+    return 8.0 * (float(np.prod([float(s) for s in shape])) + R * float(sum(shape)))
+
+
+def alg_bytes_sparse(shape, nnz, R):
+    """int32 subscripts + FP64 value per non-zero, every factor row once, output once."""
+    return float(nnz) * (4 * len(shape) + 8) + 8.0 * R * float(sum(shape))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thr = threading.Thread(target=self._read, daemon=True)
+        self.thr.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_sample(steps=1):
+    """The reference algorithm (oracle port) on a 256^3 sub-cube: seconds per ALS iteration."""
+    from oracle import sktensor_oracle as orc
+    rng = np.random.RandomState(0)
+    X = rng.rand(SAMPLE_SIDE, SAMPLE_SIDE, SAMPLE_SIDE)
+    np.random.seed(1)
+    _, _, _, _, ex = orc.cp_als(X, RANK, init='random', max_iter=steps, conv=0)
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count()
+    return np.asarray(ex), cores
+
+
+def cpu_baseline_obj(ex, cores):
+    per = float(np.mean(ex))
+    b = 3 * alg_bytes_dense((SAMPLE_SIDE,) * 3, RANK)
+    return {'value': b / per / 1e9, 'unit': UNIT, 'cores': int(cores), 'kind': 'port',
+            'als_iters_per_sec_on_sample': 1.0 / per,
+            'sample': 'oracle/sktensor_oracle.cp_als (NumPy restatement of sktensor/cp.py:46-171), %d iteration(s) '
+                      'on a %d^3 rank-%d sub-cube (1/8 of the 512^3 workload); GB/s uses the same algorithmic '
+                      'byte count per iteration; BLAS threads = cores, the rest of the algorithm is single-threaded'
+                      % (len(ex), SAMPLE_SIDE, RANK)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    total = args.warmup + args.steps
+    # keep the whole run within a few minutes: an iteration of the sample takes a few seconds
+    warm = min(args.warmup, 1)
+    steps = max(1, min(args.steps, 8))
+    ex, cores = cpu_sample(warm + steps)
+    ex = ex[warm:]
+    cb = cpu_baseline_obj(ex, cores)
+    line = {
+        'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'impl': 'reference', 'n_gpus': args.gpus,
+        'steps': int(len(ex)), 'warmup': int(warm), 'requested_steps': args.steps, 'requested_warmup': args.warmup,
+        'ms_per_step': float(np.mean(ex)) * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'cp_als dense 3-way 512x512x512 rank 32 FP64 (BASELINE.json configs[1])',
+                   'note': 'CPU arm runs a bounded 256^3 sample of this workload; GB/s is size-normalised'},
+        'als_iters_per_sec': cb['als_iters_per_sec_on_sample'] / 8.0,
+        'als_iters_per_sec_note': 'sample rate / 8 (linear in tensor volume)',
+        'cpu_baseline': cb,
+        'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from sktensor import _lib, _parallel, cp_als, dtensor
+    from sktensor import _device as dev
+
+    lib = _lib.load()
+    R = RANK
+    gshape = (SIDE * world, SIDE, SIDE)
+    lshape = (SIDE, SIDE, SIDE)
+    offsets = np.arange(world + 1, dtype=np.int64) * SIDE
+    rng = np.random.RandomState(1000 + rank)
+    Xh = rng.rand(*lshape)                                  # this rank's slab (host, pageable like a user's array)
+
+    def make_input():
+        if world == 1:
+            return dtensor(Xh)
+        return _parallel.LocalShard(dtensor(Xh), 0, gshape, offsets)
+
+    def init_factors():
+        np.random.seed(1)                                    # same stream on every rank (cp.py:197-199)
+        return [None] + [np.random.rand(gshape[n], R) for n in range(1, 3)]
+
+    # ---- device-resident arm: the engine behind cp_als, X uploaded once, outside the timed region
+    class TimedBackend(_parallel.CudaBackend):
+        def __init__(self):
+            _parallel.CudaBackend.__init__(self)
+            self.events, self.record = [], False
+
+        def mttkrp_dense(self, Xd, shape, U, R_, n, out):
+            if not self.record:
+                return _parallel.CudaBackend.mttkrp_dense(self, Xd, shape, U, R_, n, out)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = _parallel.CudaBackend.mttkrp_dense(self, Xd, shape, U, R_, n, out)
+            e1.record()
+            self.events.append((n, e0, e1))
+            return r
+
+    be = TimedBackend()
+    eng = _parallel.CpAlsEngine(make_input(), R, init_factors(), backend=be)
+    W = max(args.warmup, 3)
+    for w in range(W):
+        eng.sweep(first_iter=(w == 0))
+        eng.read_fit()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    be.record = True
+    launches0 = lib.skt_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    fit = 0.0
+    for _ in range(args.steps):
+        eng.sweep(first_iter=False)
+        fit = eng.read_fit()
+    t1.record()
+    torch.cuda.synchronize()
+    launches = lib.skt_launch_count() - launches0
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    be.record = False
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    iter_bytes = sum(alg_bytes_dense(gshape, R) for _ in range(3))      # whole job, all ranks' slabs
+    value = iter_bytes / (ms_step * 1e-3) / 1e9
+
+    # ---- dominant kernel: per-launch durations of the dense MTTKRP inside the timed iterations
+    durs = {}
+    for n, e0, e1 in be.events:
+        durs.setdefault(n, []).append(e0.elapsed_time(e1))
+    all_d = [d for v in durs.values() for d in v]
+    kbytes = alg_bytes_dense(lshape, R)                                   # one launch handles one slab
+    kern_ms = float(np.mean(all_d))
+    hbm_peak, peak_src = measured_peaks()
+    dmma_tf, dfma_tf = (0.0, 0.0)
+    if rank == 0:
+        from sktensor import _kernels as K
+        dmma_tf, dfma_tf = K.probe_fp64_peaks()
+    kflops = 2.0 * R * float(np.prod([float(s) for s in lshape]))
+    t_roof = max(kbytes / (hbm_peak * 1e9), kflops / (dmma_tf * 1e12)) if dmma_tf else kbytes / (hbm_peak * 1e9)
+    traffic = None
+    prof = os.path.join(ROOT, 'profiles', 'dense_mttkrp_traffic.json')
+    if os.path.exists(prof):
+        with open(prof) as f:
+            traffic = json.load(f).get('dram_bytes_per_launch')
+    roofline = {
+        'kernel': 'mttkrp_dense_tma_kernel (dense FP64 MTTKRP, one mode of the 512^3 slab)',
+        'bound': 'hbm', 'achieved': kbytes / (kern_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+        'frac': kbytes / (kern_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
+        'alg_bytes_per_launch': kbytes, 'avg_launch_ms': kern_ms,
+        'per_mode_ms': {str(n): float(np.mean(v)) for n, v in sorted(durs.items())},
+        'share_of_step': float(sum(all_d)) / ms_total if world == 1 else None,
+        'fp64': {'note': 'rank 32 makes the kernel FP64-tensor-pipe bound (AI 8 flop/B vs ridge %.1f): '
+                         'the binding roofline is the DMMA peak measured by skt_probe_fp64_peaks' %
+                         ((dmma_tf * 1e12) / (hbm_peak * 1e9) if dmma_tf else float('nan')),
+                 'achieved_tflops': kflops / (kern_ms * 1e-3) / 1e12, 'peak_tflops_dmma': dmma_tf,
+                 'peak_tflops_dfma': dfma_tf,
+                 'frac': (kflops / (kern_ms * 1e-3) / 1e12 / dmma_tf) if dmma_tf else None},
+        'frac_of_binding_roofline': t_roof / (kern_ms * 1e-3),
+    }
+    del eng
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm: the public call a user makes, host buffers in, host factors out
+    K2 = max(2, min(args.steps, 10))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    np.random.seed(1)
+    tic = time.perf_counter()
+    P, fit2, itr, _ = cp_als(make_input(), R, init='random', max_iter=K2, conv=0)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - tic
+    e2e = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e.item())
+    h2d = (Xh.nbytes + 8 * R * (gshape[1] + gshape[2])) / float(K2)
+    d2h = (8 * R * sum(gshape) + 8 * R) / float(K2) + 16 + 4 * 3
+    e2e_obj = {'value': iter_bytes * K2 / e2e_s / 1e9, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'als_iters_per_sec': K2 / e2e_s, 'iterations': K2,
+               'call': "cp_als(dtensor(X_host), 32, init='random', max_iter=%d, conv=0)" % K2,
+               'note': 'whole call: pageable-host tensor upload (once per call), factor upload, per-iteration '
+                       'fit read-back, final factor download; bytes are per iteration (upload amortised over '
+                       '%d iterations)' % K2}
+
+    if rank == 0:
+        ex, cores = cpu_sample(2)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': W,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'cp_als dense 3-way 512x512x512 rank 32 FP64 (BASELINE.json configs[1])'
+                                   + ('' if world == 1 else '; weak scaling: %dx512x512 cut along mode 0, one 512^3 slab per GPU' % gshape[0]),
+                       'shape': list(gshape), 'rank': R, 'init': 'random', 'fit_method': 'full',
+                       'parallelism': 'mode0-shard x%d' % world,
+                       'cache': 'tensor slab 1.07 GB per GPU >> 126 MB L2: every iteration streams it from HBM 3 times'},
+            'als_iters_per_sec': 1e3 / ms_step, 'final_fit': fit,
+            'clocks': clocks, 'e2e': e2e_obj, 'gpu_launches': int(launches),
+            'roofline': roofline, 'cpu_baseline': cpu_baseline_obj(ex, cores),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_sparse(args):
+    """Secondary bench (not the driver's line): BASELINE.json configs[2] generator, scaled by --nnz."""
+    import torch
+    from sktensor import _kernels as K
+    from sktensor import _device as dev
+    nnz, R = args.nnz, 16
+    rng = np.random.default_rng(0)
+    subs = [np.minimum((I * rng.random(nnz) ** 3.0).astype(np.int64), I - 1) for I in SPARSE_SHAPE]
+    vals = rng.random(nnz)
+    tic = time.perf_counter()
+    coo = K.CooHandle(subs, vals, SPARSE_SHAPE)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - tic
+    U = [torch.rand(s, R, dtype=torch.float64, device='cuda') for s in SPARSE_SHAPE]
+    hbm_peak, peak_src = measured_peaks()
+    out = {'metric': 'sparse_mttkrp_GBps', 'unit': UNIT, 'nnz': nnz, 'rank': R, 'shape': list(SPARSE_SHAPE),
+           'build_seconds': build_s, 'device_bytes': coo.device_bytes(), 'modes': {}}
+    for n in range(3):
+        M = dev.empty((SPARSE_SHAPE[n], R))
+        for _ in range(3):
+            K.mttkrp_coo(coo, U, R, n, out=M)
+        ts = []
+        for _ in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            K.mttkrp_coo(coo, U, R, n, out=M)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = float(np.median(ts))
+        b = alg_bytes_sparse(SPARSE_SHAPE, nnz, R)
+        out['modes'][str(n)] = {'ms': ms, 'GBps_algorithmic': b / ms / 1e6, 'frac_of_hbm': b / ms / 1e6 / hbm_peak,
+                                'Mnnz_per_s': nnz / ms / 1e3}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='dense', choices=['dense', 'sparse'])
+    ap.add_argument('--nnz', type=int, default=20000000)
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    if args.workload == 'sparse':
+        return run_sparse(args)
+    return run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

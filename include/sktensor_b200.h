@@ -53,6 +53,8 @@ typedef void *skt_stream;
 /* ---------------------------------------------------------------- library / device */
 SKT_API int         skt_version(void);
 SKT_API const char *skt_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+SKT_API uint64_t skt_launch_count(void);
 /* SM count, compute capability and opt-in shared memory of the current device. */
 SKT_API int skt_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
 

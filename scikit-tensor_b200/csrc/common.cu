@@ -8,6 +8,7 @@
 namespace skt {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -84,6 +85,8 @@ __global__ void probe_dfma_kernel(double *out, int iters) {
 using namespace skt;
 
 extern "C" int skt_version(void) { return 100; }
+
+extern "C" uint64_t skt_launch_count(void) { return g_launches; }
 
 extern "C" const char *skt_last_error(void) { return g_err; }
 

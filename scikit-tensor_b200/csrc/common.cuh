@@ -30,8 +30,13 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         }                                                                      \
     } while (0)
 
-// Launch-error check that does not synchronise.
-#define SKT_LAUNCH_CHECK() SKT_CUDA(cudaGetLastError())
+// Launch-error check that does not synchronise; also counts the launch (skt_launch_count()).
+extern unsigned long long g_launches;
+#define SKT_LAUNCH_CHECK()            \
+    do {                              \
+        ++skt::g_launches;            \
+        SKT_CUDA(cudaGetLastError()); \
+    } while (0)
 
 int sm_count();            // SMs of the current device (cached)
 size_t smem_optin_bytes(); // max opt-in dynamic shared memory per block (cached)

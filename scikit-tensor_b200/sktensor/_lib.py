@@ -27,6 +27,7 @@ c_stream = C.c_void_p
 PROTOTYPES = {
     'skt_version': (C.c_int, []),
     'skt_last_error': (C.c_char_p, []),
+    'skt_launch_count': (C.c_uint64, []),
     'skt_device_info': (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_size_t)]),
     'skt_mttkrp_dense_workspace': (C.c_size_t, [c_i64p, C.c_int, C.c_int, C.c_int]),
