@@ -73,11 +73,18 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.index, self.rows, self.proc, self.thr = index, [], None, None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '25'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -87,7 +94,7 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
 
     def stop(self):
         if self.proc is None:
@@ -99,7 +106,12 @@ class ClockSampler(object):
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if self.t_begin is not None and self.t_begin <= t <= self.t_end + 0.05]
+        window = 'timed region'
+        if len(inside) < 3:      # a very short timed region: fall back to every sample taken under load
+            inside = [r for (t, r) in self.rows]
+            window = 'warm-up + timed region (timed region shorter than 3 sampling periods)'
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -109,7 +121,7 @@ class ClockSampler(object):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'window': window, 'reasons': sorted(reasons)}
 
 
 def cpu_sample(steps=1):
@@ -213,19 +225,21 @@ def run_gpu(args):
     be = TimedBackend()
     eng = _parallel.CpAlsEngine(make_input(), R, init_factors(), backend=be)
     W = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)          # let nvidia-smi come up so that samples exist from the warm-up on
     for w in range(W):
         eng.sweep(first_iter=(w == 0))
         eng.read_fit()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     be.record = True
     launches0 = lib.skt_launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    sampler.mark_begin()
     t0.record()
     fit = 0.0
     for _ in range(args.steps):
@@ -233,6 +247,7 @@ def run_gpu(args):
         fit = eng.read_fit()
     t1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     launches = lib.skt_launch_count() - launches0
     ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -365,7 +380,7 @@ def run_sparse(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='dense', choices=['dense', 'sparse'])

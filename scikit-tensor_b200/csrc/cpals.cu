@@ -245,6 +245,68 @@ __global__ void __launch_bounds__(1024) hadamard_pinv_kernel(const double *__res
         if (tid == 0) info[0] = -1;
         return;
     }
+
+    // ---- fast path: Y is a Hadamard product of Grams, hence symmetric positive semi-definite.  When an
+    // unpivoted Cholesky factorisation sees no small pivot (pivot > 1e-7 * largest diagonal entry) Y is far
+    // from the pinv cut-off (R * eps * sigma_max), the pseudo-inverse is the inverse, and it is formed as
+    // L^-T L^-1 in a few microseconds.  Anything closer to singular takes the Jacobi route below, which
+    // implements scipy.linalg.pinv's truncation exactly.
+    {
+        __shared__ double dg[MAXR];
+        __shared__ int chol_fail;
+        __shared__ double maxdiag;
+        // V temporarily holds the factor: A(i,j) == V[j][i]
+        for (int e = tid; e < R * R; e += nthreads) V[e % R][e / R] = W[e % R][e / R];
+        if (tid == 0) {
+            double mx = 0.0;
+            for (int j = 0; j < R; ++j) mx = fmax(mx, W[j][j]);
+            maxdiag = mx;
+            chol_fail = (mx > 0.0) ? 0 : 1;
+        }
+        __syncthreads();
+        const double thr = 1e-7 * maxdiag;
+        bool fail = chol_fail != 0;
+        for (int k = 0; k < R && !fail; ++k) {
+            const double d = V[k][k];           // final after the previous trailing update
+            if (!(d > thr)) { fail = true; break; }   // same value in every thread: uniform exit
+            const double sd = sqrt(d);
+            if (tid == 0) dg[k] = sd;
+            for (int i = k + 1 + tid; i < R; i += nthreads) V[k][i] = V[k][i] / sd;     // column k of L
+            __syncthreads();
+            const int n = R - k - 1;
+            for (int e = tid; e < n * n; e += nthreads) {
+                const int i = k + 1 + e / n, j = k + 1 + e % n;
+                if (j <= i) V[j][i] -= V[k][i] * V[k][j];
+            }
+            __syncthreads();
+        }
+        if (!fail) {
+            // L^-1, one column per thread (forward substitution), stored in W: Linv(i,j) == W[j][i]
+            __syncthreads();
+            if (tid < R) {
+                const int j = tid;
+                for (int i = 0; i < j; ++i) W[j][i] = 0.0;
+                W[j][j] = 1.0 / dg[j];
+                for (int i = j + 1; i < R; ++i) {
+                    double sum = 0.0;
+                    for (int k = j; k < i; ++k) sum += V[k][i] * W[j][k];
+                    W[j][i] = -sum / dg[i];
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < R * R; e += nthreads) {
+                const int a = e / R, b = e % R;
+                double sum = 0.0;
+                for (int k = max(a, b); k < R; ++k) sum += W[a][k] * W[b][k];
+                P[e] = sum;
+            }
+            if (tid == 0) info[0] = R;
+            return;
+        }
+        __syncthreads();
+        for (int e = tid; e < R * R; e += nthreads) V[e % R][e / R] = (e % R == e / R) ? 1.0 : 0.0;
+        __syncthreads();
+    }
     // scale reference for the "both columns negligible" skip
     if (warp == 0) {
         double mx = 0.0;
