@@ -1,4 +1,5 @@
-"""Worker for tests/test_distributed_gloo.py: one rank of a world_size-N gloo job on CPU."""
+"""Worker for tests/test_distributed_gloo.py (gloo, CPU, NumPy test double) and
+tests/test_gpu_multi.py (nccl, one GPU per rank, CUDA kernels): one rank of a world_size-N job."""
 import json
 import os
 import sys
@@ -18,9 +19,15 @@ from sktensor.sptensor import fromarray  # noqa: E402
 
 def main():
     out_path = sys.argv[1]
-    dist.init_process_group('gloo')
+    mode = sys.argv[2] if len(sys.argv) > 2 else 'gloo'
+    if mode == 'nccl':        # real GPUs: the shipped CUDA backend, one rank per device
+        import torch
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        dist.init_process_group('nccl')
+    else:                     # CPU: gloo + the NumPy test double
+        dist.init_process_group('gloo')
+        _parallel.set_backend_factory(NumpyBackend)
     rank = dist.get_rank()
-    _parallel.set_backend_factory(NumpyBackend)
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'golden.npz'))
     res = {}
 
