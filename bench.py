@@ -178,6 +178,9 @@ def run_reference(args):
 
 
 def run_gpu(args):
+    # keep stdout clean for the single JSON line: libraries (NCCL prints its version banner) go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -231,6 +234,8 @@ def run_gpu(args):
         time.sleep(0.3)          # let nvidia-smi come up so that samples exist from the warm-up on
     for w in range(W):
         eng.sweep(first_iter=(w == 0))
+        eng.begin_read()
+        eng.prefetch_next_sweep()
         eng.read_fit()
     torch.cuda.synchronize()
     if world > 1:
@@ -242,8 +247,10 @@ def run_gpu(args):
     sampler.mark_begin()
     t0.record()
     fit = 0.0
-    for _ in range(args.steps):
+    for _ in range(args.steps):              # the loop body of sktensor.cp.als
         eng.sweep(first_iter=False)
+        eng.begin_read()
+        eng.prefetch_next_sweep()
         fit = eng.read_fit()
     t1.record()
     torch.cuda.synchronize()
@@ -335,7 +342,8 @@ def run_gpu(args):
             'clocks': clocks, 'e2e': e2e_obj, 'gpu_launches': int(launches),
             'roofline': roofline, 'cpu_baseline': cpu_baseline_obj(ex, cores),
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -17,6 +17,7 @@
 // slab that a second tiny kernel adds up -- no atomics, bitwise reproducible.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include <cuda.h>
 
@@ -349,7 +350,7 @@ struct TmaCfg {
     static constexpr int ZSTR = ZC + 2;
     static constexpr int ZBYTES = BMT * ZSTR * 8;
     static constexpr int STAGES = (CG == 1) ? 4 : 6;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + ZBYTES + 2 * STAGES * 8 + 1024;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + ZBYTES + 512 * 8 + 2 * STAGES * 8 + 1024;
 };
 
 // Work schedule shared by the producer and the consumers: CTA b owns items b, b+grid, ...; an item is
@@ -379,7 +380,8 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1 KB alignment
     double *Z = reinterpret_cast<double *>(base + STAGES * C::STAGE_BYTES);
-    uint64_t *full = reinterpret_cast<uint64_t *>(base + STAGES * C::STAGE_BYTES + C::ZBYTES);
+    double *red = reinterpret_cast<double *>(base + STAGES * C::STAGE_BYTES + C::ZBYTES);   // [TCONS] flush scratch
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + TCONS);
     uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x;
@@ -573,17 +575,47 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                 const int it = cs.item / p.nsplit, s = cs.item % p.nsplit;
                 double *dst = p.out + (long long)s * p.out_split_stride;
                 named_bar_sync(1, TCONS);
-                for (int o = tid; o < bi * C::ZC; o += TCONS) {
-                    const int i_off = o / C::ZC, col = o % C::ZC;
-                    const int i = it * bi + i_off;
-                    if (col < p.R && i < p.In) {
+                const int nout = bi * C::ZC;               // outputs of this item
+                const int rows_per_out = bl * bt;          // tile rows that share one output row
+                int parts = 1;                             // threads cooperating on one output (power of two)
+                while (parts * 2 * nout <= TCONS && parts * 2 <= rows_per_out) parts *= 2;
+                if (parts == 1) {
+                    for (int o = tid; o < nout; o += TCONS) {
+                        const int i_off = o / C::ZC, col = o % C::ZC;
+                        const int i = it * bi + i_off;
+                        if (col < p.R && i < p.In) {
+                            double sum = 0.0;
+                            for (int l_off = 0; l_off < bl; ++l_off)
+                                for (int t_off = 0; t_off < bt; ++t_off) {
+                                    const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
+                                    sum += Z[q * C::ZSTR + col];
+                                }
+                            dst[(long long)i * p.ld + col] = sum;
+                        }
+                    }
+                } else {
+                    // two-level ordered sum: `parts` threads each add a contiguous run of rows, then one adds the runs
+                    const int chunk = rows_per_out / parts;
+                    if (tid < nout * parts) {
+                        const int part = tid / nout, o = tid % nout;
+                        const int i_off = o / C::ZC, col = o % C::ZC;
                         double sum = 0.0;
-                        for (int l_off = 0; l_off < bl; ++l_off)
-                            for (int t_off = 0; t_off < bt; ++t_off) {
-                                const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
-                                sum += Z[q * C::ZSTR + col];
-                            }
-                        dst[(long long)i * p.ld + col] = sum;
+                        for (int j = part * chunk; j < (part + 1) * chunk; ++j) {
+                            const int l_off = j >> p.lg_bt, t_off = j & (bt - 1);
+                            const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
+                            sum += Z[q * C::ZSTR + col];
+                        }
+                        red[tid] = sum;
+                    }
+                    named_bar_sync(1, TCONS);
+                    if (tid < nout) {
+                        const int i_off = tid / C::ZC, col = tid % C::ZC;
+                        const int i = it * bi + i_off;
+                        if (col < p.R && i < p.In) {
+                            double sum = 0.0;
+                            for (int part = 0; part < parts; ++part) sum += red[part * nout + tid];
+                            dst[(long long)i * p.ld + col] = sum;
+                        }
                     }
                 }
                 named_bar_sync(1, TCONS);
@@ -662,7 +694,30 @@ int ilog2(int x) {
     return l;
 }
 
+int make_plan_uncached(const int64_t *shape, int ndim, int rank, int mode, bool tma, DensePlan &pl);
+
+// The plan depends only on (shape, rank, mode, variant); CP-ALS asks for the same N plans every sweep.
 int make_plan(const int64_t *shape, int ndim, int rank, int mode, bool tma, DensePlan &pl) {
+    struct Key { int64_t shape[SKT_MAX_NDIM]; int ndim, rank, mode, tma, sms; };
+    struct Entry { Key k; DensePlan pl; bool used; };
+    static thread_local Entry cache[16];
+    static thread_local int next = 0;
+    if (shape == nullptr || ndim < 2 || ndim > SKT_MAX_NDIM) return make_plan_uncached(shape, ndim, rank, mode, tma, pl);
+    Key k;
+    memset(&k, 0, sizeof(k));
+    for (int m = 0; m < ndim; ++m) k.shape[m] = shape[m];
+    k.ndim = ndim; k.rank = rank; k.mode = mode; k.tma = tma ? 1 : 0; k.sms = sm_count();
+    for (int e = 0; e < 16; ++e)
+        if (cache[e].used && memcmp(&cache[e].k, &k, sizeof(k)) == 0) { pl = cache[e].pl; return SKT_OK; }
+    const int rc = make_plan_uncached(shape, ndim, rank, mode, tma, pl);
+    if (rc == SKT_OK) {
+        cache[next].k = k; cache[next].pl = pl; cache[next].used = true;
+        next = (next + 1) % 16;
+    }
+    return rc;
+}
+
+int make_plan_uncached(const int64_t *shape, int ndim, int rank, int mode, bool tma, DensePlan &pl) {
     // rows per tile: 128 for the cp.async kernel; the TMA kernel uses 256 (rank <= 32 per pass) or 128
     const int ncol = std::min(rank, 64);
     const int lgbm = tma ? ((ncol <= 32) ? 8 : 7) : 7;

@@ -91,6 +91,21 @@ class CudaBackend(object):
     def to_host(self, x): return self.dev.to_host(x)
     def empty(self, shape, dtype=np.float64): return self.dev.empty(shape, dtype)
     def zeros(self, shape, dtype=np.float64): return self.dev.zeros(shape, dtype)
+    # small result read-back that does not stall the stream: start now, wait later
+    def async_read(self, tensors):
+        t = self.dev.torch()
+        host = [t.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in tensors]
+        for h, x in zip(host, tensors):
+            h.copy_(x, non_blocking=True)
+        ev = t.cuda.Event()
+        ev.record()
+        return ev, host
+
+    def wait_read(self, handle):
+        ev, host = handle
+        ev.synchronize()
+        return [h.numpy().copy() for h in host]
+
     # tensors
     def upload_dense(self, X): return self.dev.to_device(np.asarray(X))
     def upload_coo(self, subs, vals, shape): return self.K.CooHandle(subs, vals, shape)
@@ -225,6 +240,8 @@ class CpAlsEngine(object):
         self.lam = be.empty((R,))
         self.ip = be.zeros((1,))
         self.fitout = be.zeros((2,))
+        self._m0_ready = False      # True when M[0] already holds the MTTKRP for the coming sweep
+        self._pending = None
 
     @staticmethod
     def _cut(X, s, comm):
@@ -261,7 +278,10 @@ class CpAlsEngine(object):
     def sweep(self, first_iter, want_fit=True):
         be, comm, N = self.be, self.comm, self.N
         for n in range(N):
-            M = self.mttkrp(n)
+            if n == 0 and self._m0_ready:
+                M, self._m0_ready = self.M[0], False
+            else:
+                M = self.mttkrp(n)
             be.hadamard_pinv(self.G, n, self.P, self.info[n:n + 1])
             be.solve_stats(M, self.P, first_iter, self.Ud[n], self.colstat)
             if comm.active and n == self.s:
@@ -279,16 +299,35 @@ class CpAlsEngine(object):
         if want_fit:
             be.cp_fit(self.G, self.lam, self.ip, self.normX2, self.fitout)
 
-    def check_status(self):
-        info = self.be.to_host(self.info)
+    def begin_read(self):
+        """Start copying (fit, status) to the host without stalling the stream."""
+        if hasattr(self.be, 'async_read'):
+            self._pending = self.be.async_read([self.fitout, self.info])
+
+    def prefetch_next_sweep(self):
+        """Enqueue the next sweep's mode-0 MTTKRP now (it reads the current factors and writes only
+        M[0]), so the GPU has work while the host waits for the fit; harmless if no sweep follows."""
+        self.mttkrp(0)
+        self._m0_ready = True
+
+    def _results(self):
+        if self._pending is not None:
+            fitout, info = self.be.wait_read(self._pending)
+            self._pending = None
+            return fitout, info
+        return self.be.to_host(self.fitout), self.be.to_host(self.info)
+
+    def check_status(self, info=None):
+        if info is None:
+            _, info = self._results()
         if (info < 0).any():
             # scipy.linalg.pinv raises exactly this on a non-finite Gram product (cp.py:147)
             raise ValueError('array must not contain infs or NaNs')
 
     def read_fit(self):
-        fit = float(self.be.to_host(self.fitout)[0])
-        self.check_status()
-        return fit
+        fitout, info = self._results()
+        self.check_status(info)
+        return float(fitout[0])
 
     def download(self, U):
         """Write the factors into the caller's list (in place) and return lambda."""

@@ -65,6 +65,9 @@ def als(X, rank, **kwargs):
         tic = time.perf_counter()
         fitold = fit
         eng.sweep(first_iter=(itr == 0), want_fit=(fit_method == 'full'))
+        eng.begin_read()
+        if itr + 1 < maxiter:
+            eng.prefetch_next_sweep()     # keeps the GPU busy across the host's convergence check
         if fit_method == 'full':
             fit = eng.read_fit()          # synchronises; raises ValueError on a non-finite Gram
         else:
