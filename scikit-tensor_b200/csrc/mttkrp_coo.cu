@@ -51,24 +51,45 @@ struct CooParams {
     double *carry_val;  // [2*nCTA][R]
 };
 
-template <int GS, int CPL, int NO>
+// Lane layout.  A group of GS lanes owns S consecutive non-zeros; lane gl of the group owns VPL vectors of
+// VEC columns: column (gl + GS*v)*VEC + e.  VEC = 2 (16-byte factor-row loads) whenever R is even.
+// All groups of a warp run the same number of batches (validity is a predicate, not a loop bound), so every
+// shuffle uses the full warp mask and the compiler is free to hoist the B*NO gathers of a batch above their
+// first use -- that is what keeps ~B*NO 128-byte requests per group in flight.
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+    double v[1];
+    __device__ __forceinline__ void load(const double *p) { v[0] = __ldg(p); }
+};
+template <>
+struct Vec<2> {
+    double v[2];
+    __device__ __forceinline__ void load(const double *p) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+};
+
+template <int GS, int VPL, int VEC, int NO>
 __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ CooParams p) {
-    constexpr int NG = CT / GS;  // groups per CTA
+    constexpr int NG = CT / GS;       // groups per CTA
+    constexpr int CPL = VPL * VEC;    // columns per lane
+    constexpr int RW = GS * CPL;      // staged row width
     extern __shared__ double csm[];
-    // per-CTA carry staging: 2 slots per group
-    int *crow = reinterpret_cast<int *>(csm);                 // [2*NG]
-    double *cval = csm + ((2 * NG * (int)sizeof(int) + 7) / 8);  // [2*NG][GS*CPL]
-    constexpr int RW = GS * CPL;
+    int *crow = reinterpret_cast<int *>(csm);                     // [2*NG] per-CTA carry rows: 2 slots per group
+    double *cval = csm + ((2 * NG * (int)sizeof(int) + 7) / 8);   // [2*NG][RW]
 
     const int tid = threadIdx.x;
     const int gl = tid % GS;   // lane within group
     const int gi = tid / GS;   // group within CTA
-    const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << ((tid & 31) / GS * GS));
     const int gbase = (tid & 31) / GS * GS;  // first warp lane of this group
     const long long cta_start = (long long)blockIdx.x * (NG * S);
     const long long start = cta_start + (long long)gi * S;
     const long long end = min(start + (long long)S, p.nnz);
     const int R = p.R;
+    constexpr unsigned FULL = 0xffffffffu;
 
     double acc[CPL];
 #pragma unroll
@@ -76,17 +97,19 @@ __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ 
     int cur_row = -1;
     int nseg = 0;  // completed flushes of this group
 
+    auto colof = [&](int c) { return (gl + GS * (c / VEC)) * VEC + (c % VEC); };
+
     auto flush = [&](bool is_tail) {
         // first run of the group -> slot 2*gi ; last run (if not also the first) -> slot 2*gi+1 ; others -> M
         if (nseg == 0 || is_tail) {
             const int slot = 2 * gi + (nseg == 0 ? 0 : 1);
             if (gl == 0) crow[slot] = cur_row;
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) cval[slot * RW + gl + GS * c] = acc[c];
+            for (int c = 0; c < CPL; ++c) cval[slot * RW + colof(c)] = acc[c];
         } else {
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
-                const int col = gl + GS * c;
+                const int col = colof(c);
                 if (col < R) p.M[(long long)cur_row * R + col] = acc[c];
             }
         }
@@ -94,62 +117,74 @@ __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ 
     };
 
     if (gl == 0) { crow[2 * gi] = -1; crow[2 * gi + 1] = -1; }
-    __syncwarp(gmask);
 
-    if (start < end) {
-        cur_row = p.rows[start];
-        for (long long base = start; base < end; base += GS) {
-            const long long my = base + gl;
-            const bool have = my < end;
-            const int my_row = have ? p.rows[my] : -1;
-            const double my_val = have ? p.vals[my] : 0.0;
-            int my_idx[NO];
+    if (start < end) cur_row = p.rows[start];
+    // uniform trip count for the whole CTA: S / BB batches (the last groups of the tensor run on predicates)
+    constexpr int BB = (NO <= 3 && VPL <= 2) ? B : 2;   // gather batch; the many-mode and wide-rank variants keep fewer rows in registers
+    int ccol[VPL];                          // first column of each of this lane's vectors, clamped into the row
+    bool cok[VPL];
 #pragma unroll
-            for (int m = 0; m < NO; ++m) my_idx[m] = (have && m < p.nother) ? p.oidx[m][my] : 0;
-            const int cnt = (int)min((long long)GS, end - base);
-            for (int j0 = 0; j0 < cnt; j0 += B) {
-                double contrib[B][CPL];
-                int rws[B];
+    for (int vv = 0; vv < VPL; ++vv) {
+        const int col0 = (gl + GS * vv) * VEC;
+        cok[vv] = col0 < R;
+        ccol[vv] = cok[vv] ? col0 : 0;
+    }
+    for (int b0 = 0; b0 < S; b0 += BB) {
+        // lanes 0..BB-1 of the group fetch the subscripts/value of one non-zero each (BB <= GS)
+        const long long my = start + b0 + gl;
+        const bool have = (gl < BB) && (my < end);
+        const int my_row = have ? p.rows[my] : -1;
+        const double my_val = have ? p.vals[my] : 0.0;
+        int my_idx[NO];
 #pragma unroll
-                for (int b = 0; b < B; ++b) {
-                    const int j = j0 + b;
-                    const int src = gbase + (j < GS ? j : 0);
-                    const int row = __shfl_sync(gmask, my_row, src);
-                    const double v = __shfl_sync(gmask, my_val, src);
-                    const bool ok = j < cnt;
-                    rws[b] = ok ? row : -1;
+        for (int m = 0; m < NO; ++m) my_idx[m] = (have && m < p.nother) ? p.oidx[m][my] : 0;
+
+        int rws[BB];
+        double vs[BB];
+        Vec<VEC> u[BB][NO][VPL];
+        // phase 1: every gather of the batch is issued before any is used (addresses are always valid:
+        // padding entries carry subscript 0, lanes beyond R read column 0 and are masked below)
 #pragma unroll
-                    for (int c = 0; c < CPL; ++c) contrib[b][c] = ok ? v : 0.0;
+        for (int b = 0; b < BB; ++b) {
+            const int src = gbase + b;
+            rws[b] = __shfl_sync(FULL, my_row, src);
+            vs[b] = __shfl_sync(FULL, my_val, src);
 #pragma unroll
-                    for (int m = 0; m < NO; ++m) {
-                        const int im = __shfl_sync(gmask, my_idx[m], src);
-                        if (m < p.nother) {
+            for (int m = 0; m < NO; ++m) {
+                const int im = __shfl_sync(FULL, my_idx[m], src);
+                const int mm = (NO <= 3 || m < p.nother) ? m : 0;
+                const double *rowp = p.U[mm] + (long long)((NO <= 3 || m < p.nother) ? im : 0) * R;
 #pragma unroll
-                            for (int c = 0; c < CPL; ++c) {
-                                const int col = gl + GS * c;
-                                const double u = (ok && col < R) ? __ldg(p.U[m] + (long long)im * R + col) : 0.0;
-                                contrib[b][c] *= u;
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int b = 0; b < B; ++b) {
-                    if (rws[b] >= 0) {
-                        if (rws[b] != cur_row) {
-                            flush(false);
-#pragma unroll
-                            for (int c = 0; c < CPL; ++c) acc[c] = 0.0;
-                            cur_row = rws[b];
-                        }
-#pragma unroll
-                        for (int c = 0; c < CPL; ++c) acc[c] += contrib[b][c];
-                    }
-                }
+                for (int vv = 0; vv < VPL; ++vv) u[b][m][vv].load(rowp + ccol[vv]);
             }
         }
-        flush(true);
+        // phase 2: products, then the ordered run accumulation
+#pragma unroll
+        for (int b = 0; b < BB; ++b) {
+            double contrib[CPL];
+#pragma unroll
+            for (int vv = 0; vv < VPL; ++vv)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    double x = cok[vv] ? vs[b] : 0.0;
+#pragma unroll
+                    for (int m = 0; m < NO; ++m)
+                        if (NO <= 3 || m < p.nother) x *= u[b][m][vv].v[e];
+                    contrib[vv * VEC + e] = x;
+                }
+            if (rws[b] >= 0) {
+                if (rws[b] != cur_row) {
+                    flush(false);
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) acc[c] = 0.0;
+                    cur_row = rws[b];
+                }
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) acc[c] += contrib[c];
+            }
+        }
     }
+    if (start < end) flush(true);
     __syncthreads();
 
     // ---- merge the 2*NG group carries of this CTA in slot order
@@ -178,7 +213,7 @@ __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ 
         while (j < 2 * NG && (crow[j] == row || crow[j] < 0)) {
             if (crow[j] == row) {
 #pragma unroll
-                for (int c = 0; c < CPL; ++c) sum[c] += cval[j * RW + gl + GS * c];
+                for (int c = 0; c < CPL; ++c) sum[c] += cval[j * RW + colof(c)];
                 last = j;
             }
             ++j;
@@ -190,13 +225,13 @@ __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ 
             if (gl == 0) p.carry_row[slot] = row;
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
-                const int col = gl + GS * c;
+                const int col = colof(c);
                 if (col < R) p.carry_val[slot * R + col] = sum[c];
             }
         } else {
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
-                const int col = gl + GS * c;
+                const int col = colof(c);
                 if (col < R) p.M[(long long)row * R + col] = sum[c];
             }
         }
@@ -304,47 +339,55 @@ __global__ void gather_kernel(const T *__restrict__ src, const unsigned int *__r
 
 int stream_blocks(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 8LL * sm_count())); }
 
-int group_cfg(int R, int &gs, int &cpl) {
-    cpl = (R + 31) / 32;
-    SKT_REQUIRE(cpl <= 4, SKT_EUNSUPPORTED, "sparse MTTKRP supports rank <= 128, got %d", R);
-    const int per = (R + cpl - 1) / cpl;
-    gs = 4;
+// lanes per group / vectors per lane / vector width for rank R (16-byte vectors need aligned factor rows)
+int group_cfg(int R, bool aligned, int &gs, int &vpl, int &vec) {
+    SKT_REQUIRE(R >= 1 && R <= 128, SKT_EUNSUPPORTED, "sparse MTTKRP supports rank <= 128, got %d", R);
+    vec = (aligned && R % 2 == 0) ? 2 : 1;
+    const int nvec = (R + vec - 1) / vec;        // vectors per factor row
+    vpl = (nvec + 31) / 32;
+    const int per = (nvec + vpl - 1) / vpl;
+    gs = 8;                                      // >= B so that one batch's subscripts are loaded by one group pass
     while (gs < per) gs *= 2;
+    SKT_REQUIRE(vpl <= 4, SKT_EUNSUPPORTED, "sparse MTTKRP supports rank <= %d, got %d", 128 * vec, R);
     return SKT_OK;
 }
 
-long long coo_nctas(const skt_coo *t, int R) {
-    int gs, cpl;
-    if (group_cfg(R, gs, cpl) != SKT_OK) return 0;
+long long coo_nctas(const skt_coo *t, int R, bool aligned) {
+    int gs, vpl, vec;
+    if (group_cfg(R, aligned, gs, vpl, vec) != SKT_OK) return 0;
     const long long per_cta = (long long)(CT / gs) * S;
     return std::max<long long>(1, (t->nnz + per_cta - 1) / per_cta);
 }
 
-template <int GS, int CPL>
+template <int GS, int VPL, int VEC>
 int launch_coo_no(int nother, const CooParams &p, long long nctas, cudaStream_t st) {
     constexpr int NG = CT / GS;
-    const size_t smem = (size_t)((2 * NG * sizeof(int) + 7) / 8 * 8) + (size_t)2 * NG * GS * CPL * sizeof(double);
+    const size_t smem = (size_t)((2 * NG * sizeof(int) + 7) / 8 * 8) + (size_t)2 * NG * GS * VPL * VEC * sizeof(double);
     const unsigned grid = (unsigned)nctas;
-    if (nother <= 1) mttkrp_coo_kernel<GS, CPL, 1><<<grid, CT, smem, st>>>(p);
-    else if (nother == 2) mttkrp_coo_kernel<GS, CPL, 2><<<grid, CT, smem, st>>>(p);
-    else if (nother == 3) mttkrp_coo_kernel<GS, CPL, 3><<<grid, CT, smem, st>>>(p);
-    else mttkrp_coo_kernel<GS, CPL, 7><<<grid, CT, smem, st>>>(p);
+    if (nother <= 1) mttkrp_coo_kernel<GS, VPL, VEC, 1><<<grid, CT, smem, st>>>(p);
+    else if (nother == 2) mttkrp_coo_kernel<GS, VPL, VEC, 2><<<grid, CT, smem, st>>>(p);
+    else if (nother == 3) mttkrp_coo_kernel<GS, VPL, VEC, 3><<<grid, CT, smem, st>>>(p);
+    else mttkrp_coo_kernel<GS, VPL, VEC, 7><<<grid, CT, smem, st>>>(p);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
 }
 
-int launch_coo(int gs, int cpl, int nother, const CooParams &p, long long nctas, cudaStream_t st) {
-    if (cpl == 1) {
+template <int VEC>
+int launch_coo_vec(int gs, int vpl, int nother, const CooParams &p, long long nctas, cudaStream_t st) {
+    if (vpl == 1) {
         switch (gs) {
-            case 4: return launch_coo_no<4, 1>(nother, p, nctas, st);
-            case 8: return launch_coo_no<8, 1>(nother, p, nctas, st);
-            case 16: return launch_coo_no<16, 1>(nother, p, nctas, st);
-            default: return launch_coo_no<32, 1>(nother, p, nctas, st);
+            case 8: return launch_coo_no<8, 1, VEC>(nother, p, nctas, st);
+            case 16: return launch_coo_no<16, 1, VEC>(nother, p, nctas, st);
+            default: return launch_coo_no<32, 1, VEC>(nother, p, nctas, st);
         }
     }
-    if (cpl == 2) return launch_coo_no<32, 2>(nother, p, nctas, st);
-    if (cpl == 3) return launch_coo_no<32, 3>(nother, p, nctas, st);
-    return launch_coo_no<32, 4>(nother, p, nctas, st);
+    if (vpl == 2) return launch_coo_no<32, 2, VEC>(nother, p, nctas, st);
+    if (vpl == 3) return launch_coo_no<32, 3, VEC>(nother, p, nctas, st);
+    return launch_coo_no<32, 4, VEC>(nother, p, nctas, st);
+}
+
+int launch_coo(int gs, int vpl, int vec, int nother, const CooParams &p, long long nctas, cudaStream_t st) {
+    return (vec == 2) ? launch_coo_vec<2>(gs, vpl, nother, p, nctas, st) : launch_coo_vec<1>(gs, vpl, nother, p, nctas, st);
 }
 
 int first_built(const skt_coo *t) {
@@ -485,7 +528,7 @@ extern "C" int skt_coo_build_host(const int64_t *const *subs_h, const double *va
 extern "C" size_t skt_mttkrp_coo_workspace(const skt_coo *t, int rank, int mode) {
     (void)mode;
     if (!t || rank < 1) return 0;
-    const long long nctas = coo_nctas(t, rank);
+    const long long nctas = coo_nctas(t, rank, false);   // the scalar layout needs the most CTAs: covers both
     return align_up((size_t)2 * nctas * sizeof(int), 256) + align_up((size_t)2 * nctas * rank * sizeof(double), 256);
 }
 
@@ -495,15 +538,19 @@ extern "C" int skt_mttkrp_coo(const skt_coo *t, const double *const *U_d, int ra
     SKT_REQUIRE(mode >= 0 && mode < t->ndim, SKT_EINVAL, "mode %d out of range", mode);
     SKT_REQUIRE(rank >= 1, SKT_EINVAL, "rank must be >= 1");
     SKT_REQUIRE(t->built_mask & (1u << mode), SKT_EINVAL, "the sorted copy for mode %d was not built", mode);
-    int gs, cpl;
-    int rc = group_cfg(rank, gs, cpl);
+    bool aligned = true;                     // 16-byte factor-row loads need 16-byte aligned factors
+    for (int m = 0; m < t->ndim; ++m)
+        if (m != mode && U_d[m] && (((uintptr_t)U_d[m]) & 15) != 0) aligned = false;
+    int gs, vpl, vec;
+    int rc = group_cfg(rank, aligned, gs, vpl, vec);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t need = skt_mttkrp_coo_workspace(t, rank, mode);
     SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     SKT_CUDA(cudaMemsetAsync(M_d, 0, (size_t)t->shape[mode] * rank * sizeof(double), st));
     if (t->nnz == 0) return SKT_OK;
-    const long long nctas = coo_nctas(t, rank);
+    const long long nctas = coo_nctas(t, rank, aligned);
+    const long long nctas_ws = coo_nctas(t, rank, false);
     CooParams p;
     p.rows = t->idx[mode][mode];
     p.vals = t->vals[mode];
@@ -511,7 +558,7 @@ extern "C" int skt_mttkrp_coo(const skt_coo *t, const double *const *U_d, int ra
     p.R = rank;
     p.M = M_d;
     p.carry_row = (int *)ws_d;
-    p.carry_val = (double *)((char *)ws_d + align_up((size_t)2 * nctas * sizeof(int), 256));
+    p.carry_val = (double *)((char *)ws_d + align_up((size_t)2 * nctas_ws * sizeof(int), 256));
     int k = 0;
     for (int m = 0; m < t->ndim; ++m) {
         if (m == mode) continue;
@@ -522,7 +569,7 @@ extern "C" int skt_mttkrp_coo(const skt_coo *t, const double *const *U_d, int ra
     }
     p.nother = k;
     for (; k < SKT_MAX_NDIM; ++k) { p.oidx[k] = p.oidx[0]; p.U[k] = p.U[0]; }
-    rc = launch_coo(gs, cpl, p.nother, p, nctas, st);
+    rc = launch_coo(gs, vpl, vec, p.nother, p, nctas, st);
     if (rc) return rc;
     const long long nslots = 2 * nctas;
     const long long threads = nslots * rank;
