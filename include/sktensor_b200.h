@@ -58,6 +58,14 @@ SKT_API uint64_t skt_launch_count(void);
 /* SM count, compute capability and opt-in shared memory of the current device. */
 SKT_API int skt_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *smem_optin);
 
+/* ---------------------------------------------------------------- tensor ingest
+ * Copy a (pageable) host buffer to the device through a pool of pinned staging buffers filled by several
+ * host threads, each overlapping its memcpy with its own asynchronous DMA.  The reference starts every
+ * call from a host ndarray (dtensor.__new__, sktensor/dtensor.py:48-50); this is the first step of
+ * cp_als / tucker_hooi / uttkrp here.  The copy is ordered on `stream`; src_h is not referenced after
+ * the call returns.                                                                               */
+SKT_API int skt_upload(void *dst_d, const void *src_h, size_t nbytes, skt_stream stream);
+
 /* ---------------------------------------------------------------- dense MTTKRP
  * M[i_n, r] = sum_{all other i} X[i_0..i_{N-1}] * prod_{m != n} U_m[i_m, r]
  * Replaces dtensor.uttkrp (sktensor/dtensor.py:163-167) = unfold (dtensor.py:103-150) +
@@ -76,6 +84,17 @@ SKT_API int skt_mttkrp_dense_naive(const double *X_d, const int64_t *shape, int 
  * skt_mttkrp_dense, downloads M.  X_h is C-order.                                       */
 SKT_API int skt_mttkrp_dense_host(const double *X_h, const int64_t *shape, int ndim,
                           const double *const *U_h, int rank, int mode, double *M_h);
+
+/* ---------------------------------------------------------------- dimension-tree second stage
+ * The N MTTKRPs of one cp.als sweep (cp.py:142-143) share work: with T the partial contraction of X
+ * against the factors of every mode OUTSIDE a group of p consecutive modes (T is
+ * dims[0] x ... x dims[p-1] x rank, row-major; produced by skt_mttkrp_dense on a reshaped view of X),
+ *   M[i_mode, r] = sum_{other i of the group} T[i_0..i_{p-1}, r] * prod_{m != mode} W_m[i_m, r]
+ * equals dtensor.uttkrp(U, mode) (dtensor.py:163-167) for that group mode.  W_d: HOST array of p device
+ * pointers (dims[m] x rank), W_d[mode] ignored.  Deterministic (no atomics).                       */
+SKT_API size_t skt_kr_reduce_workspace(const int64_t *dims, int p, int rank, int mode);
+SKT_API int skt_kr_reduce(const double *T_d, const int64_t *dims, int p, const double *const *W_d, int rank,
+                  int mode, double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream);
 
 /* ---------------------------------------------------------------- sparse (COO) MTTKRP
  * Replaces sptensor.uttkrp (sktensor/sptensor.py:216-229) and its per-rank-column

@@ -56,6 +56,7 @@ struct DenseParams {
     int nk;
     int vecX, vecU;
     int nw;
+    int direct;          // every tile row is its own output row (L == T == 1): the TMA kernel stores accumulators straight to out
     WeightMode w[SKT_MAX_NDIM];
 };
 
@@ -538,6 +539,28 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                 // ---- tile epilogue: out += acc * prod_m U_m[i_m(row), col]   (the Khatri-Rao rows, on the fly)
                 const int it = cs.item / p.nsplit;
                 const int lt = cs.tile / p.ntt, tt = cs.tile % p.ntt;
+                if (p.direct) {
+                    // plain GEMM rows (the partial contraction of the dimension tree, dimtree.cu): no weights, no
+                    // cross-row sum -- 16-byte stores from the accumulator registers, no staging, no barrier
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const long long i = (long long)it * bi + 16 * rg + 8 * a + pg;
+                        double *orow = p.out + i * p.ld + colbase + 2 * t4;
+#pragma unroll
+                        for (int nn = 0; nn < 4; ++nn) {
+                            const int col = colbase + 8 * nn + 2 * t4;
+                            if (nn < nbw && i < p.In) {
+                                if (p.direct == 2 && col + 1 < p.R) {
+                                    *reinterpret_cast<double2 *>(orow + 8 * nn) = make_double2(acc[a][nn][0], acc[a][nn][1]);
+                                } else {
+                                    if (col < p.R) orow[8 * nn] = acc[a][nn][0];
+                                    if (col + 1 < p.R) orow[8 * nn + 1] = acc[a][nn][1];
+                                }
+                            }
+                            acc[a][nn][0] = acc[a][nn][1] = 0.0;
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
                     const int q = 16 * rg + 8 * a + pg;
@@ -570,7 +593,10 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                     }
                 }
             }
-            if (++cs.tile == cs.tile_end) {
+            if (++cs.tile == cs.tile_end && p.direct) {
+                cs.item += gridDim.x;
+                if (cs.active(p)) cs.range(p);
+            } else if (cs.tile == cs.tile_end) {
                 // ---- item flush: sum rows of equal i_n in a fixed order, write bi x R outputs
                 const int it = cs.item / p.nsplit, s = cs.item % p.nsplit;
                 double *dst = p.out + (long long)s * p.out_split_stride;
@@ -977,6 +1003,8 @@ extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndi
     p.nsplit = pl.nsplit; p.chunk = pl.chunk; p.nitems = pl.nitems;
     p.nk = use_tma ? (pl.Kc + TK - 1) / TK : (pl.Kc + BK - 1) / BK;
     p.nw = pl.nw;
+    // M-major tiles hold 16 l-rows per output row group, so only the K-major kernel has a 1:1 row map
+    p.direct = (use_tma && !pl.mmajor && pl.L == 1 && pl.T == 1 && pl.nsplit == 1 && pl.nw == 0) ? 1 : 0;
     p.out_split_stride = (pl.nsplit > 1) ? (long long)pl.In * rank : 0;
     double *outbase = (pl.nsplit > 1) ? (double *)ws_d : M_d;
     const bool xalign = (((uintptr_t)X_d) & 15) == 0;
@@ -994,6 +1022,7 @@ extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndi
             p.w[m].dim = pl.wdim[m]; p.w[m].div = pl.wdiv[m]; p.w[m].space = pl.wspace[m];
         }
         p.vecU = ((((uintptr_t)p.Uc) & 15) == 0) && (rank % 2 == 0) && (ncol % 2 == 0);
+        if (p.direct) p.direct = (((((uintptr_t)p.out) & 15) == 0) && (rank % 2 == 0)) ? 2 : 1;
         const int nb = (ncol + 7) / 8;
         if (use_tma) {
             // the tile height is fixed by the plan: 128-row tiles always run the two-column-group kernels

@@ -1,0 +1,118 @@
+// Host -> device ingest of a user's (pageable) tensor buffer.
+//
+// The reference keeps X in host memory and every call starts from there (dtensor is an ndarray view,
+// sktensor/dtensor.py:48-50), so the first thing cp_als / tucker_hooi / uttkrp do here is move X to HBM.
+// A plain cudaMemcpy from pageable memory stages through one driver-owned bounce buffer on one thread
+// (~10 GB/s); this path stages through a pool of pinned buffers with several host threads, each
+// pipelining memcpy (pageable -> pinned) against its own asynchronous DMA (pinned -> HBM), which is
+// bounded by the PCIe link instead.  The copy is ordered on the caller's stream: work enqueued on
+// `stream` after skt_upload sees the data; the host buffer is no longer referenced once skt_upload returns.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace skt {
+namespace {
+
+constexpr size_t CHUNK = 4u << 20;   // bytes per staging buffer
+constexpr int MAX_THREADS = 8;
+constexpr int SLOTS = 2;             // staging buffers per thread (memcpy of one overlaps the DMA of the other)
+
+struct Pool {
+    int device = -1;
+    int nthreads = 0;
+    char *pin[MAX_THREADS][SLOTS] = {};
+    cudaEvent_t ev[MAX_THREADS][SLOTS] = {};
+    cudaEvent_t done[MAX_THREADS] = {};
+    cudaEvent_t start = nullptr;
+    cudaStream_t cs[MAX_THREADS] = {};
+};
+
+std::mutex g_mu;
+Pool g_pool;
+
+int pool_init(Pool &P, int device) {
+    if (P.device == device && P.nthreads > 0) return SKT_OK;
+    if (P.nthreads > 0) {   // device changed: rebuild
+        for (int t = 0; t < P.nthreads; ++t) {
+            for (int s = 0; s < SLOTS; ++s) { cudaFreeHost(P.pin[t][s]); cudaEventDestroy(P.ev[t][s]); }
+            cudaEventDestroy(P.done[t]);
+            cudaStreamDestroy(P.cs[t]);
+        }
+        cudaEventDestroy(P.start);
+        P = Pool();
+    }
+    unsigned hc = std::thread::hardware_concurrency();
+    int nt = (int)std::max(1u, std::min<unsigned>(MAX_THREADS, hc ? hc / 2 : 4));
+    const char *env = getenv("SKT_UPLOAD_THREADS");
+    if (env && atoi(env) > 0) nt = std::min(MAX_THREADS, atoi(env));
+    for (int t = 0; t < nt; ++t) {
+        for (int s = 0; s < SLOTS; ++s) {
+            SKT_CUDA(cudaHostAlloc((void **)&P.pin[t][s], CHUNK, cudaHostAllocDefault));
+            SKT_CUDA(cudaEventCreateWithFlags(&P.ev[t][s], cudaEventDisableTiming));
+        }
+        SKT_CUDA(cudaEventCreateWithFlags(&P.done[t], cudaEventDisableTiming));
+        SKT_CUDA(cudaStreamCreateWithFlags(&P.cs[t], cudaStreamNonBlocking));
+    }
+    SKT_CUDA(cudaEventCreateWithFlags(&P.start, cudaEventDisableTiming));
+    P.device = device;
+    P.nthreads = nt;
+    return SKT_OK;
+}
+
+}  // namespace
+}  // namespace skt
+
+using namespace skt;
+
+extern "C" int skt_upload(void *dst_d, const void *src_h, size_t nbytes, skt_stream stream) {
+    SKT_REQUIRE((dst_d && src_h) || nbytes == 0, SKT_EINVAL, "NULL argument");
+    if (nbytes == 0) return SKT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nbytes < 2 * CHUNK) {   // small: one plain copy
+        SKT_CUDA(cudaMemcpyAsync(dst_d, src_h, nbytes, cudaMemcpyHostToDevice, st));
+        SKT_CUDA(cudaStreamSynchronize(st));
+        return SKT_OK;
+    }
+    std::lock_guard<std::mutex> lock(g_mu);
+    int device = 0;
+    SKT_CUDA(cudaGetDevice(&device));
+    int rc = pool_init(g_pool, device);
+    if (rc != SKT_OK) return rc;
+    Pool &P = g_pool;
+    const size_t nchunks = (nbytes + CHUNK - 1) / CHUNK;
+    const int nt = (int)std::min<size_t>(P.nthreads, nchunks);
+    // the copy streams start after whatever the caller's stream has queued so far (dst may be recycled memory)
+    SKT_CUDA(cudaEventRecord(P.start, st));
+    std::vector<cudaError_t> err(nt, cudaSuccess);
+    auto worker = [&](int t) {
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(P.cs[t], P.start, 0);
+        int it = 0;
+        for (size_t c = t; c < nchunks && e == cudaSuccess; c += nt, ++it) {
+            const int s = it % SLOTS;
+            if (it >= SLOTS) e = cudaEventSynchronize(P.ev[t][s]);   // the slot's previous DMA has drained
+            if (e != cudaSuccess) break;
+            const size_t off = c * CHUNK, len = std::min(CHUNK, nbytes - off);
+            memcpy(P.pin[t][s], (const char *)src_h + off, len);
+            e = cudaMemcpyAsync((char *)dst_d + off, P.pin[t][s], len, cudaMemcpyHostToDevice, P.cs[t]);
+            if (e == cudaSuccess) e = cudaEventRecord(P.ev[t][s], P.cs[t]);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(P.done[t], P.cs[t]);
+        err[t] = e;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
+    for (int t = 0; t < nt; ++t)
+        if (err[t] != cudaSuccess) return cuda_fail(err[t], "skt_upload worker", __FILE__, __LINE__);
+    for (int t = 0; t < nt; ++t) SKT_CUDA(cudaStreamWaitEvent(st, P.done[t], 0));
+    // the staging buffers are reused by the next call: drain the DMAs before handing control back
+    for (int t = 0; t < nt; ++t) SKT_CUDA(cudaEventSynchronize(P.done[t]));
+    return SKT_OK;
+}

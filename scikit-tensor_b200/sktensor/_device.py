@@ -11,6 +11,7 @@ import numpy as np
 from . import _lib
 
 _torch = None
+_UPLOAD_MIN = 8 << 20
 
 
 def torch():
@@ -48,6 +49,10 @@ def to_device(a, dtype=np.float64):
     if isinstance(a, t.Tensor):
         return a.to(device=device(), dtype=getattr(t, np.dtype(dtype).name)).contiguous()
     h = np.ascontiguousarray(np.asarray(a), dtype=dtype)
+    if h.nbytes >= _UPLOAD_MIN:     # big tensors: multi-threaded pinned staging (skt_upload), PCIe-bound
+        x = t.empty(h.shape, dtype=getattr(t, np.dtype(dtype).name), device=device())
+        _lib.check(_lib.load().skt_upload(C.c_void_p(x.data_ptr()), C.c_void_p(h.ctypes.data), h.nbytes, stream_ptr()))
+        return x
     if not h.flags.writeable:       # torch.from_numpy warns on read-only buffers
         h = h.copy()
     return t.from_numpy(h).to(device())

@@ -48,6 +48,23 @@ def mttkrp_dense_host(X, U, rank, mode):
     return M
 
 
+def kr_reduce(T, dims, W, rank, mode, out=None):
+    """Second stage of the dimension tree: MTTKRP of group mode ``mode`` from the partial tensor ``T``
+    (``dims[0] x ... x dims[p-1] x rank``) and the group's factors ``W`` (``W[mode]`` ignored)."""
+    lib = _lib.load()
+    d = _lib.shape_array(dims)
+    p = len(dims)
+    if out is None:
+        out = dev.empty((dims[mode], rank))
+    need = lib.skt_kr_reduce_workspace(d, p, rank, mode)
+    if need == 0:
+        _lib.check(-2)
+    ws, wsz = dev.workspace('mttkrp').get(need)
+    _lib.check(lib.skt_kr_reduce(dev.ptr(T), d, p, _factor_ptrs(W, mode), rank, mode, dev.ptr(out), ws, wsz,
+                                 dev.stream_ptr()))
+    return out
+
+
 # ------------------------------------------------------------------ sparse
 class CooHandle(object):
     """Owner of a device-resident sorted COO tensor (``skt_coo*``)."""

@@ -30,11 +30,15 @@ PROTOTYPES = {
     'skt_launch_count': (C.c_uint64, []),
     'skt_device_info': (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_size_t)]),
+    'skt_upload': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
     'skt_mttkrp_dense_workspace': (C.c_size_t, [c_i64p, C.c_int, C.c_int, C.c_int]),
     'skt_mttkrp_dense': (C.c_int, [c_dp, c_i64p, C.c_int, c_voidpp, C.c_int, C.c_int, c_dp,
                                    C.c_void_p, C.c_size_t, c_stream]),
     'skt_mttkrp_dense_naive': (C.c_int, [c_dp, c_i64p, C.c_int, c_voidpp, C.c_int, C.c_int, c_dp, c_stream]),
     'skt_mttkrp_dense_host': (C.c_int, [c_dp, c_i64p, C.c_int, c_voidpp, C.c_int, C.c_int, c_dp]),
+    'skt_kr_reduce_workspace': (C.c_size_t, [c_i64p, C.c_int, C.c_int, C.c_int]),
+    'skt_kr_reduce': (C.c_int, [c_dp, c_i64p, C.c_int, c_voidpp, C.c_int, C.c_int, c_dp, C.c_void_p, C.c_size_t,
+                                c_stream]),
     'skt_coo_build_host': (C.c_int, [c_voidpp, c_dp, C.c_int64, c_i64p, C.c_int, C.c_uint,
                                      C.POINTER(C.c_void_p)]),
     'skt_coo_build': (C.c_int, [c_voidpp, c_dp, C.c_int64, c_i64p, C.c_int, C.c_uint, c_stream,

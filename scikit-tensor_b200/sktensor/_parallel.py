@@ -17,6 +17,8 @@ through a backend object so that the CPU test-suite can drive the same choreogra
 NumPy stand-in (``tests/fake_backend.py``); the shipped default is the CUDA library and
 there is no automatic fallback.
 """
+import os
+
 import numpy as np
 
 from .dtensor import dtensor
@@ -56,6 +58,20 @@ def split_nnz(idx, dim, world):
 def shard_mode(shape):
     """The mode to cut: the largest one (first on ties)."""
     return int(np.argmax(np.asarray(shape)))
+
+
+def tree_split(shape):
+    """Split point ``s`` of the two-group dimension tree: modes ``[0, s)`` share one partial
+    contraction of X and modes ``[s, N)`` the other.  Chosen to keep both partial tensors small
+    (minimal ``prod(shape[:s]) + prod(shape[s:])``; ties go to the larger ``s`` so that the second
+    pass is the plain last-mode MTTKRP whose output also feeds the fit)."""
+    N = len(shape)
+    best, best_s = None, 1
+    for s in range(1, N):
+        cost = float(np.prod([float(d) for d in shape[:s]])) + float(np.prod([float(d) for d in shape[s:]]))
+        if best is None or cost <= best:
+            best, best_s = cost, s
+    return best_s
 
 
 class LocalShard(object):
@@ -112,6 +128,7 @@ class CudaBackend(object):
     # kernels
     def mttkrp_dense(self, Xd, shape, U, R, n, out): return self.K.mttkrp_dense(Xd, shape, U, R, n, out=out)
     def mttkrp_coo(self, coo, U, R, n, out): return self.K.mttkrp_coo(coo, U, R, n, out=out)
+    def kr_reduce(self, T, dims, W, R, n, out): return self.K.kr_reduce(T, dims, W, R, n, out=out)
     def sumsq(self, x): return self.K.sumsq(x)
     def coo_sumsq(self, coo): return self.K.coo_sumsq(coo)
     def gram(self, U, out): return self.K.gram(U, out=out)
@@ -243,6 +260,20 @@ class CpAlsEngine(object):
         self._m0_ready = False      # True when M[0] already holds the MTTKRP for the coming sweep
         self._pending = None
 
+        # ---- dimension tree (dense, N >= 3): two passes over X per sweep instead of N.  Modes [0, s) are
+        # served by T_A = X contracted with U_s..U_{N-1}; modes [s, N) by T_B = X contracted with
+        # U_0..U_{s-1}.  A one-mode group needs no second stage: its partial tensor IS the MTTKRP.
+        self.tree = (not self.sparse) and N >= 3 and hasattr(be, 'kr_reduce') and \
+            os.environ.get('SKT_NO_DIMTREE', '0') != '1'
+        if self.tree:
+            self.ts = s = tree_split(self.lshape)
+            nA = int(np.prod(self.lshape[:s]))
+            nB = int(np.prod(self.lshape[s:]))
+            self.shapeA = (nA,) + tuple(self.lshape[s:])
+            self.shapeB = tuple(self.lshape[:s]) + (nB,)
+            self.TA = self.M[0] if s == 1 else be.empty((nA, R))
+            self.TB = self.M[N - 1] if s == N - 1 else be.empty((nB, R))
+
     @staticmethod
     def _cut(X, s, comm):
         """Slice a full tensor down to this rank's slab along mode ``s``."""
@@ -263,12 +294,31 @@ class CpAlsEngine(object):
         return dtensor(np.ascontiguousarray(np.asarray(X)[tuple(sl)])), offs
 
     # ------------------------------------------------------------------ one ALS iteration
+    def _tree_pass(self, group):
+        """One pass over X: the partial contraction that serves every mode of ``group`` (0: modes
+        ``[0, s)``, 1: modes ``[s, N)``), by the dense MTTKRP kernel on a reshaped view of X."""
+        be, s, N = self.be, self.ts, self.N
+        if group == 0:
+            be.mttkrp_dense(self.Xd, self.shapeA, [None] + list(self.Ud[s:]), self.R, 0, self.TA)
+        else:
+            be.mttkrp_dense(self.Xd, self.shapeB, list(self.Ud[:s]) + [None], self.R, s, self.TB)
+
     def mttkrp(self, n):
         """Local MTTKRP for mode ``n`` into ``self.M[n]`` (partial sums reduced across ranks)."""
         be = self.be
         # the reference ignores U[n]; on the first sweep the not-yet-computed factors are never read
         if self.sparse:
             be.mttkrp_coo(self.Xd, self.Ud, self.R, n, self.M[n])
+        elif self.tree:
+            s, N = self.ts, self.N
+            if n == 0:
+                self._tree_pass(0)
+            elif n == s:
+                self._tree_pass(1)
+            if n < s and s > 1:
+                be.kr_reduce(self.TA, self.lshape[:s], self.Ud[:s], self.R, n, self.M[n])
+            elif n >= s and s < N - 1:
+                be.kr_reduce(self.TB, self.lshape[s:], self.Ud[s:], self.R, n - s, self.M[n])
         else:
             be.mttkrp_dense(self.Xd, self.lshape, self.Ud, self.R, n, self.M[n])
         if self.comm.active and n != self.s:

@@ -36,7 +36,21 @@ class NumpyBackend(object):
 
     def mttkrp_dense(self, Xd, shape, U, R, n, out):
         Un = self._np(U)
-        out.copy_(torch.from_numpy(orc.mttkrp_dense(Xd, Un, n)))
+        out.copy_(torch.from_numpy(orc.mttkrp_dense(np.asarray(Xd).reshape(tuple(int(d) for d in shape)), Un, n)))
+        return out
+
+    def kr_reduce(self, T, dims, W, R, n, out):
+        # the partial tensor with its trailing rank axis, one rank column at a time
+        t = T.numpy().reshape(tuple(int(d) for d in dims) + (R,))
+        Wn = self._np(W)
+        res = np.empty((int(dims[n]), R))
+        for r in range(R):
+            v = t[..., r]
+            for m in range(len(dims) - 1, -1, -1):
+                if m != n:
+                    v = np.tensordot(v, Wn[m][:, r], axes=([m], [0]))
+            res[:, r] = v
+        out.copy_(torch.from_numpy(res))
         return out
 
     def mttkrp_coo(self, coo, U, R, n, out):

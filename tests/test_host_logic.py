@@ -256,3 +256,13 @@ def test_partition_helpers():
         heaviest_row = np.bincount(idx).max()
         assert max(counts) <= len(idx) / world + heaviest_row
     assert _parallel.shard_mode((4, 9, 9, 2)) == 1
+
+
+def test_tree_split():
+    from sktensor._parallel import tree_split
+    assert tree_split((512, 512, 512)) == 2          # tie -> last-mode MTTKRP is the second pass
+    assert tree_split((160, 160, 160, 160)) == 2
+    assert tree_split((10, 11)) == 1
+    assert tree_split((1000, 10, 10)) == 1
+    assert tree_split((10, 10, 1000)) == 2
+    assert tree_split((4, 5, 6, 7, 8)) in (2, 3)

@@ -74,7 +74,71 @@ def main():
             nbytes = nnz * (4 * 3 + 8) + 8 * R * sum(shape)
             print('sparse nnz=%d R=%d mode %d: median %.3f ms best %.3f ms  %.0f GB/s (algorithmic)  %.1f Mnnz/s' %
                   (nnz, R, n, med, best, nbytes / med / 1e6, nnz / med / 1e3))
+    if 'tree' in which:
+        for shape, R in (((512, 512, 512), 32), ((160, 160, 160, 160), 64)):
+            N = len(shape)
+            X = torch.rand(*shape, dtype=torch.float64, device='cuda')
+            U = [torch.rand(s, R, dtype=torch.float64, device='cuda') for s in shape]
+            s_ = 2
+            nA, nB = int(np.prod(shape[:s_])), int(np.prod(shape[s_:]))
+            shapeA, shapeB = (nA,) + tuple(shape[s_:]), tuple(shape[:s_]) + (nB,)
+            TA, TB = dev.empty((nA, R)), dev.empty((nB, R))
+            med, best = timeit(lambda: K.mttkrp_dense(X, shapeA, [None] + U[s_:], R, 0, out=TA), reps=5)
+            print('tree %s R=%d pass A (%s mode 0): median %.3f ms  %.1f TFLOP/s' % (shape, R, shapeA, med, 2.0 * R * X.numel() / med / 1e9))
+            med, best = timeit(lambda: K.mttkrp_dense(X, shapeB, U[:s_] + [None], R, s_, out=TB), reps=5)
+            print('tree %s R=%d pass B (%s mode %d): median %.3f ms  %.1f TFLOP/s' % (shape, R, shapeB, s_, med, 2.0 * R * X.numel() / med / 1e9))
+            for n in range(s_):
+                out = dev.empty((shape[n], R))
+                med, best = timeit(lambda: K.kr_reduce(TA, shape[:s_], U[:s_], R, n, out=out))
+                print('  kr_reduce group A mode %d: median %.4f ms (%.0f GB/s over T)' % (n, med, TA.numel() * 8 / med / 1e6))
+            if s_ < N - 1:
+                for n in range(s_, N):
+                    out = dev.empty((shape[n], R))
+                    med, best = timeit(lambda: K.kr_reduce(TB, shape[s_:], U[s_:], R, n - s_, out=out))
+                    print('  kr_reduce group B mode %d: median %.4f ms (%.0f GB/s over T)' % (n, med, TB.numel() * 8 / med / 1e6))
+            del X, TA, TB
+    if 'upload' in which:
+        h = np.random.RandomState(0).rand(512, 512, 512)
+        for rep in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            x = dev.to_device(h)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            y = torch.from_numpy(h).to('cuda')
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            print('upload 1.07 GB: skt_upload %.1f ms (%.1f GB/s)   torch pageable %.1f ms (%.1f GB/s)  equal=%s' %
+                  ((t1 - t0) * 1e3, h.nbytes / (t1 - t0) / 1e9, (t2 - t1) * 1e3, h.nbytes / (t2 - t1) / 1e9,
+                   bool(torch.equal(x, y))))
+            del x, y
+    if 'als4' in which:
+        from sktensor import _parallel, dtensor
+        X = np.random.RandomState(0).rand(160, 160, 160, 160)
+        np.random.seed(1)
+        U = [None] + [np.random.rand(160, 64) for _ in range(3)]
+        for flag in ('1', '0'):
+            os.environ['SKT_NO_DIMTREE'] = flag
+            eng = _parallel.CpAlsEngine(dtensor(X), 64, list(U))
+            eng.sweep(True)
+            f0 = eng.read_fit()
+            med, best = timeit(lambda: (eng.sweep(False), eng.read_fit()), reps=6, warm=2)
+            print('cp_als 160^4 R=64 iteration (dimtree %s): median %.3f ms best %.3f ms -> %.1f it/s (fit %.12f)' %
+                  ('off' if flag == '1' else 'on', med, best, 1e3 / med, eng.read_fit()))
+            del eng
+        os.environ['SKT_NO_DIMTREE'] = '0'
+    if 'hooi' in which:
+        from sktensor import dtensor, tucker_hooi
+        X = np.random.RandomState(0).rand(384, 384, 384)
+        for rep in range(2):
+            np.random.seed(0)
+            t0 = time.perf_counter()
+            core, Uh = tucker_hooi(dtensor(X), [32, 32, 32], init='random', maxIter=5, conv=0)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            print('tucker_hooi 384^3 -> 32^3, 5 iterations, whole call: %.1f ms -> %.2f it/s' % (dt * 1e3, 5 / dt))
     if 'als' in which:
+        os.environ['SKT_NO_DIMTREE'] = os.environ.get('SKT_NO_DIMTREE', '0')
         from sktensor import _parallel, dtensor
         X = np.random.RandomState(0).rand(512, 512, 512)
         np.random.seed(1)
