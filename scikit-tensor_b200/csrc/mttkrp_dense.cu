@@ -1004,7 +1004,8 @@ extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndi
     p.nk = use_tma ? (pl.Kc + TK - 1) / TK : (pl.Kc + BK - 1) / BK;
     p.nw = pl.nw;
     // M-major tiles hold 16 l-rows per output row group, so only the K-major kernel has a 1:1 row map
-    p.direct = (use_tma && !pl.mmajor && pl.L == 1 && pl.T == 1 && pl.nsplit == 1 && pl.nw == 0) ? 1 : 0;
+    p.direct = (use_tma && !pl.mmajor && pl.L == 1 && pl.T == 1 && pl.lg_bt == 0 && pl.lg_bl == 0 && pl.nsplit == 1 &&
+                pl.nw == 0) ? 1 : 0;
     p.out_split_stride = (pl.nsplit > 1) ? (long long)pl.In * rank : 0;
     double *outbase = (pl.nsplit > 1) ? (double *)ws_d : M_d;
     const bool xalign = (((uintptr_t)X_d) & 15) == 0;
