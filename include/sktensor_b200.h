@@ -168,6 +168,16 @@ SKT_API size_t skt_normalise_gram_workspace(int64_t rows, int rank);
 SKT_API int skt_normalise_gram(double *U_d, const double *colstat_d, int64_t rows, int rank,
                        int first_iter, double *lambda_d, double *G_d, const double *Mip_d,
                        double *ip_d, void *ws_d, size_t ws_bytes, skt_stream stream);
+/* The whole inter-MTTKRP block of cp.als for a factor that fits in shared memory (cp.py:144-159) in one
+ * single-CTA launch: P = pinv(hadamard_{m != mode} G_m), Unew = M P, lambda, U = Unew / lambda (U_d),
+ * G[mode] = U^T U (written into G_d), and optionally ip_d[0] = <P,X> (M being the MTTKRP of the last mode,
+ * ktensor.py:128-150) and fit_d[0..1] = (fit, ||P||^2) (cp.py:157-159).  skt_cp_update_fused_fits() tells
+ * whether (rows, rank) qualifies; tall factors use skt_hadamard_pinv / skt_solve_stats /
+ * skt_normalise_gram.  info_d[0]: rank kept by the pseudo-inverse, -1 on a non-finite Gram product.   */
+SKT_API int skt_cp_update_fused_fits(int64_t rows, int rank);
+SKT_API int skt_cp_update_fused(const double *M_d, int64_t rows, int rank, int ndim, int mode, int first_iter,
+                        double *G_d, double *U_d, double *lambda_d, int *info_d, double *ip_d,
+                        const double *normX2_d, double *fit_d, skt_stream stream);
 /* fit = 1 - (normX2 + ||P||^2 - 2 ip) / normX2 with ||P||^2 = sum(lambda lambda^T *
  * hadamard_m G_m) (cp.py:157-159, ktensor.py:113-126).  out_d[0] = fit, out_d[1] = ||P||^2. */
 SKT_API int skt_cp_fit(const double *G_d, int ndim, int rank, const double *lambda_d,

@@ -6,6 +6,7 @@
 #include <cfloat>
 
 #include "common.cuh"
+#include "pinv.cuh"
 
 namespace skt {
 namespace {
@@ -210,191 +211,20 @@ __global__ void __launch_bounds__(NT) solve_stats_kernel(const double *__restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// P = pinv( hadamard_{m != mode} G_m ),  scipy.linalg.pinv semantics (cp.py:144-147):
-// singular values <= R*eps*sigma_max are dropped.  One CTA, one warp per column pair, one-sided
-// (Hestenes) Jacobi with a round-robin ordering; symmetric Y so Y V = W with orthogonal columns,
-// sigma_j = |w_j| and pinv(Y) = sum_j v_j w_j^T / sigma_j^2.
+// P = pinv( hadamard_{m != mode} G_m ),  scipy.linalg.pinv semantics (cp.py:144-147); one CTA.
+// The algorithm lives in pinv.cuh (shared with the fused small-factor update).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) hadamard_pinv_kernel(const double *__restrict__ G, int ndim, int R, int mode,
                                                              double *P, int *info) {
     extern __shared__ double jsm[];
-    double (*W)[MAXR + 1] = reinterpret_cast<double (*)[MAXR + 1]>(jsm);                        // W[j][i]: column j of the working matrix
-    double (*V)[MAXR + 1] = reinterpret_cast<double (*)[MAXR + 1]>(jsm + MAXR * (MAXR + 1));    // V[j][i]: column j of the accumulated rotations
-    double *sig2 = jsm + 2 * MAXR * (MAXR + 1);
-    __shared__ int flag_rot, flag_bad;
-    __shared__ double smax2;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nthreads = blockDim.x;
-    const int npairs = (R + 1) / 2;
-    const int m = 2 * npairs - 1;  // round-robin modulus (n' - 1), n' = R rounded up to even
-
-    if (tid == 0) { flag_bad = 0; flag_rot = 0; }
-    __syncthreads();
-    for (int e = tid; e < R * R; e += nthreads) {
-        const int a = e / R, b = e % R;
-        double y = 1.0;
-        for (int k = 0; k < ndim; ++k)
-            if (k != mode) y *= G[(size_t)k * R * R + e];
-        if (!isfinite(y)) flag_bad = 1;
-        W[b][a] = y;
-        V[b][a] = (a == b) ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    if (flag_bad) {
-        for (int e = tid; e < R * R; e += nthreads) P[e] = nan("");
-        if (tid == 0) info[0] = -1;
+    const PinvShared s = pinv_carve(jsm, R);
+    if (pinv_load_y(s, G, ndim, R, mode)) {
+        for (int e = threadIdx.x; e < R * R; e += blockDim.x) P[e] = nan("");
+        if (threadIdx.x == 0) info[0] = -1;
         return;
     }
-
-    // ---- fast path: Y is a Hadamard product of Grams, hence symmetric positive semi-definite.  When an
-    // unpivoted Cholesky factorisation sees no small pivot (pivot > 1e-7 * largest diagonal entry) Y is far
-    // from the pinv cut-off (R * eps * sigma_max), the pseudo-inverse is the inverse, and it is formed as
-    // L^-T L^-1 in a few microseconds.  Anything closer to singular takes the Jacobi route below, which
-    // implements scipy.linalg.pinv's truncation exactly.
-    {
-        __shared__ double dg[MAXR];
-        __shared__ int chol_fail;
-        __shared__ double maxdiag;
-        // V temporarily holds the factor: A(i,j) == V[j][i]
-        for (int e = tid; e < R * R; e += nthreads) V[e % R][e / R] = W[e % R][e / R];
-        if (tid == 0) {
-            double mx = 0.0;
-            for (int j = 0; j < R; ++j) mx = fmax(mx, W[j][j]);
-            maxdiag = mx;
-            chol_fail = (mx > 0.0) ? 0 : 1;
-        }
-        __syncthreads();
-        const double thr = 1e-7 * maxdiag;
-        bool fail = chol_fail != 0;
-        for (int k = 0; k < R && !fail; ++k) {
-            const double d = V[k][k];           // final after the previous trailing update
-            if (!(d > thr)) { fail = true; break; }   // same value in every thread: uniform exit
-            const double sd = sqrt(d);
-            if (tid == 0) dg[k] = sd;
-            for (int i = k + 1 + tid; i < R; i += nthreads) V[k][i] = V[k][i] / sd;     // column k of L
-            __syncthreads();
-            const int n = R - k - 1;
-            for (int e = tid; e < n * n; e += nthreads) {
-                const int i = k + 1 + e / n, j = k + 1 + e % n;
-                if (j <= i) V[j][i] -= V[k][i] * V[k][j];
-            }
-            __syncthreads();
-        }
-        if (!fail) {
-            // L^-1, one column per thread (forward substitution), stored in W: Linv(i,j) == W[j][i]
-            __syncthreads();
-            if (tid < R) {
-                const int j = tid;
-                for (int i = 0; i < j; ++i) W[j][i] = 0.0;
-                W[j][j] = 1.0 / dg[j];
-                for (int i = j + 1; i < R; ++i) {
-                    double sum = 0.0;
-                    for (int k = j; k < i; ++k) sum += V[k][i] * W[j][k];
-                    W[j][i] = -sum / dg[i];
-                }
-            }
-            __syncthreads();
-            for (int e = tid; e < R * R; e += nthreads) {
-                const int a = e / R, b = e % R;
-                double sum = 0.0;
-                for (int k = max(a, b); k < R; ++k) sum += W[a][k] * W[b][k];
-                P[e] = sum;
-            }
-            if (tid == 0) info[0] = R;
-            return;
-        }
-        __syncthreads();
-        for (int e = tid; e < R * R; e += nthreads) V[e % R][e / R] = (e % R == e / R) ? 1.0 : 0.0;
-        __syncthreads();
-    }
-    // scale reference for the "both columns negligible" skip
-    if (warp == 0) {
-        double mx = 0.0;
-        for (int j = lane; j < R; j += 32) {
-            double s = 0.0;
-            for (int i = 0; i < R; ++i) s += W[j][i] * W[j][i];
-            mx = fmax(mx, s);
-        }
-        mx = warp_max(mx);
-        if (lane == 0) smax2 = mx;
-    }
-    __syncthreads();
-    const double eps = DBL_EPSILON;
-    const double negl = smax2 * (R * eps) * (R * eps) * 1e-4;  // far below the pinv cut-off
-
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        for (int step = 0; step < m; ++step) {
-            if (warp < npairs) {
-                int p, q;
-                if (warp == 0) { p = m; q = step % m; }
-                else { p = (step + warp) % m; q = (step - warp + m) % m; }
-                if (p > q) { const int t = p; p = q; q = t; }
-                if (q < R) {
-                    double wp0 = (lane < R) ? W[p][lane] : 0.0, wq0 = (lane < R) ? W[q][lane] : 0.0;
-                    double wp1 = (lane + 32 < R) ? W[p][lane + 32] : 0.0, wq1 = (lane + 32 < R) ? W[q][lane + 32] : 0.0;
-                    const double alpha = warp_sum(wp0 * wp0 + wp1 * wp1);
-                    const double beta = warp_sum(wq0 * wq0 + wq1 * wq1);
-                    const double gamma = warp_sum(wp0 * wq0 + wp1 * wq1);
-                    const double lim = eps * sqrt(alpha * beta);
-                    const bool tiny = (alpha <= negl && beta <= negl);
-                    if (fabs(gamma) > lim && !tiny && alpha * beta > 0.0) {
-                        const double zeta = (beta - alpha) / (2.0 * gamma);
-                        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-                        if (lane < R) {
-                            W[p][lane] = c * wp0 - s * wq0;
-                            W[q][lane] = s * wp0 + c * wq0;
-                            const double vp = V[p][lane], vq = V[q][lane];
-                            V[p][lane] = c * vp - s * vq;
-                            V[q][lane] = s * vp + c * vq;
-                        }
-                        if (lane + 32 < R) {
-                            W[p][lane + 32] = c * wp1 - s * wq1;
-                            W[q][lane + 32] = s * wp1 + c * wq1;
-                            const double vp = V[p][lane + 32], vq = V[q][lane + 32];
-                            V[p][lane + 32] = c * vp - s * vq;
-                            V[q][lane + 32] = s * vp + c * vq;
-                        }
-                        if (lane == 0) flag_rot = 1;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        const int any = flag_rot;
-        __syncthreads();
-        if (tid == 0) flag_rot = 0;
-        __syncthreads();
-        if (!any) break;
-    }
-    // singular values and cut-off
-    for (int j = warp; j < R; j += (nthreads >> 5)) {
-        double s = 0.0;
-        for (int i = lane; i < R; i += 32) s += W[j][i] * W[j][i];
-        s = warp_sum(s);
-        if (lane == 0) sig2[j] = s;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double mx = 0.0;
-        for (int j = 0; j < R; ++j) mx = fmax(mx, sig2[j]);
-        smax2 = mx;
-        const double cut = (double)R * eps * sqrt(mx);
-        int kept = 0;
-        for (int j = 0; j < R; ++j) {
-            if (sqrt(sig2[j]) > cut) ++kept;
-            else sig2[j] = 0.0;  // dropped
-        }
-        info[0] = kept;
-    }
-    __syncthreads();
-    for (int e = tid; e < R * R; e += nthreads) {
-        const int a = e / R, b = e % R;
-        double s = 0.0;
-        for (int j = 0; j < R; ++j)
-            if (sig2[j] > 0.0) s += V[j][a] * W[j][b] / sig2[j];
-        P[e] = s;
-    }
+    const int kept = block_pinv(s, G, ndim, R, mode, [&](int a, int b, double v) { P[a * R + b] = v; });
+    if (threadIdx.x == 0) info[0] = kept;
 }
 
 // fit (cp.py:157-159) with ||P||^2 from the Grams (ktensor.py:113-126)
@@ -564,15 +394,14 @@ extern "C" int skt_hadamard_pinv(const double *G_d, int ndim, int rank, int mode
     SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= -1 && mode < ndim, SKT_EINVAL, "bad ndim/mode");
     int rc = check_rank(rank);
     if (rc) return rc;
-    const int npairs = (rank + 1) / 2;
-    const int threads = std::max(64, 32 * npairs);
-    const size_t smem = (size_t)(2 * MAXR * (MAXR + 1) + MAXR) * sizeof(double);
+    const size_t smem = pinv_smem_doubles(rank) * sizeof(double);
     static bool cfg = false;
     if (!cfg) {
-        SKT_CUDA(cudaFuncSetAttribute(hadamard_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SKT_CUDA(cudaFuncSetAttribute(hadamard_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(pinv_smem_doubles(MAXR) * sizeof(double))));
         cfg = true;
     }
-    hadamard_pinv_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(G_d, ndim, rank, mode, P_d, info_d);
+    hadamard_pinv_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(G_d, ndim, rank, mode, P_d, info_d);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
 }

@@ -1,0 +1,307 @@
+// Fused factor update for small factors: everything cp.als does between two MTTKRPs
+// (sktensor/cp.py:144-159) in ONE single-CTA kernel when the factor fits in shared memory:
+//
+//   Y = hadamard_{m != n} G_m ;  P = pinv(Y)            cp.py:144-147   (pinv.cuh)
+//   Unew = M P                                          cp.py:147       (FP64 tensor-core MMA, operands in smem)
+//   lambda = column 2-norms (itr 0) | max(col max, 1)   cp.py:149-153
+//   U_n = Unew / lambda ;  G_n = U_n^T U_n              cp.py:154, 146  (DMMA again)
+//   <P,X> = sum_r lambda_r sum_i U[i,r] M[i,r]          ktensor.py:128-150 via the last-mode MTTKRP
+//   fit = 1 - (|X|^2 + |P|^2 - 2<P,X>) / |X|^2          cp.py:157-159, ktensor.py:113-126
+//
+// For the dense configurations the factors are tiny (512 x 32, 160 x 64): three launches with grid-wide
+// "last block" reductions cost ~55 us per mode against ~300 us for the MTTKRP itself; this kernel does the
+// same arithmetic in ~10 us.  Tall factors (sparse tensors: 10^5..10^7 rows) keep the streaming kernels of
+// cpals.cu.  All reductions are ordered: results are bitwise reproducible.
+#include <algorithm>
+#include <cfloat>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "pinv.cuh"
+
+namespace skt {
+namespace {
+
+constexpr int FT = 1024;            // threads
+constexpr int FW = FT / 32;         // warps
+constexpr int QMAX = 10;            // 8x8 output blocks per warp in the solve (covers rows8*R8/64 <= 320)
+constexpr int MAXELEMS = 20480;     // rows8 * R8 limit (160 KB of factor in shared memory)
+
+struct FusedParams {
+    const double *M;      // rows x R MTTKRP
+    double *G;            // [ndim][R][R]; G[mode] is rewritten
+    double *U;            // rows x R out
+    double *lambda;       // R out
+    int *info;            // rank kept by pinv, -1 on non-finite Y
+    double *ip;           // <P,X> out (may be NULL)
+    const double *normX2; // with fit: |X|^2
+    double *fit;          // out[0] = fit, out[1] = |P|^2 (may be NULL)
+    long long rows;
+    int R, ndim, mode, first_iter;
+    long long *trace;     // debug: clock64 at the phase boundaries (may be NULL)
+};
+
+__host__ __device__ inline int round8(int x) { return (x + 7) & ~7; }
+
+struct FusedLayout {
+    int R8, LD, rows8;
+    size_t ms, ps, pv, cs, gp, lam, red, total;   // offsets in doubles
+};
+
+__host__ __device__ inline FusedLayout fused_layout(long long rows, int R) {
+    FusedLayout L;
+    L.R8 = round8(R);
+    L.LD = L.R8 + 4;                       // == 4 or 12 mod 16: conflict-free DMMA fragment loads
+    L.rows8 = round8((int)rows);
+    size_t o = 0;
+    L.ms = o; o += (size_t)L.rows8 * L.LD;          // M, then Unew, then U
+    L.ps = o; o += (size_t)L.R8 * L.LD;             // P (zero padded)
+    L.pv = o; o += pinv_smem_doubles(R);            // pinv scratch; later: column partials / Gram partials
+    L.cs = L.pv;                                    // [nchunk][RP] column-statistic partials (aliases pinv scratch)
+    L.gp = L.pv;                                    // Gram partials [S][R8][R8+1]   (aliases pinv scratch)
+    const size_t gp_need = (size_t)FW * 64 + 64;    // at most 32 jobs x 64 entries in flight per round
+    const size_t cs_need = (size_t)FT;
+    const size_t alias = gp_need > cs_need ? gp_need : cs_need;
+    if (pinv_smem_doubles(R) < alias) o = L.pv + alias;
+    L.lam = o; o += 64;
+    L.red = o; o += 64;
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_constant__ FusedParams p) {
+    extern __shared__ __align__(16) double fsm[];
+    const int R = p.R, rows = (int)p.rows;
+    const FusedLayout L = fused_layout(p.rows, R);
+    const int R8 = L.R8, LD = L.LD, rows8 = L.rows8;
+    double *Ms = fsm + L.ms, *Ps = fsm + L.ps, *cs = fsm + L.cs, *gp = fsm + L.gp, *lam = fsm + L.lam, *red = fsm + L.red;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+#define SKT_TRACE(k) do { if (p.trace && tid == 0) p.trace[k] = clock64(); } while (0)
+    SKT_TRACE(0);
+
+    // ---- stage M (zero padded to rows8 x R8) while the pseudo-inverse is being formed
+    for (int e = tid; e < rows8 * R8; e += FT) {
+        const int i = e / R8, c = e - i * R8;
+        Ms[i * LD + c] = (i < rows && c < R) ? __ldg(p.M + (long long)i * R + c) : 0.0;
+    }
+    for (int e = tid; e < R8 * LD; e += FT) Ps[e] = 0.0;
+
+    // ---- P = pinv(Y) straight into shared memory
+    const PinvShared ps = pinv_carve(fsm + L.pv, R);
+    const bool bad = pinv_load_y(ps, p.G, p.ndim, R, p.mode);   // contains block barriers: Ms / Ps are visible after it
+    SKT_TRACE(1);
+    if (bad) {
+        // the reference raises ValueError('array must not contain infs or NaNs') inside pinv (cp.py:147)
+        for (int e = tid; e < rows * R; e += FT) p.U[e] = nan("");
+        if (tid == 0) p.info[0] = -1;
+        return;
+    }
+    const int kept = block_pinv(ps, p.G, p.ndim, R, p.mode, [&](int a, int b, double v) { Ps[a * LD + b] = v; });
+    if (tid == 0) p.info[0] = kept;
+    __syncthreads();
+    SKT_TRACE(2);
+
+    // ---- Unew = M P : 8x8 output blocks, K = R8, FP64 tensor cores; warp w owns blocks w, w+32, ...
+    const int ncb = R8 >> 3, nrb = rows8 >> 3, nblk = nrb * ncb;
+    double acc[QMAX][2];
+    double ipp = 0.0;
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q) {
+        acc[q][0] = acc[q][1] = 0.0;
+        const int blk = warp + FW * q;
+        if (blk < nblk) {
+            const int ib = blk / ncb, jb = blk - ib * ncb;
+            const double *arow = Ms + (ib * 8 + g) * LD + t4;
+            const double *bcol = Ps + t4 * LD + jb * 8 + g;
+            for (int k0 = 0; k0 < R8; k0 += 4) dmma884(acc[q][0], acc[q][1], arow[k0], bcol[k0 * LD]);
+            if (p.ip) {   // <P,X> = sum Unew[i,c] M[i,c]  (lambda_c * U[i,c] == Unew[i,c])
+                const double *mrow = Ms + (ib * 8 + g) * LD + jb * 8 + 2 * t4;
+                ipp += acc[q][0] * mrow[0] + acc[q][1] * mrow[1];
+            }
+        }
+    }
+    __syncthreads();            // every warp is done reading M
+#pragma unroll
+    for (int q = 0; q < QMAX; ++q) {
+        const int blk = warp + FW * q;
+        if (blk < nblk) {
+            const int ib = blk / ncb, jb = blk - ib * ncb;
+            double *urow = Ms + (ib * 8 + g) * LD + jb * 8 + 2 * t4;
+            urow[0] = acc[q][0];
+            urow[1] = acc[q][1];
+        }
+    }
+    // <P,X>: ordered block sum
+    if (p.ip) {
+        ipp = warp_sum(ipp);
+        if (lane == 0) red[warp] = ipp;
+    }
+    __syncthreads();
+    if (p.ip && tid == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < FW; ++w) sum += red[w];
+        p.ip[0] = sum;
+        red[FW] = sum;
+    }
+
+    SKT_TRACE(3);
+    // ---- column statistics: sum of squares (first iteration) or signed maximum, in a fixed order
+    {
+        const int RP = (R <= 16) ? 16 : (R <= 32 ? 32 : 64);
+        const int nchunk = FT / RP;
+        const int c = tid % RP, ch = tid / RP;
+        const int per = (rows + nchunk - 1) / nchunk;
+        double st = p.first_iter ? 0.0 : -DBL_MAX;
+        if (c < R) {
+            const int i1 = min(rows, (ch + 1) * per);
+            for (int i = ch * per; i < i1; ++i) {
+                const double v = Ms[i * LD + c];
+                st = p.first_iter ? st + v * v : fmax(st, v);
+            }
+        }
+        cs[ch * RP + c] = st;
+        __syncthreads();
+        if (tid < R) {
+            double sacc = p.first_iter ? 0.0 : -DBL_MAX;
+            for (int k = 0; k < nchunk; ++k) {
+                const double v = cs[k * RP + tid];
+                sacc = p.first_iter ? sacc + v : fmax(sacc, v);
+            }
+            const double l = p.first_iter ? sqrt(sacc) : (sacc < 1.0 ? 1.0 : sacc);   // cp.py:150 / cp.py:152-153
+            lam[tid] = l;
+            p.lambda[tid] = l;
+        }
+        __syncthreads();
+    }
+
+    SKT_TRACE(4);
+    // ---- U = Unew / lambda (shared + global)
+    for (int e = tid; e < rows * R; e += FT) {
+        const int i = e / R, c = e - i * R;
+        const double v = Ms[i * LD + c] / lam[c];
+        Ms[i * LD + c] = v;
+        p.U[e] = v;
+    }
+    __syncthreads();
+
+    SKT_TRACE(5);
+    // ---- G_n = U^T U : 8x8 blocks x S row parts on the tensor cores, parts summed in order
+    {
+        const int nb2 = ncb * ncb;
+        const int S = max(1, FW / nb2);
+        const int rp = (((rows8 + S - 1) / S) + 3) & ~3;   // rows per part, a multiple of the DMMA k step
+        const int njobs = nb2 * S;
+        double *Gn = p.G + (size_t)p.mode * R * R;
+        for (int j0 = 0; j0 < njobs; j0 += FW) {
+            const int job = j0 + warp;
+            double c0 = 0.0, c1 = 0.0;
+            int ab = 0, bb = 0, part = 0;
+            if (job < njobs) {
+                const int b2 = job % nb2;
+                part = job / nb2;
+                ab = b2 / ncb; bb = b2 - ab * ncb;
+                const int k1 = min(rows8, (part + 1) * rp);
+                const double *ap = Ms + t4 * LD + ab * 8 + g;
+                const double *bp = Ms + t4 * LD + bb * 8 + g;
+                for (int k = part * rp; k < k1; k += 4) dmma884(c0, c1, ap[k * LD], bp[k * LD]);
+                double *dst = gp + (size_t)warp * 64 + g * 8 + 2 * t4;
+                dst[0] = c0;
+                dst[1] = c1;
+            }
+            __syncthreads();
+            // the S parts of one block sit in warps b2, b2 + nb2, ... of this round
+            if (S > 1) {
+                for (int e = tid; e < nb2 * 64; e += FT) {
+                    const int b2 = e >> 6, w = e & 63;
+                    double sum = 0.0;
+                    for (int s_ = 0; s_ < S; ++s_) sum += gp[(size_t)(s_ * nb2 + b2) * 64 + w];
+                    const int a_ = (b2 / ncb) * 8 + (w >> 3), b_ = (b2 % ncb) * 8 + (w & 7);
+                    if (a_ < R && b_ < R) Gn[a_ * R + b_] = sum;
+                }
+            } else {
+                for (int e = tid; e < FW * 64; e += FT) {
+                    const int jb_ = j0 + (e >> 6), w = e & 63;
+                    if (jb_ < njobs) {
+                        const int a_ = (jb_ / ncb) * 8 + (w >> 3), b_ = (jb_ % ncb) * 8 + (w & 7);
+                        if (a_ < R && b_ < R) Gn[a_ * R + b_] = gp[e];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    SKT_TRACE(6);
+    // ---- fit (cp.py:157-159); G_n was written by this block, so it is visible to it after the barrier
+    if (p.fit) {
+        double sacc = 0.0;
+        for (int e = tid; e < R * R; e += FT) {
+            const int a = e / R, b = e - a * R;
+            double y = lam[a] * lam[b];
+            for (int k = 0; k < p.ndim; ++k) y *= p.G[(size_t)k * R * R + e];
+            sacc += y;
+        }
+        sacc = warp_sum(sacc);
+        __syncthreads();
+        if (lane == 0) red[warp] = sacc;
+        __syncthreads();
+        if (tid == 0) {
+            double normP2 = 0.0;
+            for (int w = 0; w < FW; ++w) normP2 += red[w];
+            const double nx2 = p.normX2[0];
+            p.fit[0] = 1.0 - (nx2 + normP2 - 2.0 * red[FW]) / nx2;
+            p.fit[1] = normP2;
+        }
+    }
+    SKT_TRACE(7);
+}
+
+}  // namespace
+}  // namespace skt
+
+using namespace skt;
+
+extern "C" int skt_cp_update_fused_fits(int64_t rows, int rank) {
+    if (rows < 1 || rank < 1 || rank > SKT_MAX_RANK || rows > (1 << 20)) return 0;
+    const FusedLayout L = fused_layout(rows, rank);
+    if ((long long)L.rows8 * L.R8 > MAXELEMS) return 0;
+    if ((long long)(L.rows8 / 8) * (L.R8 / 8) > (long long)QMAX * FW) return 0;
+    return (L.total * sizeof(double) <= smem_optin_bytes()) ? 1 : 0;
+}
+
+extern "C" int skt_cp_update_fused(const double *M_d, int64_t rows, int rank, int ndim, int mode, int first_iter,
+                                   double *G_d, double *U_d, double *lambda_d, int *info_d, double *ip_d,
+                                   const double *normX2_d, double *fit_d, skt_stream stream) {
+    SKT_REQUIRE(M_d && G_d && U_d && lambda_d && info_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= 0 && mode < ndim, SKT_EINVAL, "bad ndim/mode");
+    SKT_REQUIRE(fit_d == nullptr || (ip_d != nullptr && normX2_d != nullptr), SKT_EINVAL, "the fit needs ip_d and normX2_d");
+    SKT_REQUIRE(skt_cp_update_fused_fits(rows, rank), SKT_EUNSUPPORTED,
+                "factor of %lld x %d does not fit the fused update kernel", (long long)rows, rank);
+    const FusedLayout L = fused_layout(rows, rank);
+    const size_t smem = L.total * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        SKT_CUDA(cudaFuncSetAttribute(cp_update_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin_bytes()));
+        configured = smem_optin_bytes();
+    }
+    FusedParams p;
+    p.M = M_d; p.G = G_d; p.U = U_d; p.lambda = lambda_d; p.info = info_d; p.ip = ip_d; p.normX2 = normX2_d; p.fit = fit_d;
+    p.rows = rows; p.R = rank; p.ndim = ndim; p.mode = mode; p.first_iter = first_iter;
+    p.trace = nullptr;
+    static long long *trace_d = nullptr;
+    const char *tr = getenv("SKT_FUSED_TRACE");
+    if (tr && tr[0] == '1') {
+        if (!trace_d) cudaMalloc(&trace_d, 8 * sizeof(long long));
+        p.trace = trace_d;
+    }
+    cp_update_fused_kernel<<<1, FT, smem, (cudaStream_t)stream>>>(p);
+    SKT_LAUNCH_CHECK();
+    if (p.trace) {
+        long long h[8];
+        cudaMemcpy(h, trace_d, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "fused trace (cycles): stage+loadY %lld  pinv %lld  solve %lld  stats %lld  normalise %lld  gram %lld  fit %lld  total %lld\n",
+                h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[7] - h[0]);
+    }
+    return SKT_OK;
+}

@@ -204,6 +204,19 @@ def normalise_gram(U, colstat, first_iter, lam=None, G=None, Mip=None, ip=None):
     return lam, G, ip
 
 
+def cp_update_fused_fits(rows, rank):
+    return bool(_lib.load().skt_cp_update_fused_fits(int(rows), int(rank)))
+
+
+def cp_update_fused(M, G, mode, first_iter, U, lam, info, ip=None, normX2=None, fit=None):
+    """pinv + solve + normalise + Gram (+ <P,X> and the fit) for a small factor in one launch (cp.py:144-159)."""
+    lib = _lib.load()
+    rows, R = M.shape
+    _lib.check(lib.skt_cp_update_fused(dev.ptr(M), rows, R, int(G.shape[0]), mode, 1 if first_iter else 0, dev.ptr(G),
+                                       dev.ptr(U), dev.ptr(lam), dev.ptr(info), dev.ptr(ip), dev.ptr(normX2),
+                                       dev.ptr(fit), dev.stream_ptr()))
+
+
 def cp_fit(G, lam, ip, normX2, out=None):
     lib = _lib.load()
     if out is None:

@@ -66,6 +66,9 @@ PROTOTYPES = {
     'skt_normalise_gram_workspace': (C.c_size_t, [C.c_int64, C.c_int]),
     'skt_normalise_gram': (C.c_int, [c_dp, c_dp, C.c_int64, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp,
                                      C.c_void_p, C.c_size_t, c_stream]),
+    'skt_cp_update_fused_fits': (C.c_int, [C.c_int64, C.c_int]),
+    'skt_cp_update_fused': (C.c_int, [c_dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp,
+                                      C.c_void_p, c_dp, c_dp, c_dp, c_stream]),
     'skt_cp_fit': (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_stream]),
     'skt_ttm_dense': (C.c_int, [c_dp, c_i64p, C.c_int, c_dp, C.c_int64, C.c_int, C.c_int, c_dp, c_stream]),
     'skt_unfold_gram_workspace': (C.c_size_t, [c_i64p, C.c_int, C.c_int]),

@@ -137,6 +137,9 @@ class CudaBackend(object):
     def normalise_gram(self, U, colstat, first, lam, G, Mip, ip):
         return self.K.normalise_gram(U, colstat, first, lam=lam, G=G, Mip=Mip, ip=ip)
     def cp_fit(self, G, lam, ip, normX2, out): return self.K.cp_fit(G, lam, ip, normX2, out=out)
+    def update_fused_fits(self, rows, R): return self.K.cp_update_fused_fits(rows, R)
+    def update_fused(self, M, G, n, first, U, lam, info, ip, normX2, fit):
+        return self.K.cp_update_fused(M, G, n, first, U, lam, info, ip=ip, normX2=normX2, fit=fit)
 
 
 _backend_factory = CudaBackend
@@ -260,6 +263,12 @@ class CpAlsEngine(object):
         self._m0_ready = False      # True when M[0] already holds the MTTKRP for the coming sweep
         self._pending = None
 
+        # ---- modes whose whole update runs in the fused single-launch kernel: the factor fits in shared
+        # memory and the solve is replicated (the sharded mode needs collectives between the phases)
+        use_fused = hasattr(be, 'update_fused') and os.environ.get('SKT_NO_FUSED_UPDATE', '0') != '1'
+        self.fused = [bool(use_fused and not (comm.active and m == self.s) and be.update_fused_fits(self.lshape[m], R))
+                      for m in range(N)]
+
         # ---- dimension tree (dense, N >= 3): two passes over X per sweep instead of N.  Modes [0, s) are
         # served by T_A = X contracted with U_s..U_{N-1}; modes [s, N) by T_B = X contracted with
         # U_0..U_{s-1}.  A one-mode group needs no second stage: its partial tensor IS the MTTKRP.
@@ -327,11 +336,20 @@ class CpAlsEngine(object):
 
     def sweep(self, first_iter, want_fit=True):
         be, comm, N = self.be, self.comm, self.N
+        fit_done = False
         for n in range(N):
             if n == 0 and self._m0_ready:
                 M, self._m0_ready = self.M[0], False
             else:
                 M = self.mttkrp(n)
+            last = (n == N - 1) and want_fit
+            if self.fused[n]:
+                # small factor, replicated solve: pinv + solve + normalise + Gram (+ <P,X>, fit) in one launch
+                be.update_fused(M, self.G, n, first_iter, self.Ud[n], self.lam, self.info[n:n + 1],
+                                self.ip if last else None, self.normX2 if last else None,
+                                self.fitout if last else None)
+                fit_done = fit_done or last
+                continue
             be.hadamard_pinv(self.G, n, self.P, self.info[n:n + 1])
             be.solve_stats(M, self.P, first_iter, self.Ud[n], self.colstat)
             if comm.active and n == self.s:
@@ -339,14 +357,13 @@ class CpAlsEngine(object):
                     comm.allreduce_sum(self.colstat)
                 else:
                     comm.allreduce_max(self.colstat)
-            last = (n == N - 1) and want_fit
             be.normalise_gram(self.Ud[n], self.colstat, first_iter, self.lam, self.G[n],
                               M if last else None, self.ip if last else None)
             if comm.active and n == self.s:
                 comm.allreduce_sum(self.G[n])
                 if last:
                     comm.allreduce_sum(self.ip)
-        if want_fit:
+        if want_fit and not fit_done:
             be.cp_fit(self.G, self.lam, self.ip, self.normX2, self.fitout)
 
     def begin_read(self):

@@ -114,3 +114,16 @@ class NumpyBackend(object):
         out[0] = 1.0 - (nx2 + normP2 - 2.0 * float(ip[0])) / nx2
         out[1] = normP2
         return out
+
+    # the fused small-factor update (cpals_fused.cu): same arithmetic, one call
+    def update_fused_fits(self, rows, R):
+        return int(rows) * int(R) <= 20480 and R <= 64
+
+    def update_fused(self, M, G, n, first, U, lam, info, ip, normX2, fit):
+        P = torch.zeros(G.shape[1:], dtype=torch.float64)
+        self.hadamard_pinv(G, n, P, info)
+        colstat = torch.zeros(G.shape[1], dtype=torch.float64)
+        self.solve_stats(M, P, first, U, colstat)
+        self.normalise_gram(U, colstat, first, lam, G[n], M if ip is not None else None, ip)
+        if fit is not None:
+            self.cp_fit(G, lam, ip, normX2, fit)

@@ -260,3 +260,92 @@ def test_tucker_hooi_golden(golden):
     assert relerr(np.abs(core), np.abs(golden['hooi_b_core'])) < 1e-6
     core, U = tucker_hooi(dtensor(X), 2, init='random', maxIter=3)           # scalar rank (tucker.py:90-91)
     assert core.shape == (2, 2, 2)
+
+
+# ------------------------------------------------------------------ fused small-factor update (cpals_fused.cu)
+@pytest.mark.parametrize('rows,R,N', [(10, 3, 3), (11, 3, 3), (512, 32, 3), (160, 64, 4), (97, 17, 3), (1200, 16, 3),
+                                      (8, 1, 2), (300, 48, 5), (64, 64, 3), (2500, 8, 3)])
+def test_fused_update_matches_reference_arithmetic(K, dev, rows, R, N):
+    """One launch == pinv(Y) . M, normalise, Gram, <P,X>, fit of cp.py:144-159 (NumPy/SciPy restatement here)."""
+    if not K.cp_update_fused_fits(rows, R):
+        pytest.skip('does not fit the fused kernel')
+    rng = np.random.RandomState(rows * 131 + R)
+    F = [rng.rand(40 + 3 * m, R) for m in range(N)]
+    G = np.stack([f.T.dot(f) for f in F])
+    M = rng.rand(rows, R) * 2 - 0.5
+    normX2 = 1234.5
+    for mode in (0, N - 1):
+        for first in (True, False):
+            Gd = dev.to_device(G)
+            U, lam, info = dev.empty((rows, R)), dev.empty((R,)), dev.zeros((1,), np.int32)
+            ip, fit = dev.zeros((1,)), dev.zeros((2,))
+            K.cp_update_fused(dev.to_device(M), Gd, mode, first, U, lam, info, ip=ip,
+                              normX2=dev.to_device(np.array([normX2])), fit=fit)
+            Y = np.ones((R, R))
+            for m in range(N):
+                if m != mode:
+                    Y = Y * G[m]
+            Unew = M.dot(pinv(Y))
+            l = np.sqrt((Unew ** 2).sum(0)) if first else np.where(Unew.max(0) < 1, 1.0, Unew.max(0))
+            Uref = Unew / l
+            cond = np.linalg.cond(Y)
+            tol = 1e-13 * max(1e2, cond)
+            assert int(dev.to_host(info)[0]) == R
+            assert relerr(dev.to_host(U), Uref) < tol, (rows, R, mode, first)
+            assert relerr(dev.to_host(lam), l) < tol
+            Gn = dev.to_host(Gd)
+            assert relerr(Gn[mode], Uref.T.dot(Uref)) < tol
+            for m in range(N):
+                if m != mode:
+                    assert (Gn[m] == G[m]).all()
+            ipref = (l * Uref * M).sum()
+            assert abs(dev.to_host(ip)[0] - ipref) < tol * abs(ipref)
+            G2 = G.copy()
+            G2[mode] = Uref.T.dot(Uref)
+            coef = np.outer(l, l)
+            for m in range(N):
+                coef = coef * G2[m]
+            fitref = 1.0 - (normX2 + coef.sum() - 2 * ipref) / normX2
+            got = dev.to_host(fit)
+            assert abs(got[0] - fitref) < tol * max(1.0, abs(fitref)) * 10
+            assert abs(got[1] - coef.sum()) < tol * coef.sum()
+
+
+def test_fused_update_singular_and_nonfinite(K, dev, golden):
+    # rank-deficient Y goes through the Jacobi pinv inside the fused kernel (KAT-5 style); NaN gives status -1
+    for name in golden.j['solve_cases']:
+        M, Y = golden['slv_%s_M' % name], golden['slv_%s_Y' % name]
+        R = M.shape[1]
+        F = [golden['slv_%s_F0' % name], golden['slv_%s_F1' % name]]
+        G = np.zeros((3, R, R))
+        G[1], G[2] = F[0].T.dot(F[0]), F[1].T.dot(F[1])
+        for itr in (0, 1):
+            if name == 'zerocol' and itr == 0:
+                continue
+            Gd = dev.to_device(G)
+            U, lam, info = dev.empty(M.shape), dev.empty((R,)), dev.zeros((1,), np.int32)
+            K.cp_update_fused(dev.to_device(M), Gd, 0, itr == 0, U, lam, info)
+            assert relerr(dev.to_host(U), golden['slv_%s_U%d' % (name, itr)]) < 1e-8, (name, itr)
+            assert relerr(dev.to_host(lam), golden['slv_%s_lam%d' % (name, itr)]) < 1e-9, (name, itr)
+    G = np.ones((3, 4, 4))
+    G[1, 2, 2] = np.nan
+    U, lam, info = dev.empty((6, 4)), dev.empty((4,)), dev.zeros((1,), np.int32)
+    K.cp_update_fused(dev.to_device(np.ones((6, 4))), dev.to_device(G), 0, True, U, lam, info)
+    assert int(dev.to_host(info)[0]) == -1
+
+
+def test_fused_and_streaming_updates_agree():
+    """cp_als with the fused update and with the three streaming kernels: same trajectory."""
+    import os
+    from sktensor import cp_als, dtensor
+    rng = np.random.RandomState(2)
+    X = rng.rand(30, 28, 26)
+    res = {}
+    for flag in ('0', '1'):
+        os.environ['SKT_NO_FUSED_UPDATE'] = flag
+        np.random.seed(9)
+        P, fit, itr, _ = cp_als(dtensor(X), 5, init='random', max_iter=40)
+        res[flag] = (float(fit), itr)
+    os.environ['SKT_NO_FUSED_UPDATE'] = '0'
+    assert res['0'][1] == res['1'][1]
+    assert abs(res['0'][0] - res['1'][0]) < 1e-10

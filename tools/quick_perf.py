@@ -97,6 +97,25 @@ def main():
                     med, best = timeit(lambda: K.kr_reduce(TB, shape[s_:], U[s_:], R, n - s_, out=out))
                     print('  kr_reduce group B mode %d: median %.4f ms (%.0f GB/s over T)' % (n, med, TB.numel() * 8 / med / 1e6))
             del X, TA, TB
+    if 'small' in which:
+        for rows, R, N in ((512, 32, 3), (160, 64, 4)):
+            rng = np.random.RandomState(0)
+            G = dev.to_device(np.stack([(lambda f: f.T.dot(f))(rng.rand(rows, R)) for _ in range(N)]))
+            M = dev.to_device(rng.rand(rows, R))
+            U, lam, info = dev.empty((rows, R)), dev.empty((R,)), dev.zeros((1,), np.int32)
+            P, colstat = dev.empty((R, R)), dev.empty((R,))
+            ip, fit, nx2 = dev.zeros((1,)), dev.zeros((2,)), dev.to_device(np.array([1e6]))
+            G0 = G.clone()
+            def fused():
+                K.cp_update_fused(M, G, 0, False, U, lam, info, ip=ip, normX2=nx2, fit=fit)
+            print('rows=%d R=%d: fused update            %.2f us' % (rows, R, 1e3 * timeit(fused, reps=20)[0]))
+            G.copy_(G0)
+            print('             hadamard_pinv           %.2f us' % (1e3 * timeit(lambda: K.hadamard_pinv(G, 0, P=P, info=info), reps=20)[0]))
+            print('             solve_stats             %.2f us' % (1e3 * timeit(lambda: K.solve_stats(M, P, False, Unew=U, colstat=colstat), reps=20)[0]))
+            print('             normalise_gram          %.2f us' % (1e3 * timeit(lambda: K.normalise_gram(U, colstat, False, lam=lam, G=G[0], Mip=M, ip=ip), reps=20)[0]))
+            print('             cp_fit                  %.2f us' % (1e3 * timeit(lambda: K.cp_fit(G, lam, ip, nx2, out=fit), reps=20)[0]))
+            e = dev.empty((1,))
+            print('             (empty torch op)        %.2f us' % (1e3 * timeit(lambda: e.zero_(), reps=20)[0]))
     if 'upload' in which:
         h = np.random.RandomState(0).rand(512, 512, 512)
         for rep in range(3):
