@@ -188,6 +188,12 @@ SKT_API int skt_cp_fit(const double *G_d, int ndim, int rank, const double *lamb
  * (dtensor._ttm_compute, dtensor.py:58-76), without the transpose/reshape copies.        */
 SKT_API int skt_ttm_dense(const double *X_d, const int64_t *shape, int ndim, const double *V_d,
                   int64_t p, int mode, int transp, double *Y_d, skt_stream stream);
+/* Y = X x_0 V^T (V is shape[0] x p) with the NEW mode stored LAST: Y has shape (shape[1], ..., shape[ndim-1], p).
+ * Same numbers as dtensor._ttm_compute (dtensor.py:58-76) up to that rotation of the mode order; tucker.hooi
+ * keeps the rotated order between the steps of its TTM chain (tucker.py:103, core.py:99-102), so the big first
+ * contraction runs as an M-major GEMM on the TMA / FP64 tensor-core kernel and no transpose is materialised. */
+SKT_API int skt_ttm_dense_first_rot(const double *X_d, const int64_t *shape, int ndim, const double *V_d, int64_t p,
+                            double *Y_d, skt_stream stream);
 /* G = X_(mode) X_(mode)^T  (I_mode x I_mode), the Gram inside core.nvecs (core.py:279,285). */
 SKT_API size_t skt_unfold_gram_workspace(const int64_t *shape, int ndim, int mode);
 SKT_API int skt_unfold_gram(const double *X_d, const int64_t *shape, int ndim, int mode, double *G_d,

@@ -540,16 +540,20 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                 const int it = cs.item / p.nsplit;
                 const int lt = cs.tile / p.ntt, tt = cs.tile % p.ntt;
                 if (p.direct) {
-                    // plain GEMM rows (the partial contraction of the dimension tree, dimtree.cu): no weights, no
-                    // cross-row sum -- 16-byte stores from the accumulator registers, no staging, no barrier
+                    // plain GEMM rows (the partial contraction of the dimension tree, dimtree.cu, and the big TTM of
+                    // HOOI): every tile row is its own output row (l, i_n, t) -- no weights, no cross-row sum, 16-byte
+                    // stores straight from the accumulator registers, no staging, no barrier
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
-                        const long long i = (long long)it * bi + 16 * rg + 8 * a + pg;
-                        double *orow = p.out + i * p.ld + colbase + 2 * t4;
+                        const int q = 16 * rg + 8 * a + pg;
+                        int l, i, t;
+                        const bool ok = decompose(q, it, lt, tt, l, i, t);
+                        const long long rho = ((long long)l * p.In + i) * p.T + t;
+                        double *orow = p.out + rho * p.ld + colbase + 2 * t4;
 #pragma unroll
                         for (int nn = 0; nn < 4; ++nn) {
                             const int col = colbase + 8 * nn + 2 * t4;
-                            if (nn < nbw && i < p.In) {
+                            if (nn < nbw && ok) {
                                 if (p.direct == 2 && col + 1 < p.R) {
                                     *reinterpret_cast<double2 *>(orow + 8 * nn) = make_double2(acc[a][nn][0], acc[a][nn][1]);
                                 } else {
@@ -972,8 +976,11 @@ extern "C" size_t skt_mttkrp_dense_workspace(const int64_t *shape, int ndim, int
     return need;
 }
 
-extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndim, const double *const *U_d, int rank,
-                                int mode, double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+namespace skt {
+// rows_only: store the GEMM rows acc[(l, i_n, t), r] themselves (TTM semantics: no Khatri-Rao weights, no
+// reduction over l, t); needs the TMA kernel.  Otherwise the MTTKRP of `mode`.
+int dense_impl(const double *X_d, const int64_t *shape, int ndim, const double *const *U_d, int rank, int mode,
+               double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream, bool rows_only) {
     SKT_REQUIRE(X_d && U_d && M_d, SKT_EINVAL, "NULL tensor / factor list / output");
     DensePlan pl;
     int rc = make_plan(shape, ndim, rank, mode, false, pl);
@@ -986,10 +993,20 @@ extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndi
         rc = make_tensor_map(X_d, pl, tm);
         if (rc != SKT_OK) return rc;
     }
-    for (int m = 0; m < ndim; ++m)
-        SKT_REQUIRE(m == mode || U_d[m] != nullptr, SKT_EINVAL, "U[%d] is NULL (only U[mode] may be)", m);
+    if (rows_only) {
+        SKT_REQUIRE(use_tma, SKT_EUNSUPPORTED, "row-store (TTM) mode needs the TMA kernel (16-byte aligned rows)");
+        SKT_REQUIRE(rank <= 64, SKT_EUNSUPPORTED, "row-store (TTM) mode supports at most 64 columns");
+        SKT_REQUIRE(U_d[pl.c] != nullptr, SKT_EINVAL, "the matrix of the contracted mode is NULL");
+        pl.nw = 0;
+    } else {
+        for (int m = 0; m < ndim; ++m)
+            SKT_REQUIRE(m == mode || U_d[m] != nullptr, SKT_EINVAL, "U[%d] is NULL (only U[mode] may be)", m);
+    }
+    // every tile row is its own output row: the accumulators are stored straight from registers
+    const bool direct = rows_only || (use_tma && !pl.mmajor && pl.L == 1 && pl.T == 1 && pl.nw == 0);
+    const int nsplit_out = direct ? 1 : pl.nsplit;   // direct: nothing is reduced across tiles, the splits only partition them
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t need = (pl.nsplit > 1) ? (size_t)pl.nsplit * pl.In * rank * sizeof(double) : 0;
+    const size_t need = (nsplit_out > 1) ? (size_t)nsplit_out * pl.In * rank * sizeof(double) : 0;
     SKT_REQUIRE(ws_bytes >= need && (need == 0 || ws_d != nullptr), SKT_EWORKSPACE,
                 "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
 
@@ -1003,11 +1020,9 @@ extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndi
     p.nsplit = pl.nsplit; p.chunk = pl.chunk; p.nitems = pl.nitems;
     p.nk = use_tma ? (pl.Kc + TK - 1) / TK : (pl.Kc + BK - 1) / BK;
     p.nw = pl.nw;
-    // M-major tiles hold 16 l-rows per output row group, so only the K-major kernel has a 1:1 row map
-    p.direct = (use_tma && !pl.mmajor && pl.L == 1 && pl.T == 1 && pl.lg_bt == 0 && pl.lg_bl == 0 && pl.nsplit == 1 &&
-                pl.nw == 0) ? 1 : 0;
-    p.out_split_stride = (pl.nsplit > 1) ? (long long)pl.In * rank : 0;
-    double *outbase = (pl.nsplit > 1) ? (double *)ws_d : M_d;
+    p.direct = direct ? 1 : 0;
+    p.out_split_stride = (nsplit_out > 1) ? (long long)pl.In * rank : 0;
+    double *outbase = (nsplit_out > 1) ? (double *)ws_d : M_d;
     const bool xalign = (((uintptr_t)X_d) & 15) == 0;
     if (pl.mmajor) p.vecX = xalign && (pl.In % 2 == 0) && (pl.lg_bi >= 1);
     else p.vecX = xalign && (pl.Kc % 2 == 0);
@@ -1034,13 +1049,19 @@ extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndi
             rc = pl.mmajor ? launch_dense_nb<true>(nb, p, pl.grid, st) : launch_dense_nb<false>(nb, p, pl.grid, st);
         if (rc != SKT_OK) return rc;
     }
-    if (pl.nsplit > 1) {
+    if (nsplit_out > 1) {
         const long long n = (long long)pl.In * rank;
         const int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * sm_count());
-        reduce_splits_kernel<<<blocks, 256, 0, st>>>((const double *)ws_d, pl.nsplit, n, M_d);
+        reduce_splits_kernel<<<blocks, 256, 0, st>>>((const double *)ws_d, nsplit_out, n, M_d);
         SKT_LAUNCH_CHECK();
     }
     return SKT_OK;
+}
+}  // namespace skt
+
+extern "C" int skt_mttkrp_dense(const double *X_d, const int64_t *shape, int ndim, const double *const *U_d, int rank,
+                                int mode, double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    return dense_impl(X_d, shape, ndim, U_d, rank, mode, M_d, ws_d, ws_bytes, stream, false);
 }
 
 extern "C" int skt_mttkrp_dense_naive(const double *X_d, const int64_t *shape, int ndim, const double *const *U_d,

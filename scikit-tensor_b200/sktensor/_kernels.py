@@ -238,6 +238,17 @@ def ttm_dense(Xd, shape, V, mode, transp):
     return Y, tuple(oshape)
 
 
+def ttm_dense_first_rot(Xd, shape, V):
+    """``X x_0 V^T`` with the new mode stored last: shape ``(shape[1], ..., shape[-1], p)``."""
+    lib = _lib.load()
+    p = int(V.shape[1])
+    oshape = tuple(int(s) for s in shape[1:]) + (p,)
+    Y = dev.empty(oshape)
+    _lib.check(lib.skt_ttm_dense_first_rot(dev.ptr(Xd), _lib.shape_array(shape), len(shape), dev.ptr(V), p,
+                                           dev.ptr(Y), dev.stream_ptr()))
+    return Y, oshape
+
+
 def unfold_gram(Xd, shape, mode):
     lib = _lib.load()
     n = int(shape[mode])

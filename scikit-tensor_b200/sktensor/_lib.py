@@ -71,6 +71,7 @@ PROTOTYPES = {
                                       C.c_void_p, c_dp, c_dp, c_dp, c_stream]),
     'skt_cp_fit': (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_stream]),
     'skt_ttm_dense': (C.c_int, [c_dp, c_i64p, C.c_int, c_dp, C.c_int64, C.c_int, C.c_int, c_dp, c_stream]),
+    'skt_ttm_dense_first_rot': (C.c_int, [c_dp, c_i64p, C.c_int, c_dp, C.c_int64, c_dp, c_stream]),
     'skt_unfold_gram_workspace': (C.c_size_t, [c_i64p, C.c_int, C.c_int]),
     'skt_unfold_gram': (C.c_int, [c_dp, c_i64p, C.c_int, C.c_int, c_dp, C.c_void_p, C.c_size_t, c_stream]),
     'skt_probe_fp64_peaks': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -81,25 +81,36 @@ def _hooi_dense_device(X, rank, U, maxIter, conv):
         tic = time.perf_counter()
         fitold = fit
         for n in range(N):
-            # Utilde = X x_{m != n} U_m^T, modes ascending (tucker.py:103, core.py:99-102)
-            Yd, yshape = Xd, shape
+            # Utilde = X x_{m != n} U_m^T (tucker.py:103, core.py:99-102).  The first -- by far the largest --
+            # contraction runs on the TMA / FP64 tensor-core kernel: the last mode for n < N-1, the first mode
+            # (result stored with the new mode last) for n = N-1.  `layout` lists which original mode sits at
+            # each position; the later, 12x smaller contractions and the Gram work on any position.
+            if n < N - 1:
+                Yd, yshape = K.ttm_dense(Xd, shape, Ud[N - 1], N - 1, True)
+                layout = list(range(N))
+            else:
+                Yd, yshape = K.ttm_dense_first_rot(Xd, shape, Ud[0])
+                layout = list(range(1, N)) + [0]
+            done = layout[-1]
             for m in range(N):
-                if m != n:
-                    Yd, yshape = K.ttm_dense(Yd, yshape, Ud[m], m, True)
+                if m != n and m != done:
+                    Yd, yshape = K.ttm_dense(Yd, yshape, Ud[m], layout.index(m), True)
             # U_n = leading eigenvectors of Utilde_(n) Utilde_(n)^T, descending, sign-fixed (core.py:275-306)
-            G = K.unfold_gram(Yd, yshape, n)
+            G = K.unfold_gram(Yd, yshape, layout.index(n))
             _, V = t.linalg.eigh(G)
             Un = flipsign(np.array(dev.to_host(V[:, -rank[n]:].flip(1).contiguous())))
             U[n] = Un
             Ud[n] = dev.to_device(Un)
-        core_d, core_shape = K.ttm_dense(Yd, yshape, Ud[N - 1], N - 1, True)
+        core_d, core_shape = K.ttm_dense(Yd, yshape, Ud[N - 1], layout.index(N - 1), True)
         normcore2 = float(dev.to_host(K.sumsq(core_d))[0])
         fit = 1 - (np.sqrt(max(normX2 - normcore2, 0.0)) / normX)
         fitchange = abs(fitold - fit)
         _log.debug('[%3d] fit: %.5f | delta: %7.1e | secs: %.5f' % (itr, fit, fitchange, time.perf_counter() - tic))
         if itr > 1 and fitchange < conv:
             break
-    return dtensor(dev.to_host(core_d)), fit
+    # back to the reference's mode order (the last sweep's chain left the modes rotated)
+    core = np.ascontiguousarray(np.transpose(dev.to_host(core_d), [layout.index(m) for m in range(N)]))
+    return dtensor(core), fit
 
 
 def hosvd(X, rank, dims=None, dtype=None, compute_core=True):

@@ -349,3 +349,60 @@ def test_fused_and_streaming_updates_agree():
     os.environ['SKT_NO_FUSED_UPDATE'] = '0'
     assert res['0'][1] == res['1'][1]
     assert abs(res['0'][0] - res['1'][0]) < 1e-10
+
+
+# ------------------------------------------------------------------ HOOI building blocks on the tensor-core path
+@pytest.mark.parametrize('shape,p', [((48, 40, 64), 8), ((130, 36, 70), 32), ((20, 18, 16, 24), 5), ((300, 260), 64),
+                                     ((64, 64, 64), 32), ((33, 17, 21), 4), ((16, 12, 10), 70)])
+def test_ttm_tensor_core_paths(K, dev, shape, p):
+    """Last-mode TTM (row-store mode of the dense TMA kernel) and the rotated first-mode TTM equal
+    dtensor._ttm_compute (dtensor.py:58-76) for aligned, odd and over-wide (p > 64 -> generic kernel) cases."""
+    rng = np.random.RandomState(sum(shape) + p)
+    X = rng.rand(*shape) - 0.5
+    N = len(shape)
+    Xd = dev.to_device(X)
+    Vl = rng.rand(shape[-1], p) - 0.5
+    Y, ysh = K.ttm_dense(Xd, shape, dev.to_device(Vl), N - 1, True)
+    assert tuple(ysh) == tuple(shape[:-1]) + (p,)
+    assert relerr(dev.to_host(Y), orc.ttm_dense(X, Vl, N - 1, transp=True)) < 1e-13
+    Vf = rng.rand(shape[0], p) - 0.5
+    Y, ysh = K.ttm_dense_first_rot(Xd, shape, dev.to_device(Vf))
+    assert tuple(ysh) == tuple(shape[1:]) + (p,)
+    ref = np.moveaxis(orc.ttm_dense(X, Vf, 0, transp=True), 0, -1)
+    assert relerr(dev.to_host(Y), ref) < 1e-13
+
+
+@pytest.mark.parametrize('shape', [(40, 32, 32), (7, 9, 5), (384, 32, 32), (32, 384, 32), (32, 32, 384), (12, 10, 8, 6),
+                                   (1000, 24), (24, 1000), (3, 129, 2)])
+def test_unfold_gram_all_modes(K, dev, shape):
+    rng = np.random.RandomState(sum(shape))
+    X = rng.rand(*shape) - 0.5
+    Xd = dev.to_device(X)
+    for n in range(len(shape)):
+        Xn = np.moveaxis(X, n, 0).reshape(shape[n], -1)
+        assert relerr(dev.to_host(K.unfold_gram(Xd, shape, n)), Xn.dot(Xn.T)) < 1e-13, (shape, n)
+
+
+def test_tucker_hooi_midsize_vs_oracle():
+    """The rotated-layout TTM chain gives the reference's HOOI (tucker.py:36-123): same fit, same core up to
+    the sign of the factor columns, orthonormal factors spanning the same subspaces."""
+    from sktensor import dtensor, tucker_hooi
+    rng = np.random.RandomState(4)
+    for shape, rank in (((48, 40, 64), [6, 5, 8]), ((20, 18, 16, 24), [3, 4, 2, 5])):
+        N = len(shape)
+        G = rng.rand(*rank)
+        F = [np.linalg.qr(rng.randn(shape[m], rank[m]))[0] for m in range(N)]
+        X = G
+        for m in range(N):
+            X = np.moveaxis(np.tensordot(F[m], X, axes=(1, m)), 0, m)
+        X = X + 0.05 * rng.randn(*shape)
+        np.random.seed(1)
+        core, U = tucker_hooi(dtensor(X), rank, init='random', maxIter=8, conv=0)
+        np.random.seed(1)
+        core_o, U_o = orc.hooi(X, rank, init='random', maxIter=8, conv=0)[:2]
+        assert core.shape == tuple(rank)
+        assert abs(np.linalg.norm(core) - np.linalg.norm(core_o)) < 1e-9 * np.linalg.norm(core_o)
+        for m in range(N):
+            assert relerr(U[m].T.dot(U[m]), np.eye(rank[m])) < 1e-12
+            assert relerr(U[m].dot(U[m].T), U_o[m].dot(U_o[m].T)) < 1e-7        # same subspace
+        assert relerr(np.abs(core), np.abs(core_o)) < 1e-6
