@@ -264,7 +264,7 @@ def run_gpu(args):
     be.record = False
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
-    iter_bytes = sum(alg_bytes_dense(gshape, R) for _ in range(3))      # whole job, all ranks' slabs
+    iter_bytes = sum(alg_bytes_dense(gshape, R) for _ in range(3))      # whole job, all ranks' slabs: the 3 MTTKRPs of cp.py:142-143
     value = iter_bytes / (ms_step * 1e-3) / 1e9
 
     # ---- dominant kernel: per-launch durations of the dense MTTKRP inside the timed iterations
@@ -286,19 +286,27 @@ def run_gpu(args):
     if os.path.exists(prof):
         with open(prof) as f:
             traffic = json.load(f).get('dram_bytes_per_launch')
+    ach_tf = kflops / (kern_ms * 1e-3) / 1e12
+    ach_gb = kbytes / (kern_ms * 1e-3) / 1e9
     roofline = {
-        'kernel': 'mttkrp_dense_tma_kernel (dense FP64 MTTKRP, one mode of the 512^3 slab)',
-        'bound': 'hbm', 'achieved': kbytes / (kern_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-        'frac': kbytes / (kern_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': traffic, 'peak_source': peak_src,
-        'alg_bytes_per_launch': kbytes, 'avg_launch_ms': kern_ms,
-        'per_mode_ms': {str(n): float(np.mean(v)) for n, v in sorted(durs.items())},
+        'kernel': 'mttkrp_dense_tma_kernel (dense FP64 MTTKRP pass over the 512^3 slab: TMA-staged tiles, FP64 '
+                  'tensor-core MMA; two launches per iteration -- the dimension-tree pass that serves modes 0 and 1, '
+                  'and the mode-2 MTTKRP)',
+        # rank 32 -> 8 flop per algorithmic byte, above the FP64 ridge (peak_dmma / peak_hbm ~ 5.7 flop/B): the FP64
+        # tensor pipe is the binding roof.  MEASURED_PEAKS.json carries no FP64 figure (its tensor number is bf16),
+        # so the denominator is measured live by skt_probe_fp64_peaks (DMMA issue rate; cuBLAS DGEMM 8192^3 reaches
+        # 35.5 TFLOP/s on the same parts, profiles/r1_quick_perf.log).
+        'bound': 'tensor', 'achieved': ach_tf, 'peak': dmma_tf, 'unit': 'TFLOP/s',
+        'frac': (ach_tf / dmma_tf) if dmma_tf else None, 'traffic': traffic,
+        'peak_source': 'FP64 DMMA peak measured live by bench.py (skt_probe_fp64_peaks); MEASURED_PEAKS.json has no FP64 entry',
+        'alg_flops_per_launch': kflops, 'alg_bytes_per_launch': kbytes, 'avg_launch_ms': kern_ms,
+        'per_pass_ms': {('tree pass A (modes 0,1)' if n == 0 else 'mode %d' % n): float(np.mean(v))
+                        for n, v in sorted(durs.items())},
+        'launches_timed': len(all_d),
         'share_of_step': float(sum(all_d)) / ms_total if world == 1 else None,
-        'fp64': {'note': 'rank 32 makes the kernel FP64-tensor-pipe bound (AI 8 flop/B vs ridge %.1f): '
-                         'the binding roofline is the DMMA peak measured by skt_probe_fp64_peaks' %
-                         ((dmma_tf * 1e12) / (hbm_peak * 1e9) if dmma_tf else float('nan')),
-                 'achieved_tflops': kflops / (kern_ms * 1e-3) / 1e12, 'peak_tflops_dmma': dmma_tf,
-                 'peak_tflops_dfma': dfma_tf,
-                 'frac': (kflops / (kern_ms * 1e-3) / 1e12 / dmma_tf) if dmma_tf else None},
+        'hbm': {'achieved': ach_gb, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gb / hbm_peak, 'peak_source': peak_src,
+                'note': 'algorithmic bytes 8(prod I + R sum I) per launch over the same launch time'},
+        'peak_tflops_dfma': dfma_tf,
         'frac_of_binding_roofline': t_roof / (kern_ms * 1e-3),
     }
     del eng
@@ -328,7 +336,11 @@ def run_gpu(args):
                        '%d iterations)' % K2}
 
     if rank == 0:
-        ex, cores = cpu_sample(2)
+        # the CPU baseline is taken at N = 1 only (torchrun pins OMP_NUM_THREADS=1 for N > 1, which would misstate it)
+        cpu_obj = None
+        if world == 1:
+            ex, cores = cpu_sample(2)
+            cpu_obj = cpu_baseline_obj(ex, cores)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': W,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -337,10 +349,13 @@ def run_gpu(args):
                                    + ('' if world == 1 else '; weak scaling: %dx512x512 cut along mode 0, one 512^3 slab per GPU' % gshape[0]),
                        'shape': list(gshape), 'rank': R, 'init': 'random', 'fit_method': 'full',
                        'parallelism': 'mode0-shard x%d' % world,
-                       'cache': 'tensor slab 1.07 GB per GPU >> 126 MB L2: every iteration streams it from HBM 3 times'},
+                       'algorithm': 'dimension tree: X is streamed twice per iteration (pass A = X x_2 U_2 serves the '
+                                    'MTTKRPs of modes 0 and 1, pass B is the mode-2 MTTKRP); value counts the '
+                                    "reference's three MTTKRPs per iteration as the algorithmic bytes",
+                       'cache': 'tensor slab 1.07 GB per GPU >> 126 MB L2: every pass streams it from HBM'},
             'als_iters_per_sec': 1e3 / ms_step, 'final_fit': fit,
             'clocks': clocks, 'e2e': e2e_obj, 'gpu_launches': int(launches),
-            'roofline': roofline, 'cpu_baseline': cpu_baseline_obj(ex, cores),
+            'roofline': roofline, 'cpu_baseline': cpu_obj,
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + '\n').encode())

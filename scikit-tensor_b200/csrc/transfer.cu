@@ -8,6 +8,7 @@
 // bounded by the PCIe link instead.  The copy is ordered on the caller's stream: work enqueued on
 // `stream` after skt_upload sees the data; the host buffer is no longer referenced once skt_upload returns.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -46,8 +47,12 @@ int pool_init(Pool &P, int device) {
         cudaEventDestroy(P.start);
         P = Pool();
     }
+    // half the host cores, shared fairly between the ranks of one node (torchrun exports LOCAL_WORLD_SIZE)
     unsigned hc = std::thread::hardware_concurrency();
-    int nt = (int)std::max(1u, std::min<unsigned>(MAX_THREADS, hc ? hc / 2 : 4));
+    unsigned ranks = 1;
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(lw));
+    int nt = (int)std::max(1u, std::min<unsigned>(MAX_THREADS, (hc ? hc / 2 : 4) / ranks));
+    if (ranks > 1) nt = std::max(nt, 2);
     const char *env = getenv("SKT_UPLOAD_THREADS");
     if (env && atoi(env) > 0) nt = std::min(MAX_THREADS, atoi(env));
     for (int t = 0; t < nt; ++t) {
