@@ -178,6 +178,18 @@ SKT_API int skt_cp_update_fused_fits(int64_t rows, int rank);
 SKT_API int skt_cp_update_fused(const double *M_d, int64_t rows, int rank, int ndim, int mode, int first_iter,
                         double *G_d, double *U_d, double *lambda_d, int *info_d, double *ip_d,
                         const double *normX2_d, double *fit_d, skt_stream stream);
+/* The same update given P = pinv(Y) (from skt_hadamard_pinv): one 8-CTA thread-block cluster splits the factor
+ * rows, exchanges the column statistics and partial Grams through distributed shared memory in CTA-rank order
+ * (deterministic), and also writes <P,X> and the fit when asked.  cp.als needs pinv(Y) of mode n only after the
+ * MTTKRP of mode n (cp.py:143-147) while Y depends on the OTHER modes' Grams alone, so the caller can run
+ * skt_hadamard_pinv on a second stream during that MTTKRP and keep only this short kernel on the critical path. */
+SKT_API int skt_cp_update_cluster_fits(int64_t rows, int rank);
+SKT_API int skt_cp_update_cluster(const double *M_d, const double *P_d, int64_t rows, int rank, int ndim, int mode,
+                          int first_iter, double *G_d, double *U_d, double *lambda_d, double *ip_d,
+                          const double *normX2_d, double *fit_d, skt_stream stream);
+/* Leave `n` SMs out of the persistent grids (dense MTTKRP) so that a small kernel on another stream can run
+ * beside them; returns the previous value.  0 restores the full chip.                                      */
+SKT_API int skt_set_reserved_sms(int n);
 /* fit = 1 - (normX2 + ||P||^2 - 2 ip) / normX2 with ||P||^2 = sum(lambda lambda^T *
  * hadamard_m G_m) (cp.py:157-159, ktensor.py:113-126).  out_d[0] = fit, out_d[1] = ||P||^2. */
 SKT_API int skt_cp_fit(const double *G_d, int ndim, int rank, const double *lambda_d,

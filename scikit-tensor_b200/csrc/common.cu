@@ -23,7 +23,13 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
     return SKT_ECUDA;
 }
 
-int sm_count() {
+static int g_reserved_sms = 0;
+
+int sm_count_total();
+
+int sm_count() { return std::max(1, sm_count_total() - g_reserved_sms); }
+
+int sm_count_total() {
     static int n = 0;
     if (n == 0) {
         int dev = 0;
@@ -107,7 +113,7 @@ extern "C" int skt_probe_fp64_peaks(double *dmma_tflops, double *dfma_tflops) {
     cudaEvent_t e0, e1;
     SKT_CUDA(cudaEventCreate(&e0));
     SKT_CUDA(cudaEventCreate(&e1));
-    const int sms = sm_count(), blocks = sms * 4, threads = 256, iters = 20000;
+    const int sms = sm_count_total(), blocks = sms * 4, threads = 256, iters = 20000;
     float ms = 0.f;
     double best;
     if (dmma_tflops) {
@@ -140,4 +146,10 @@ extern "C" int skt_probe_fp64_peaks(double *dmma_tflops, double *dfma_tflops) {
     cudaEventDestroy(e1);
     cudaFree(d);
     return SKT_OK;
+}
+
+extern "C" int skt_set_reserved_sms(int n) {
+    const int prev = skt::g_reserved_sms;
+    skt::g_reserved_sms = (n < 0) ? 0 : n;
+    return prev;
 }

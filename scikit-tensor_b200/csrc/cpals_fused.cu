@@ -257,6 +257,217 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
     SKT_TRACE(7);
 }
 
+
+// =============================================================================================
+// Cluster version of the update (everything but the pseudo-inverse): 8 CTAs of one thread-block cluster
+// split the factor rows, exchange the R column statistics and the R x R partial Grams through distributed
+// shared memory (ordered by CTA rank: deterministic) and finish in a few microseconds.  P = pinv(Y) comes from
+// skt_hadamard_pinv, which the engine runs on a side stream WHILE the MTTKRP of the same mode is still
+// streaming the tensor (Y only needs the Grams of the other modes), so it leaves the critical path.
+// =============================================================================================
+constexpr int CL = 8;               // CTAs per cluster (portable maximum)
+constexpr int CTH = 512;            // threads per CTA
+constexpr int CWARPS = CTH / 32;
+constexpr int CMAXSLICE = 12288;    // per-CTA slice limit: rows_per_cta * LD doubles (96 KB)
+
+struct ClusterParams {
+    const double *M, *P;
+    double *G, *U, *lambda, *ip;
+    const double *normX2;
+    double *fit;
+    long long rows;
+    int R, ndim, mode, first_iter;
+};
+
+struct ClusterLayout {
+    int R8, LD, per;                // per: rows per CTA (multiple of 8)
+    size_t ms, us, ps, gp, cst, lam, red, total;
+};
+
+__host__ __device__ inline ClusterLayout cluster_layout(long long rows, int R) {
+    ClusterLayout L;
+    L.R8 = round8(R);
+    L.LD = L.R8 + 4;
+    const int rows8 = round8((int)rows);
+    L.per = ((rows8 / 8 + CL - 1) / CL) * 8;
+    if (L.per < 8) L.per = 8;
+    size_t o = 0;
+    L.ms = o; o += (size_t)L.per * L.LD;
+    L.us = o; o += (size_t)L.per * L.LD;
+    L.ps = o; o += (size_t)L.R8 * L.LD;          // P, later the summed Gram on rank 0
+    L.gp = o; o += ((size_t)L.R8 * L.R8 > (size_t)CTH) ? (size_t)L.R8 * L.R8 : (size_t)CTH;   // partial Gram; first the column-statistic scratch
+    L.cst = o; o += 72;                          // [0..63] column statistic partials, [64] <P,X> partial
+    L.lam = o; o += 64;
+    L.red = o; o += 64;
+    L.total = o;
+    return L;
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
+    cp_update_cluster_kernel(const __grid_constant__ ClusterParams p) {
+    extern __shared__ __align__(16) double csm2[];
+    const int R = p.R, rows = (int)p.rows;
+    const ClusterLayout L = cluster_layout(p.rows, R);
+    const int R8 = L.R8, LD = L.LD, per = L.per;
+    double *Ms = csm2 + L.ms, *Us = csm2 + L.us, *Ps = csm2 + L.ps, *gp = csm2 + L.gp, *cst = csm2 + L.cst;
+    double *lam = csm2 + L.lam, *red = csm2 + L.red;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    unsigned crank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
+    const int r0 = (int)crank * per;                       // first row of this CTA's slice
+    const int nr = max(0, min(per, rows - r0));            // valid rows in it
+
+    auto cluster_sync = [&]() {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+    };
+    // generic address of `ptr` (own shared memory) as seen in the shared memory of CTA `rank` of the cluster
+    auto remote = [&](const double *ptr, unsigned rank) -> const double * {
+        uint64_t in = (uint64_t)(uintptr_t)ptr, out;
+        asm volatile("mapa.u64 %0, %1, %2;\n" : "=l"(out) : "l"(in), "r"(rank));
+        return (const double *)(uintptr_t)out;
+    };
+
+    // ---- stage the slice of M and P (zero padded)
+    for (int e = tid; e < per * R8; e += CTH) {
+        const int i = e / R8, c = e - i * R8;
+        Ms[i * LD + c] = (i < nr && c < R) ? __ldg(p.M + (long long)(r0 + i) * R + c) : 0.0;
+    }
+    for (int e = tid; e < R8 * LD; e += CTH) {
+        const int a = e / LD, b = e - a * LD;
+        Ps[e] = (a < R && b < R) ? __ldg(p.P + a * R + b) : 0.0;
+    }
+    __syncthreads();
+
+    // ---- Unew = M P on the slice (FP64 tensor cores); <P,X> partial = sum Unew .* M
+    const int ncb = R8 >> 3, nblk = (per >> 3) * ncb;
+    double ipp = 0.0;
+    for (int blk = warp; blk < nblk; blk += CWARPS) {
+        const int ib = blk / ncb, jb = blk - ib * ncb;
+        const double *arow = Ms + (ib * 8 + g) * LD + t4;
+        const double *bcol = Ps + t4 * LD + jb * 8 + g;
+        double c0 = 0.0, c1 = 0.0;
+        for (int k0 = 0; k0 < R8; k0 += 4) dmma884(c0, c1, arow[k0], bcol[k0 * LD]);
+        const int off = (ib * 8 + g) * LD + jb * 8 + 2 * t4;
+        Us[off] = c0;
+        Us[off + 1] = c1;
+        ipp += c0 * Ms[off] + c1 * Ms[off + 1];
+    }
+    ipp = warp_sum(ipp);
+    if (lane == 0) red[warp] = ipp;
+    __syncthreads();
+
+    // ---- per-CTA column statistics (fixed order), then the cluster-wide combination in rank order
+    {
+        const int RP = (R <= 16) ? 16 : (R <= 32 ? 32 : 64);
+        const int nchunk = CTH / RP;
+        const int c = tid % RP, ch = tid / RP;
+        const int perc = (nr + nchunk - 1) / nchunk;
+        double st = p.first_iter ? 0.0 : -DBL_MAX;
+        if (c < R) {
+            const int i1 = min(nr, (ch + 1) * perc);
+            for (int i = ch * perc; i < i1; ++i) {
+                const double v = Us[i * LD + c];
+                st = p.first_iter ? st + v * v : fmax(st, v);
+            }
+        }
+        double *scr = gp;                                   // [nchunk][RP] scratch (the Gram comes later)
+        scr[ch * RP + c] = st;
+        __syncthreads();
+        if (tid < R) {
+            double sacc = p.first_iter ? 0.0 : -DBL_MAX;
+            for (int k = 0; k < nchunk; ++k) {
+                const double v = scr[k * RP + tid];
+                sacc = p.first_iter ? sacc + v : fmax(sacc, v);
+            }
+            cst[tid] = sacc;
+        }
+        if (tid == 0) {
+            double sum = 0.0;
+            for (int w = 0; w < CWARPS; ++w) sum += red[w];
+            cst[64] = sum;
+        }
+    }
+    cluster_sync();
+    if (tid < R) {
+        double sacc = p.first_iter ? 0.0 : -DBL_MAX;
+        for (unsigned k = 0; k < CL; ++k) {
+            const double v = remote(cst, k)[tid];
+            sacc = p.first_iter ? sacc + v : fmax(sacc, v);
+        }
+        const double l = p.first_iter ? sqrt(sacc) : (sacc < 1.0 ? 1.0 : sacc);   // cp.py:150 / cp.py:152-153
+        lam[tid] = l;
+        if (crank == 0) p.lambda[tid] = l;
+    }
+    __syncthreads();
+
+    // ---- U = Unew / lambda on the slice (shared + global)
+    for (int e = tid; e < nr * R; e += CTH) {
+        const int i = e / R, c = e - i * R;
+        const double v = Us[i * LD + c] / lam[c];
+        Us[i * LD + c] = v;
+        p.U[(long long)(r0 + i) * R + c] = v;
+    }
+    __syncthreads();
+
+    // ---- partial Gram of the slice (rows beyond nr are zero)
+    {
+        const int nb2 = ncb * ncb;
+        for (int job = warp; job < nb2; job += CWARPS) {
+            const int ab = job / ncb, bb = job - ab * ncb;
+            const double *ap = Us + t4 * LD + ab * 8 + g;
+            const double *bp = Us + t4 * LD + bb * 8 + g;
+            double c0 = 0.0, c1 = 0.0;
+            for (int k = 0; k < per; k += 4) dmma884(c0, c1, ap[k * LD], bp[k * LD]);
+            double *dst = gp + (ab * 8 + g) * R8 + bb * 8 + 2 * t4;
+            dst[0] = c0;
+            dst[1] = c1;
+        }
+    }
+    cluster_sync();
+
+    // ---- rank 0: G_n = sum of the partial Grams in rank order, <P,X>, fit
+    if (crank == 0) {
+        double *Gn = p.G + (size_t)p.mode * R * R;
+        double *Gs = Ps;                                    // P is no longer needed
+        for (int e = tid; e < R * R; e += CTH) {
+            const int a = e / R, b = e - a * R;
+            double sum = 0.0;
+            for (unsigned k = 0; k < CL; ++k) sum += remote(gp, k)[a * R8 + b];
+            Gn[e] = sum;
+            Gs[e] = sum;
+        }
+        if (tid == 0 && p.ip) {
+            double sum = 0.0;
+            for (unsigned k = 0; k < CL; ++k) sum += remote(cst, k)[64];
+            p.ip[0] = sum;
+            red[CWARPS] = sum;
+        }
+        __syncthreads();
+        if (p.fit) {
+            double sacc = 0.0;
+            for (int e = tid; e < R * R; e += CTH) {
+                const int a = e / R, b = e - a * R;
+                double y = lam[a] * lam[b];
+                for (int k = 0; k < p.ndim; ++k) y *= (k == p.mode) ? Gs[e] : __ldg(p.G + (size_t)k * R * R + e);
+                sacc += y;
+            }
+            sacc = warp_sum(sacc);
+            if (lane == 0) red[warp] = sacc;
+            __syncthreads();
+            if (tid == 0) {
+                double normP2 = 0.0;
+                for (int w = 0; w < CWARPS; ++w) normP2 += red[w];
+                const double nx2 = p.normX2[0];
+                p.fit[0] = 1.0 - (nx2 + normP2 - 2.0 * red[CWARPS]) / nx2;
+                p.fit[1] = normP2;
+            }
+        }
+    }
+    cluster_sync();     // the peers' shared memory must outlive rank 0's reads
+}
+
 }  // namespace
 }  // namespace skt
 
@@ -303,5 +514,35 @@ extern "C" int skt_cp_update_fused(const double *M_d, int64_t rows, int rank, in
         fprintf(stderr, "fused trace (cycles): stage+loadY %lld  pinv %lld  solve %lld  stats %lld  normalise %lld  gram %lld  fit %lld  total %lld\n",
                 h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[7] - h[0]);
     }
+    return SKT_OK;
+}
+
+extern "C" int skt_cp_update_cluster_fits(int64_t rows, int rank) {
+    if (rows < 1 || rank < 1 || rank > SKT_MAX_RANK || rows > (1 << 20)) return 0;
+    const ClusterLayout L = cluster_layout(rows, rank);
+    if ((long long)L.per * L.LD > CMAXSLICE) return 0;
+    return (L.total * sizeof(double) <= smem_optin_bytes()) ? 1 : 0;
+}
+
+extern "C" int skt_cp_update_cluster(const double *M_d, const double *P_d, int64_t rows, int rank, int ndim, int mode,
+                                     int first_iter, double *G_d, double *U_d, double *lambda_d, double *ip_d,
+                                     const double *normX2_d, double *fit_d, skt_stream stream) {
+    SKT_REQUIRE(M_d && P_d && G_d && U_d && lambda_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= 0 && mode < ndim, SKT_EINVAL, "bad ndim/mode");
+    SKT_REQUIRE(fit_d == nullptr || (ip_d != nullptr && normX2_d != nullptr), SKT_EINVAL, "the fit needs ip_d and normX2_d");
+    SKT_REQUIRE(skt_cp_update_cluster_fits(rows, rank), SKT_EUNSUPPORTED,
+                "factor of %lld x %d does not fit the cluster update kernel", (long long)rows, rank);
+    const ClusterLayout L = cluster_layout(rows, rank);
+    const size_t smem = L.total * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        SKT_CUDA(cudaFuncSetAttribute(cp_update_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin_bytes()));
+        configured = true;
+    }
+    ClusterParams p;
+    p.M = M_d; p.P = P_d; p.G = G_d; p.U = U_d; p.lambda = lambda_d; p.ip = ip_d; p.normX2 = normX2_d; p.fit = fit_d;
+    p.rows = rows; p.R = rank; p.ndim = ndim; p.mode = mode; p.first_iter = first_iter;
+    cp_update_cluster_kernel<<<CL, CTH, smem, (cudaStream_t)stream>>>(p);
+    SKT_LAUNCH_CHECK();
     return SKT_OK;
 }

@@ -163,15 +163,17 @@ def gram(U, out=None):
     return out
 
 
-def hadamard_pinv(G, mode, P=None, info=None):
-    """``pinv(hadamard_{m != mode} G[m])`` (cp.py:144-147); ``G`` is (ndim, R, R)."""
+def hadamard_pinv(G, mode, P=None, info=None, stream=None):
+    """``pinv(hadamard_{m != mode} G[m])`` (cp.py:144-147); ``G`` is (ndim, R, R).  ``stream``: a torch
+    stream to enqueue on instead of the current one."""
     lib = _lib.load()
     nd, R = int(G.shape[0]), int(G.shape[1])
     if P is None:
         P = dev.empty((R, R))
     if info is None:
         info = dev.empty((1,), np.int32)
-    _lib.check(lib.skt_hadamard_pinv(dev.ptr(G), nd, R, mode, dev.ptr(P), dev.ptr(info), dev.stream_ptr()))
+    sp = dev.stream_ptr() if stream is None else C.c_void_p(stream.cuda_stream)
+    _lib.check(lib.skt_hadamard_pinv(dev.ptr(G), nd, R, mode, dev.ptr(P), dev.ptr(info), sp))
     return P, info
 
 
@@ -215,6 +217,23 @@ def cp_update_fused(M, G, mode, first_iter, U, lam, info, ip=None, normX2=None, 
     _lib.check(lib.skt_cp_update_fused(dev.ptr(M), rows, R, int(G.shape[0]), mode, 1 if first_iter else 0, dev.ptr(G),
                                        dev.ptr(U), dev.ptr(lam), dev.ptr(info), dev.ptr(ip), dev.ptr(normX2),
                                        dev.ptr(fit), dev.stream_ptr()))
+
+
+def cp_update_cluster_fits(rows, rank):
+    return bool(_lib.load().skt_cp_update_cluster_fits(int(rows), int(rank)))
+
+
+def cp_update_cluster(M, P, G, mode, first_iter, U, lam, ip=None, normX2=None, fit=None):
+    """solve + normalise + Gram (+ <P,X>, fit) given P = pinv(Y), on one 8-CTA cluster (cp.py:147-159)."""
+    lib = _lib.load()
+    rows, R = M.shape
+    _lib.check(lib.skt_cp_update_cluster(dev.ptr(M), dev.ptr(P), rows, R, int(G.shape[0]), mode, 1 if first_iter else 0,
+                                         dev.ptr(G), dev.ptr(U), dev.ptr(lam), dev.ptr(ip), dev.ptr(normX2),
+                                         dev.ptr(fit), dev.stream_ptr()))
+
+
+def set_reserved_sms(n):
+    return int(_lib.load().skt_set_reserved_sms(int(n)))
 
 
 def cp_fit(G, lam, ip, normX2, out=None):

@@ -69,6 +69,10 @@ PROTOTYPES = {
     'skt_cp_update_fused_fits': (C.c_int, [C.c_int64, C.c_int]),
     'skt_cp_update_fused': (C.c_int, [c_dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp,
                                       C.c_void_p, c_dp, c_dp, c_dp, c_stream]),
+    'skt_cp_update_cluster_fits': (C.c_int, [C.c_int64, C.c_int]),
+    'skt_cp_update_cluster': (C.c_int, [c_dp, c_dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp,
+                                        c_dp, c_dp, c_dp, c_stream]),
+    'skt_set_reserved_sms': (C.c_int, [C.c_int]),
     'skt_cp_fit': (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_stream]),
     'skt_ttm_dense': (C.c_int, [c_dp, c_i64p, C.c_int, c_dp, C.c_int64, C.c_int, C.c_int, c_dp, c_stream]),
     'skt_ttm_dense_first_rot': (C.c_int, [c_dp, c_i64p, C.c_int, c_dp, C.c_int64, c_dp, c_stream]),

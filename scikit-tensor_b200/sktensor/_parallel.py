@@ -137,6 +137,34 @@ class CudaBackend(object):
     def normalise_gram(self, U, colstat, first, lam, G, Mip, ip):
         return self.K.normalise_gram(U, colstat, first, lam=lam, G=G, Mip=Mip, ip=ip)
     def cp_fit(self, G, lam, ip, normX2, out): return self.K.cp_fit(G, lam, ip, normX2, out=out)
+    # the short update on an 8-CTA cluster, with pinv(Y) running on a side stream during the MTTKRP
+    def update_cluster_fits(self, rows, R): return self.K.cp_update_cluster_fits(rows, R)
+
+    def pinv_async(self, G, n, P, info):
+        t = self.dev.torch()
+        if getattr(self, '_side', None) is None:
+            self._side = t.cuda.Stream()
+            self._ev = {}
+            self.K.set_reserved_sms(1)      # the persistent MTTKRP grid leaves one SM to the side stream
+        ready, done = self._ev.setdefault(n, (t.cuda.Event(), t.cuda.Event()))
+        ready.record()                      # the Grams this pinv reads are final on the main stream
+        self._side.wait_event(ready)
+        self.K.hadamard_pinv(G, n, P=P, info=info, stream=self._side)
+        done.record(self._side)
+        return done
+
+    def wait_pinv(self, handle):
+        self.dev.torch().cuda.current_stream().wait_event(handle)
+
+    def release_side(self):
+        if getattr(self, '_side', None) is not None:
+            self.dev.torch().cuda.current_stream().wait_stream(self._side)
+            self.K.set_reserved_sms(0)
+            self._side = None
+
+    def update_cluster(self, M, P, G, n, first, U, lam, ip, normX2, fit):
+        return self.K.cp_update_cluster(M, P, G, n, first, U, lam, ip=ip, normX2=normX2, fit=fit)
+
     def update_fused_fits(self, rows, R): return self.K.cp_update_fused_fits(rows, R)
     def update_fused(self, M, G, n, first, U, lam, info, ip, normX2, fit):
         return self.K.cp_update_fused(M, G, n, first, U, lam, info, ip=ip, normX2=normX2, fit=fit)
@@ -269,6 +297,13 @@ class CpAlsEngine(object):
         self.fused = [bool(use_fused and not (comm.active and m == self.s) and be.update_fused_fits(self.lshape[m], R))
                       for m in range(N)]
 
+        # ---- ... and, preferably, on an 8-CTA cluster with pinv(Y_n) computed on a side stream while the MTTKRP
+        # of mode n is still streaming the tensor (Y_n only needs the Grams of the other modes)
+        use_cluster = use_fused and hasattr(be, 'update_cluster') and os.environ.get('SKT_NO_CLUSTER_UPDATE', '0') != '1'
+        self.cluster = [bool(use_cluster and self.fused[m] and be.update_cluster_fits(self.lshape[m], R)) for m in range(N)]
+        self.Pn = [be.empty((R, R)) if self.cluster[m] else None for m in range(N)]
+        self._pinv_pending = [None] * N
+
         # ---- dimension tree (dense, N >= 3): two passes over X per sweep instead of N.  Modes [0, s) are
         # served by T_A = X contracted with U_s..U_{N-1}; modes [s, N) by T_B = X contracted with
         # U_0..U_{s-1}.  A one-mode group needs no second stage: its partial tensor IS the MTTKRP.
@@ -338,11 +373,24 @@ class CpAlsEngine(object):
         be, comm, N = self.be, self.comm, self.N
         fit_done = False
         for n in range(N):
+            if self.cluster[n] and self._pinv_pending[n] is None:      # first mode of the first sweep
+                self._pinv_pending[n] = be.pinv_async(self.G, n, self.Pn[n], self.info[n:n + 1])
             if n == 0 and self._m0_ready:
                 M, self._m0_ready = self.M[0], False
             else:
                 M = self.mttkrp(n)
             last = (n == N - 1) and want_fit
+            if self.cluster[n]:
+                be.wait_pinv(self._pinv_pending[n])
+                self._pinv_pending[n] = None
+                be.update_cluster(M, self.Pn[n], self.G, n, first_iter, self.Ud[n], self.lam,
+                                  self.ip if last else None, self.normX2 if last else None,
+                                  self.fitout if last else None)
+                fit_done = fit_done or last
+                nxt = (n + 1) % N          # its Grams are final now: start the next mode's pinv beside the next MTTKRP
+                if self.cluster[nxt]:
+                    self._pinv_pending[nxt] = be.pinv_async(self.G, nxt, self.Pn[nxt], self.info[nxt:nxt + 1])
+                continue
             if self.fused[n]:
                 # small factor, replicated solve: pinv + solve + normalise + Gram (+ <P,X>, fit) in one launch
                 be.update_fused(M, self.G, n, first_iter, self.Ud[n], self.lam, self.info[n:n + 1],
@@ -398,6 +446,9 @@ class CpAlsEngine(object):
 
     def download(self, U):
         """Write the factors into the caller's list (in place) and return lambda."""
+        if hasattr(self.be, 'release_side'):
+            self.be.release_side()          # a speculative pinv of the next sweep may still be running
+        self._pinv_pending = [None] * self.N
         for m in range(self.N):
             if self.comm.active and m == self.s:
                 U[m] = self.comm.allgather_rows(self.Ud[m], self.offsets, self.be)

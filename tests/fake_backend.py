@@ -127,3 +127,21 @@ class NumpyBackend(object):
         self.normalise_gram(U, colstat, first, lam, G[n], M if ip is not None else None, ip)
         if fit is not None:
             self.cp_fit(G, lam, ip, normX2, fit)
+
+    # the cluster update with the side-stream pinv (cpals_fused.cu): same arithmetic, synchronous here
+    def update_cluster_fits(self, rows, R):
+        return int(rows) * int(R) <= 100000 and R <= 64
+
+    def pinv_async(self, G, n, P, info):
+        self.hadamard_pinv(G, n, P, info)
+        return ('pinv', n)
+
+    def wait_pinv(self, handle):
+        assert handle[0] == 'pinv'
+
+    def update_cluster(self, M, P, G, n, first, U, lam, ip, normX2, fit):
+        colstat = torch.zeros(G.shape[1], dtype=torch.float64)
+        self.solve_stats(M, P, first, U, colstat)
+        self.normalise_gram(U, colstat, first, lam, G[n], M if ip is not None else None, ip)
+        if fit is not None:
+            self.cp_fit(G, lam, ip, normX2, fit)

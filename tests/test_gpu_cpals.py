@@ -406,3 +406,72 @@ def test_tucker_hooi_midsize_vs_oracle():
             assert relerr(U[m].T.dot(U[m]), np.eye(rank[m])) < 1e-12
             assert relerr(U[m].dot(U[m].T), U_o[m].dot(U_o[m].T)) < 1e-7        # same subspace
         assert relerr(np.abs(core), np.abs(core_o)) < 1e-6
+
+
+@pytest.mark.parametrize('rows,R,N', [(10, 3, 3), (512, 32, 3), (160, 64, 4), (97, 17, 3), (2000, 16, 3), (7, 1, 2),
+                                      (300, 48, 5), (64, 64, 3), (2500, 8, 3), (1, 4, 3)])
+def test_cluster_update_matches_reference_arithmetic(K, dev, rows, R, N):
+    """skt_hadamard_pinv + skt_cp_update_cluster (8-CTA cluster, DSMEM exchange) == cp.py:144-159."""
+    if not K.cp_update_cluster_fits(rows, R):
+        pytest.skip('does not fit the cluster kernel')
+    rng = np.random.RandomState(rows * 17 + R)
+    F = [rng.rand(40 + 3 * m, R) for m in range(N)]
+    G = np.stack([f.T.dot(f) for f in F])
+    M = rng.rand(rows, R) * 2 - 0.5
+    normX2 = 987.25
+    for mode in (0, N - 1):
+        for first in (True, False):
+            Gd = dev.to_device(G)
+            P, info = K.hadamard_pinv(Gd, mode)
+            U, lam = dev.empty((rows, R)), dev.empty((R,))
+            ip, fit = dev.zeros((1,)), dev.zeros((2,))
+            K.cp_update_cluster(dev.to_device(M), P, Gd, mode, first, U, lam, ip=ip,
+                                normX2=dev.to_device(np.array([normX2])), fit=fit)
+            Y = np.ones((R, R))
+            for m in range(N):
+                if m != mode:
+                    Y = Y * G[m]
+            Unew = M.dot(pinv(Y))
+            l = np.sqrt((Unew ** 2).sum(0)) if first else np.where(Unew.max(0) < 1, 1.0, Unew.max(0))
+            Uref = Unew / l
+            tol = 1e-13 * max(1e2, np.linalg.cond(Y))
+            assert relerr(dev.to_host(U), Uref) < tol, (rows, R, mode, first)
+            assert relerr(dev.to_host(lam), l) < tol
+            Gn = dev.to_host(Gd)
+            assert relerr(Gn[mode], Uref.T.dot(Uref)) < tol
+            for m in range(N):
+                if m != mode:
+                    assert (Gn[m] == G[m]).all()
+            ipref = (l * Uref * M).sum()
+            assert abs(dev.to_host(ip)[0] - ipref) < tol * abs(ipref)
+            G2 = G.copy()
+            G2[mode] = Uref.T.dot(Uref)
+            coef = np.outer(l, l)
+            for m in range(N):
+                coef = coef * G2[m]
+            got = dev.to_host(fit)
+            assert abs(got[1] - coef.sum()) < tol * coef.sum()
+            assert abs(got[0] - (1.0 - (normX2 + coef.sum() - 2 * ipref) / normX2)) < tol * 10 * max(1.0, coef.sum() / normX2)
+            # run to run bitwise reproducible (ordered DSMEM reductions)
+            Gd2 = dev.to_device(G)
+            U2, lam2 = dev.empty((rows, R)), dev.empty((R,))
+            K.cp_update_cluster(dev.to_device(M), P, Gd2, mode, first, U2, lam2)
+            assert (dev.to_host(U2) == dev.to_host(U)).all() and (dev.to_host(Gd2) == Gn).all()
+
+
+def test_cluster_fused_and_streaming_updates_agree():
+    """cp_als through the three update paths (cluster + side-stream pinv, single-CTA fused, streaming kernels)."""
+    import os
+    from sktensor import cp_als, dtensor
+    rng = np.random.RandomState(21)
+    for shape, R in (((30, 28, 26), 5), ((24, 20, 18, 22), 7)):
+        X = rng.rand(*shape)
+        res = []
+        for nocl, nofu in (('0', '0'), ('1', '0'), ('1', '1')):
+            os.environ['SKT_NO_CLUSTER_UPDATE'], os.environ['SKT_NO_FUSED_UPDATE'] = nocl, nofu
+            np.random.seed(9)
+            P, fit, itr, _ = cp_als(dtensor(X), R, init='random', max_iter=40)
+            res.append((float(fit), itr))
+        os.environ['SKT_NO_CLUSTER_UPDATE'] = os.environ['SKT_NO_FUSED_UPDATE'] = '0'
+        assert res[0][1] == res[1][1] == res[2][1]
+        assert abs(res[0][0] - res[1][0]) < 1e-10 and abs(res[0][0] - res[2][0]) < 1e-10

@@ -110,6 +110,11 @@ def main():
                 K.cp_update_fused(M, G, 0, False, U, lam, info, ip=ip, normX2=nx2, fit=fit)
             print('rows=%d R=%d: fused update            %.2f us' % (rows, R, 1e3 * timeit(fused, reps=20)[0]))
             G.copy_(G0)
+            Pd, _ = K.hadamard_pinv(G, 0)
+            def clus():
+                K.cp_update_cluster(M, Pd, G, 0, False, U, lam, ip=ip, normX2=nx2, fit=fit)
+            print('             cluster update (no pinv) %.2f us' % (1e3 * timeit(clus, reps=20)[0]))
+            G.copy_(G0)
             print('             hadamard_pinv           %.2f us' % (1e3 * timeit(lambda: K.hadamard_pinv(G, 0, P=P, info=info), reps=20)[0]))
             print('             solve_stats             %.2f us' % (1e3 * timeit(lambda: K.solve_stats(M, P, False, Unew=U, colstat=colstat), reps=20)[0]))
             print('             normalise_gram          %.2f us' % (1e3 * timeit(lambda: K.normalise_gram(U, colstat, False, lam=lam, G=G[0], Mip=M, ip=ip), reps=20)[0]))
