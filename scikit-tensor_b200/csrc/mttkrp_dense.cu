@@ -56,6 +56,11 @@ struct DenseParams {
     int nk;
     int vecX, vecU;
     int nw;
+    // TMA kernel: stream-K schedule.  CTA b owns the contiguous tile range [b*ntiles/grid, (b+1)*ntiles/grid) of
+    // the linearised (output-row tile, reduction tile) space and flushes when the output-row tile changes.
+    long long ntiles;      // nit * nred
+    double *slab;          // partial outputs: 2 slots of slab_stride doubles per CTA (first / last partial segment)
+    long long slab_stride; // bi * ld
     int direct;          // every tile row is its own output row (L == T == 1): the TMA kernel stores accumulators straight to out
     WeightMode w[SKT_MAX_NDIM];
 };
@@ -357,19 +362,15 @@ struct TmaCfg {
 // Work schedule shared by the producer and the consumers: CTA b owns items b, b+grid, ...; an item is
 // (output-row tile, split) and covers reduction tiles [t0, t1); every tile is nk k-slices.
 struct StepState {
-    int item, tile, tile_end, ks;
+    int tau, tau_begin, tau_end;   // linear tile index: tau = it * nred + red  (ntiles < 2^31 on this path)
+    int ks;
     __device__ __forceinline__ void init(const DenseParams &p) {
-        item = blockIdx.x;
-        tile = tile_end = 0;
+        tau_begin = (int)((p.ntiles * (long long)blockIdx.x) / gridDim.x);
+        tau_end = (int)((p.ntiles * (long long)(blockIdx.x + 1)) / gridDim.x);
+        tau = tau_begin;
         ks = 0;
-        if (item < p.nitems) range(p);
     }
-    __device__ __forceinline__ void range(const DenseParams &p) {
-        const int s = item % p.nsplit;
-        tile = s * p.chunk;
-        tile_end = min(tile + p.chunk, p.nred);
-    }
-    __device__ __forceinline__ bool active(const DenseParams &p) const { return item < p.nitems; }
+    __device__ __forceinline__ bool active(const DenseParams &) const { return tau < tau_end; }
 };
 
 template <int NB, bool MMAJOR>
@@ -430,23 +431,24 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             }
             cp_async_mbar_arrive_noinc(&full[stage]);
             if (lane == 0) {
-                const int it = st.item / p.nsplit;
-                const int lt = st.tile / p.ntt, tt = st.tile % p.ntt;
+                const int it = st.tau / p.nred, red = st.tau - it * p.nred;
+                const int lt = red / p.ntt, tt = red % p.ntt;
                 mbar_arrive_expect_tx(&full[stage], C::XBYTES);
                 if (!MMAJOR) {
                     tma_load_4d(sb, &tmX, &full[stage], k0, tt * bt, it * bi, lt * bl);
                 } else {
+                    // row group j holds 16 consecutive i of one l: tile = (bl l) x (bi i), bi a multiple of 16 --
+                    // the wider the tile is in i (the contiguous axis), the longer the DRAM bursts per k
+                    const int lg_nsub = p.lg_bi - 4;
 #pragma unroll
                     for (int j = 0; j < RG; ++j)
-                        tma_load_3d(sb + j * (TK * 128), &tmX, &full[stage], it * 16, lt * RG + j, k0);
+                        tma_load_3d(sb + j * (TK * 128), &tmX, &full[stage], it * bi + 16 * (j & ((1 << lg_nsub) - 1)),
+                                    lt * bl + (j >> lg_nsub), k0);
                 }
             }
             if (++st.ks == p.nk) {
                 st.ks = 0;
-                if (++st.tile == st.tile_end) {
-                    st.item += gridDim.x;
-                    if (st.active(p)) st.range(p);
-                }
+                ++st.tau;
             }
             if (++stage == STAGES) { stage = 0; ++use; }
         }
@@ -537,8 +539,8 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             cs.ks = 0;
             {
                 // ---- tile epilogue: out += acc * prod_m U_m[i_m(row), col]   (the Khatri-Rao rows, on the fly)
-                const int it = cs.item / p.nsplit;
-                const int lt = cs.tile / p.ntt, tt = cs.tile % p.ntt;
+                const int it = cs.tau / p.nred, red = cs.tau - it * p.nred;
+                const int lt = red / p.ntt, tt = red % p.ntt;
                 if (p.direct) {
                     // plain GEMM rows (the partial contraction of the dimension tree, dimtree.cu, and the big TTM of
                     // HOOI): every tile row is its own output row (l, i_n, t) -- no weights, no cross-row sum, 16-byte
@@ -597,13 +599,19 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                     }
                 }
             }
-            if (++cs.tile == cs.tile_end && p.direct) {
-                cs.item += gridDim.x;
-                if (cs.active(p)) cs.range(p);
-            } else if (cs.tile == cs.tile_end) {
-                // ---- item flush: sum rows of equal i_n in a fixed order, write bi x R outputs
-                const int it = cs.item / p.nsplit, s = cs.item % p.nsplit;
-                double *dst = p.out + (long long)s * p.out_split_stride;
+            const int it_done = cs.tau / p.nred;
+            ++cs.tau;
+            const bool seg_end = (cs.tau == cs.tau_end) || (cs.tau == (it_done + 1) * p.nred);
+            if (seg_end && !p.direct) {
+                // ---- segment flush: sum rows of equal i_n in a fixed order, write bi x R outputs.  A segment that covers
+                // its output-row tile completely goes straight to M; a partial one goes to this CTA's slab slot (0: the
+                // first segment of the range, 1: the last) and is added up, in CTA order, by streamk_fixup_kernel.
+                const int it = it_done;
+                const int it_lo = it * p.nred, it_hi = it_lo + p.nred;
+                const int seg_lo = (cs.tau_begin > it_lo) ? cs.tau_begin : it_lo;
+                const bool full = (seg_lo == it_lo) && (cs.tau == it_hi);
+                double *dst = full ? (p.out + (long long)it * bi * p.ld)
+                                   : (p.slab + (2LL * blockIdx.x + (seg_lo == cs.tau_begin ? 0 : 1)) * p.slab_stride);
                 named_bar_sync(1, TCONS);
                 const int nout = bi * C::ZC;               // outputs of this item
                 const int rows_per_out = bl * bt;          // tile rows that share one output row
@@ -620,7 +628,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                                     const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
                                     sum += Z[q * C::ZSTR + col];
                                 }
-                            dst[(long long)i * p.ld + col] = sum;
+                            dst[(long long)i_off * p.ld + col] = sum;
                         }
                     }
                 } else {
@@ -644,7 +652,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                         if (col < p.R && i < p.In) {
                             double sum = 0.0;
                             for (int part = 0; part < parts; ++part) sum += red[part * nout + tid];
-                            dst[(long long)i * p.ld + col] = sum;
+                            dst[(long long)i_off * p.ld + col] = sum;
                         }
                     }
                 }
@@ -654,8 +662,6 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                     zrow0[8 * nn] = zrow0[8 * nn + 1] = 0.0;
                     zrow1[8 * nn] = zrow1[8 * nn + 1] = 0.0;
                 }
-                cs.item += gridDim.x;
-                if (cs.active(p)) cs.range(p);
             }
         }
     }
@@ -669,6 +675,33 @@ __global__ void reduce_splits_kernel(const double *__restrict__ P, int nsplit, l
         for (int k = 0; k < nsplit; ++k) s += P[(long long)k * n + e];
         M[e] = s;
     }
+}
+
+// Stream-K fix-up: an output-row tile whose reduction tiles were shared by several CTAs gets the sum of their
+// partial slabs, in CTA order (deterministic for a fixed grid).  One thread per (it, i_off, column).
+__global__ void streamk_fixup_kernel(const double *__restrict__ slab, long long slab_stride, long long ntiles, int nred,
+                                     int grid, int nit, int bi, int In, int R, int ld, double *__restrict__ M) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long per_it = (long long)bi * R;
+    if (e >= (long long)nit * per_it) return;
+    const int it = (int)(e / per_it);
+    const int rem = (int)(e - (long long)it * per_it);
+    const int i_off = rem / R, col = rem - i_off * R;
+    if (it * bi + i_off >= In) return;
+    const long long ta = (long long)it * nred, tb = ta + nred - 1;       // first / last tile of this row tile
+    // CTA b owns [b*ntiles/grid, (b+1)*ntiles/grid): the owner of tile t is floor(((t+1)*grid - 1) / ntiles)
+    const int b_first = (int)((((ta + 1) * grid) - 1) / ntiles);
+    const int b_last = (int)((((tb + 1) * grid) - 1) / ntiles);
+    if (b_first == b_last) return;                                         // written directly by its single owner
+    double sum = 0.0;
+    for (int b = b_first; b <= b_last; ++b) {
+        const long long t0 = (ntiles * (long long)b) / grid, t1 = (ntiles * (long long)(b + 1)) / grid;
+        const long long lo = t0 > ta ? t0 : ta, hi = t1 < tb + 1 ? t1 : tb + 1;
+        if (lo >= hi) continue;
+        const int slot = (lo == t0) ? 0 : 1;
+        sum += slab[(2LL * b + slot) * slab_stride + (long long)i_off * ld + col];
+    }
+    M[((long long)it * bi + i_off) * ld + col] = sum;
 }
 
 struct NaiveParams {
@@ -796,11 +829,17 @@ int make_plan_uncached(const int64_t *shape, int ndim, int rank, int mode, bool 
             const int ll = lgbm - lt - li;
             const long long bt = 1LL << lt, bi = 1LL << li, bl = 1LL << ll;
             if (pl.mmajor && lt != 0) continue;
-            if (pl.mmajor && tma && li != 4) continue;  // the M-major TMA box is fixed: 16 i per row group
+            if (pl.mmajor && tma && li < 4) continue;   // an M-major TMA row group holds 16 consecutive i
+            if (pl.mmajor && tma) {
+                static const char *force = getenv("SKT_MM_LI");   // tuning knob: force log2(bi)
+                if (force && atoi(force) >= 4 && li != std::min(atoi(force), lgbm)) continue;
+            }
             const double padded = (double)((T + bt - 1) / bt * bt) * (double)((pl.In + bi - 1) / bi * bi) *
                                   (double)((L + bl - 1) / bl * bl);
             // prefer (slightly) boxes whose inner run is long: fewer DRAM page switches
-            const double score = padded * (1.0 + 1e-3 * (pl.mmajor ? (lgbm - li) : (lgbm - lt)) + 1e-5 * ll);
+            // K-major: long runs in t; M-major (TMA): 32 consecutive i per l measured best (sweep in profiles/r1_notes.md)
+            const int pref = pl.mmajor ? (tma ? std::abs(li - 5) : (lgbm - li)) : (lgbm - lt);
+            const double score = padded * (1.0 + 1e-3 * pref + 1e-5 * ll);
             if (score < best) { best = score; bbt = lt; bbi = li; bbl = ll; }
         }
     pl.lg_bt = bbt; pl.lg_bi = bbi; pl.lg_bl = bbl;
@@ -971,7 +1010,12 @@ extern "C" size_t skt_mttkrp_dense_workspace(const int64_t *shape, int ndim, int
     for (int tma = 0; tma < 2; ++tma) {
         DensePlan pl;
         if (make_plan(shape, ndim, rank, mode, tma != 0, pl) != SKT_OK) return 0;
-        if (pl.nsplit > 1) need = std::max(need, align_up((size_t)pl.nsplit * pl.In * rank * sizeof(double), 256));
+        if (tma) {   // stream-K slabs: two partial segments of bi x rank per CTA
+            const long long g = std::min<long long>(sm_count() + 4, (long long)pl.nit * pl.nred);
+            need = std::max(need, align_up((size_t)2 * g * (1 << pl.lg_bi) * rank * sizeof(double), 256));
+        } else if (pl.nsplit > 1) {
+            need = std::max(need, align_up((size_t)pl.nsplit * pl.In * rank * sizeof(double), 256));
+        }
     }
     return need;
 }
@@ -1004,9 +1048,17 @@ int dense_impl(const double *X_d, const int64_t *shape, int ndim, const double *
     }
     // every tile row is its own output row: the accumulators are stored straight from registers
     const bool direct = rows_only || (use_tma && !pl.mmajor && pl.L == 1 && pl.T == 1 && pl.nw == 0);
-    const int nsplit_out = direct ? 1 : pl.nsplit;   // direct: nothing is reduced across tiles, the splits only partition them
+    // TMA kernel: stream-K (contiguous tile ranges, partial segments in per-CTA slabs); cp.async kernel: split slabs
+    const bool streamk = use_tma;
+    const int nsplit_out = (direct || streamk) ? 1 : pl.nsplit;
+    const long long ntiles = (long long)pl.nit * pl.nred;
+    SKT_REQUIRE(ntiles < (1LL << 31), SKT_ESHAPE, "tensor too large for the tile scheduler (%lld tiles)", ntiles);
+    const int sk_grid = (int)std::min<long long>(sm_count(), ntiles);
+    const long long slab_stride = (long long)(1 << pl.lg_bi) * rank;
+    const bool sk_partials = streamk && !direct && pl.nred > 1;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t need = (nsplit_out > 1) ? (size_t)nsplit_out * pl.In * rank * sizeof(double) : 0;
+    const size_t need = sk_partials ? (size_t)2 * sk_grid * slab_stride * sizeof(double)
+                                    : ((nsplit_out > 1) ? (size_t)nsplit_out * pl.In * rank * sizeof(double) : 0);
     SKT_REQUIRE(ws_bytes >= need && (need == 0 || ws_d != nullptr), SKT_EWORKSPACE,
                 "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
 
@@ -1021,6 +1073,10 @@ int dense_impl(const double *X_d, const int64_t *shape, int ndim, const double *
     p.nk = use_tma ? (pl.Kc + TK - 1) / TK : (pl.Kc + BK - 1) / BK;
     p.nw = pl.nw;
     p.direct = direct ? 1 : 0;
+    p.ntiles = ntiles;
+    p.slab = sk_partials ? (double *)ws_d : nullptr;
+    p.slab_stride = slab_stride;
+    const int grid = streamk ? sk_grid : pl.grid;
     p.out_split_stride = (nsplit_out > 1) ? (long long)pl.In * rank : 0;
     double *outbase = (nsplit_out > 1) ? (double *)ws_d : M_d;
     const bool xalign = (((uintptr_t)X_d) & 15) == 0;
@@ -1043,11 +1099,17 @@ int dense_impl(const double *X_d, const int64_t *shape, int ndim, const double *
         if (use_tma) {
             // the tile height is fixed by the plan: 128-row tiles always run the two-column-group kernels
             const int nbk = (pl.bm == 128) ? std::max(nb, 5) : nb;
-            rc = pl.mmajor ? launch_dense_tma_nb<true>(nbk, tm, p, pl.grid, st) : launch_dense_tma_nb<false>(nbk, tm, p, pl.grid, st);
+            rc = pl.mmajor ? launch_dense_tma_nb<true>(nbk, tm, p, grid, st) : launch_dense_tma_nb<false>(nbk, tm, p, grid, st);
         }
         else
             rc = pl.mmajor ? launch_dense_nb<true>(nb, p, pl.grid, st) : launch_dense_nb<false>(nb, p, pl.grid, st);
         if (rc != SKT_OK) return rc;
+        if (sk_partials) {
+            const long long n = (long long)pl.nit * (1 << pl.lg_bi) * ncol;
+            streamk_fixup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.slab, slab_stride, ntiles, pl.nred, grid, pl.nit,
+                                                                           1 << pl.lg_bi, pl.In, ncol, rank, p.out);
+            SKT_LAUNCH_CHECK();
+        }
     }
     if (nsplit_out > 1) {
         const long long n = (long long)pl.In * rank;
