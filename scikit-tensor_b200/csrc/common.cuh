@@ -68,6 +68,10 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, int 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
                  "r"(src_bytes));
 }
+// 16-byte async copy with an L2 cache-policy hint (createpolicy)
+__device__ __forceinline__ void cp_async16_hint(void *smem_dst, const void *gsrc, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "l"(pol));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

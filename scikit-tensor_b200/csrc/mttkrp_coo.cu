@@ -14,6 +14,8 @@
 // fix-up kernel, always in storage order -- a segmented reduction without a single atomic and
 // with a reproducible summation order.  Rows without non-zeros are zero (M is cleared first).
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 #include <cstring>
 
 #include <cub/cub.cuh>
@@ -72,7 +74,18 @@ struct Vec<2> {
     }
 };
 
-template <int GS, int VPL, int VEC, int NO>
+// STAGED (VEC == 2, VPL == 1): factor rows are gathered with cp.async (LDGSTS) into a per-warp ring of shared-memory
+// stages instead of registers.  A lane later reads back exactly the 16-byte chunks it copied itself, so the ring
+// needs no barrier -- it is a deep, register-free extension of each lane's load queue: SD-1 batches of
+// 8 non-zeros x NO rows x 16 bytes per lane stay in flight (the register version is limited to one batch by its
+// 124 registers and 25 % occupancy; ncu: 60 % long-scoreboard stalls with L2 and DRAM both under 40 %).
+constexpr int SD = 3;             // ring depth (stages)
+// per-group (value,row) block of a stage: SBB x 16 bytes + 16 bytes of padding so that the groups of a warp read
+// their broadcast words from different banks
+template <int GS, int NO, int SBB>
+constexpr size_t staged_warp_bytes() { return (size_t)SD * ((32 / GS) * SBB * NO * GS * 16 + (32 / GS) * (SBB * 16 + 16)); }
+
+template <int GS, int VPL, int VEC, int NO, bool STAGED = false, int SBB = 8>
 __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ CooParams p) {
     constexpr int NG = CT / GS;       // groups per CTA
     constexpr int CPL = VPL * VEC;    // columns per lane
@@ -130,6 +143,122 @@ __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ 
         cok[vv] = col0 < R;
         ccol[vv] = cok[vv] ? col0 : 0;
     }
+    if constexpr (STAGED) {
+        static_assert(!STAGED || (VEC == 2 && VPL == 1), "staged gathers use one 16-byte chunk per lane and row");
+        constexpr int NGW = 32 / GS;                       // groups per warp
+        constexpr int ROWB = GS * 16;                      // bytes per staged row
+        constexpr int DATAB = NGW * SBB * NO * ROWB;       // row data per stage
+        constexpr int METAG = SBB * 16 + 16;               // padded (value, row id) block of one group
+        constexpr int STAGEB = DATAB + NGW * METAG;        // + (value, row id) per non-zero
+        constexpr int NBATCH = S / SBB;                    // 32 batches per group
+        constexpr int RND = 4;                             // batches per subscript round
+        unsigned char *ring = reinterpret_cast<unsigned char *>(cval + 2 * NG * RW) + (size_t)(tid >> 5) * (SD * STAGEB);
+        const int gw = (tid & 31) / GS;                    // group within the warp
+        const bool colok = cok[0];
+        // subscripts / values of one round (4 batches x 8 non-zeros per group): lane gl < 8 holds non-zero 8c + gl
+        int r_row[2][RND], r_idx[2][RND][NO];
+        double r_val[2][RND];
+        // (round buffers and components are compile-time constants everywhere: the arrays stay in registers)
+        auto load_round = [&](int rnd, auto BUF) {
+            constexpr int buf = decltype(BUF)::value;
+#pragma unroll
+            for (int c = 0; c < RND; ++c) {
+                const long long q = start + (long long)rnd * (RND * SBB) + c * SBB + gl;
+                const bool have = (gl < SBB) && (q < end) && (rnd * RND + c < NBATCH);
+                // (L2 evict_last on the factor rows / streaming loads here were measured: no effect at 200 M nnz)
+                r_row[buf][c] = have ? p.rows[q] : -1;
+                r_val[buf][c] = have ? p.vals[q] : 0.0;
+#pragma unroll
+                for (int m = 0; m < NO; ++m) r_idx[buf][c][m] = (have && m < p.nother) ? p.oidx[m][q] : 0;
+            }
+        };
+        auto issue_batch = [&](int k, auto BUF, auto COMP) {    // batch k lives in round buffer BUF, component COMP
+            constexpr int buf = decltype(BUF)::value, c = decltype(COMP)::value;
+            unsigned char *st = ring + (k % SD) * STAGEB;
+#pragma unroll
+            for (int b = 0; b < SBB; ++b) {
+                const int src = gbase + b;
+#pragma unroll
+                for (int m = 0; m < NO; ++m) {
+                    const int im = __shfl_sync(FULL, r_idx[buf][c][m], src);
+                    const int mm = (NO <= 3 || m < p.nother) ? m : 0;
+                    const double *rowp = p.U[mm] + (long long)((NO <= 3 || m < p.nother) ? im : 0) * R + ccol[0];
+                    cp_async16(st + ((gw * SBB + b) * NO + m) * ROWB + gl * 16, rowp, 16);
+                }
+            }
+            if (gl < SBB) {
+                double *meta = reinterpret_cast<double *>(st + DATAB + gw * METAG + gl * 16);
+                meta[0] = r_val[buf][c];
+                reinterpret_cast<int *>(meta + 1)[0] = r_row[buf][c];
+            }
+        };
+        auto compute_batch = [&](int t) {
+            const unsigned char *st = ring + (t % SD) * STAGEB;
+#pragma unroll
+            for (int b = 0; b < SBB; ++b) {
+                const double *meta = reinterpret_cast<const double *>(st + DATAB + gw * METAG + b * 16);
+                const double v = meta[0];
+                const int row = reinterpret_cast<const int *>(meta + 1)[0];
+                double x0 = colok ? v : 0.0, x1 = x0;
+#pragma unroll
+                for (int m = 0; m < NO; ++m) {
+                    if (NO <= 3 || m < p.nother) {
+                        const double2 u = *reinterpret_cast<const double2 *>(st + ((gw * SBB + b) * NO + m) * ROWB + gl * 16);
+                        x0 *= u.x; x1 *= u.y;
+                    }
+                }
+                if (row >= 0) {
+                    if (row != cur_row) {
+                        flush(false);
+                        acc[0] = acc[1] = 0.0;
+                        cur_row = row;
+                    }
+                    acc[0] += x0; acc[1] += x1;
+                }
+            }
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        // one round: RND batches whose subscripts sit in buffer CUR; the ring is refilled SD-1 batches ahead, from
+        // this round's registers or (for the last SD-1 batches) from the next round's
+        auto round_body = [&](int rnd, auto CUR) {
+            constexpr int cur = decltype(CUR)::value;
+            using C = std::integral_constant<int, cur>;
+            using N = std::integral_constant<int, cur ^ 1>;
+            auto step = [&](auto CC) {
+                constexpr int c = decltype(CC)::value;
+                const int t = rnd * RND + c;
+                const int k = t + SD - 1;
+                constexpr int kc = (c + SD - 1) % RND;
+                if (k < NBATCH) {
+                    if constexpr (c + SD - 1 >= RND) issue_batch(k, N{}, std::integral_constant<int, kc>{});
+                    else issue_batch(k, C{}, std::integral_constant<int, kc>{});
+                }
+                cp_async_commit();
+                cp_async_wait<SD - 1>();
+                __syncwarp();                              // the (value, row) pairs were written by other lanes
+                compute_batch(t);
+                __syncwarp();                              // stage t % SD is refilled by the next issue
+            };
+            step(std::integral_constant<int, 0>{});
+            step(std::integral_constant<int, 1>{});
+            step(std::integral_constant<int, 2>{});
+            step(std::integral_constant<int, 3>{});
+            load_round(rnd + 2, C{});                      // this round's registers are free: fetch round rnd + 2
+        };
+        load_round(0, I0{});
+        load_round(1, I1{});
+        issue_batch(0, I0{}, I0{});
+        cp_async_commit();
+        issue_batch(1, I0{}, I1{});
+        cp_async_commit();
+        static_assert(SD == 3 && RND == 4 && (NBATCH / RND) % 2 == 0, "prologue / round pairing written for SD = 3");
+        for (int rnd = 0; rnd < NBATCH / RND; rnd += 2) {
+            round_body(rnd, I0{});
+            round_body(rnd + 1, I1{});
+        }
+        cp_async_wait<0>();
+    } else
     for (int b0 = 0; b0 < S; b0 += BB) {
         // lanes 0..BB-1 of the group fetch the subscripts/value of one non-zero each (BB <= GS)
         const long long my = start + b0 + gl;
@@ -373,6 +502,39 @@ int launch_coo_no(int nother, const CooParams &p, long long nctas, cudaStream_t 
     return SKT_OK;
 }
 
+// cp.async-staged variant (16-byte aligned factors, even rank <= 64, at most 3 gathered modes)
+template <int GS, int NO, int SBB>
+int launch_coo_staged_one(const CooParams &p, long long nctas, cudaStream_t st) {
+    constexpr int NG = CT / GS;
+    const size_t carry = (size_t)((2 * NG * sizeof(int) + 7) / 8 * 8) + (size_t)2 * NG * GS * 2 * sizeof(double);
+    const size_t smem = carry + (CT / 32) * staged_warp_bytes<GS, NO, SBB>();
+    static bool configured = false;
+    if (!configured) {
+        SKT_CUDA(cudaFuncSetAttribute(mttkrp_coo_kernel<GS, 1, 2, NO, true, SBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    mttkrp_coo_kernel<GS, 1, 2, NO, true, SBB><<<(unsigned)nctas, CT, smem, st>>>(p);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+template <int GS>
+int launch_coo_staged(int nother, const CooParams &p, long long nctas, cudaStream_t st) {
+    static const char *e = getenv("SKT_COO_SBB");
+    const bool small = !(e && atoi(e) == 8);   // 4 non-zeros per group and batch: 16 warps per SM (measured 6-10 % faster than 8)
+    if (nother <= 1) return small ? launch_coo_staged_one<GS, 1, 4>(p, nctas, st) : launch_coo_staged_one<GS, 1, 8>(p, nctas, st);
+    if (nother == 2) return small ? launch_coo_staged_one<GS, 2, 4>(p, nctas, st) : launch_coo_staged_one<GS, 2, 8>(p, nctas, st);
+    return small ? launch_coo_staged_one<GS, 3, 4>(p, nctas, st) : launch_coo_staged_one<GS, 3, 8>(p, nctas, st);
+}
+
+bool staged_ok(int gs, int vpl, int vec, int nother) {
+    const char *off = getenv("SKT_COO_NO_STAGED");
+    if (off && off[0] == '1') return false;
+    if (vec != 2 || vpl != 1 || nother > 3) return false;
+    const size_t ring = (size_t)(CT / 32) * SD * ((32 / gs) * 8 * nother * gs * 16 + (32 / gs) * (8 * 16 + 16));
+    return ring + 16384 <= smem_optin_bytes();
+}
+
 template <int VEC>
 int launch_coo_vec(int gs, int vpl, int nother, const CooParams &p, long long nctas, cudaStream_t st) {
     if (vpl == 1) {
@@ -388,6 +550,13 @@ int launch_coo_vec(int gs, int vpl, int nother, const CooParams &p, long long nc
 }
 
 int launch_coo(int gs, int vpl, int vec, int nother, const CooParams &p, long long nctas, cudaStream_t st) {
+    if (staged_ok(gs, vpl, vec, nother)) {
+        switch (gs) {
+            case 8: return launch_coo_staged<8>(nother, p, nctas, st);
+            case 16: return launch_coo_staged<16>(nother, p, nctas, st);
+            default: return launch_coo_staged<32>(nother, p, nctas, st);
+        }
+    }
     return (vec == 2) ? launch_coo_vec<2>(gs, vpl, nother, p, nctas, st) : launch_coo_vec<1>(gs, vpl, nother, p, nctas, st);
 }
 

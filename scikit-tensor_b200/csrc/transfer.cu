@@ -20,7 +20,7 @@ namespace skt {
 namespace {
 
 constexpr size_t CHUNK = 4u << 20;   // bytes per staging buffer
-constexpr int MAX_THREADS = 8;
+constexpr int MAX_THREADS = 16;
 constexpr int SLOTS = 2;             // staging buffers per thread (memcpy of one overlaps the DMA of the other)
 
 struct Pool {

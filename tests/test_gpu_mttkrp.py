@@ -35,6 +35,15 @@ def dense_path(request):
     os.environ['SKT_DENSE_NO_TMA'] = '0'
 
 
+@pytest.fixture(params=['staged', 'registers'])
+def sparse_path(request):
+    """Both sparse kernels: cp.async-staged gathers (default for even ranks) and the register-gather variant."""
+    import os
+    os.environ['SKT_COO_NO_STAGED'] = '1' if request.param == 'registers' else '0'
+    yield request.param
+    os.environ['SKT_COO_NO_STAGED'] = '0'
+
+
 def gpu_mttkrp_dense(K, dev, X, U, n, naive=False):
     R = next(u for m, u in enumerate(U) if m != n and u is not None).shape[1]
     Ud = [None if (u is None or m == n) else dev.to_device(u) for m, u in enumerate(U)]
@@ -191,7 +200,7 @@ def gpu_mttkrp_coo(K, dev, subs, vals, shape, U, n, atomic=False):
     return M
 
 
-def test_sparse_golden_all_modes(K, dev, golden):
+def test_sparse_golden_all_modes(K, dev, golden, sparse_path):
     for name, c in golden.j['sp_cases'].items():
         N = len(c['shape'])
         subs = [golden['mts_%s_sub%d' % (name, m)] for m in range(N)]
@@ -214,7 +223,7 @@ def test_sparse_golden_all_modes(K, dev, golden):
     ((50, 40, 30, 20), 8000, 8, 2.0), ((20000, 300, 7), 60000, 64, 3.0), ((9, 8, 7, 6, 5), 3000, 5, 1.0),
     ((300, 200), 4000, 4, 2.0), ((40, 30, 20), 1, 16, 1.0), ((5, 200000, 3), 50000, 33, 3.0),
 ])
-def test_sparse_random_vs_oracle(K, dev, shape, nnz, R, alpha):
+def test_sparse_random_vs_oracle(K, dev, shape, nnz, R, alpha, sparse_path):
     g = np.random.default_rng(abs(hash((shape, nnz, R))) % (2 ** 31))
     subs = [np.minimum((I * g.random(nnz) ** alpha).astype(np.int64), I - 1) for I in shape]
     vals = g.random(nnz) - 0.25
@@ -225,7 +234,7 @@ def test_sparse_random_vs_oracle(K, dev, shape, nnz, R, alpha):
         assert relerr(got, ref) < TOL, (shape, n)
 
 
-def test_sparse_edge_cases(K, dev):
+def test_sparse_edge_cases(K, dev, sparse_path):
     from sktensor import sptensor
     # one heavy row spanning many CTAs, the rest empty; plus a lone entry in the last row
     nnz = 300000
@@ -266,7 +275,7 @@ def test_sparse_method_contract(K, dev, golden):
     assert abs(S.norm() - golden.j['mts_%s_norm' % name]) < 1e-12
 
 
-def test_sparse_power_law_200k(K, dev):
+def test_sparse_power_law_200k(K, dev, sparse_path):
     """BASELINE config 3 generator at 2e5 nnz: parity vs the oracle, all modes."""
     shape = (10000000, 1000000, 100000)
     nnz = 200000
