@@ -406,19 +406,113 @@ def run_sparse(args):
     print(json.dumps(out))
 
 
+def run_config(args):
+    """Secondary, multi-GPU-capable runs of the other BASELINE.json configurations (not the driver's line):
+
+      --workload cfg3 : cp_als on the sparse 10M x 1M x 100K power-law tensor, --nnz non-zeros in total (200 M =
+                        configs[2]), rank 16, cut along mode 0 into equal-nnz row ranges, one per GPU
+      --workload cfg5 : cp_als on the dense 160^4 tensor, rank 64, cut along mode 0 (configs[4]; strong scaling)
+
+    Every rank generates only its own slab (same distribution as SURVEY 8(d): mode-0 subscripts are drawn by
+    inverse-CDF sampling inside the rank's quantile range).  Prints one JSON line on rank 0.
+    """
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from sktensor import _lib, _parallel, dtensor, sptensor
+    lib = _lib.load()
+    rng = np.random.default_rng(1000 + rank)
+    tic = time.perf_counter()
+    if args.workload == 'cfg3':
+        R, gshape = 16, SPARSE_SHAPE
+        I0 = gshape[0]
+        offsets = np.array([int(np.ceil(I0 * (r / float(world)) ** 3.0)) for r in range(world)] + [I0], dtype=np.int64)
+        nloc = args.nnz // world
+        u = (rank + rng.random(nloc)) / float(world)                          # this rank's quantile range
+        i0 = np.clip((I0 * u ** 3.0).astype(np.int64), offsets[rank], offsets[rank + 1] - 1) - offsets[rank]
+        subs = (i0,) + tuple(np.minimum((I * rng.random(nloc) ** 3.0).astype(np.int64), I - 1) for I in gshape[1:])
+        lshape = (int(offsets[rank + 1] - offsets[rank]),) + tuple(gshape[1:])
+        X = _parallel.LocalShard(sptensor(subs, rng.random(nloc), shape=lshape), 0, gshape, offsets)
+        alg = 3 * alg_bytes_sparse(gshape, nloc * world, R)
+        desc = 'cp_als sparse 10Mx1Mx100K power-law, %d nnz, rank 16 (BASELINE.json configs[2]), mode-0 equal-nnz cuts' % (nloc * world)
+    else:
+        R, gshape = 64, (160, 160, 160, 160)
+        offsets = _parallel.split_rows(gshape[0], world)
+        rows = int(offsets[rank + 1] - offsets[rank])
+        X = _parallel.LocalShard(dtensor(rng.random((rows,) + gshape[1:])), 0, gshape, offsets)
+        alg = 4 * alg_bytes_dense(gshape, R)
+        desc = 'cp_als dense 4-way 160^4 rank 64 (BASELINE.json configs[4]), cut along mode 0 (strong scaling)'
+    gen_s = time.perf_counter() - tic
+    np.random.seed(1)
+    U = [None] + [np.random.rand(gshape[n], R) for n in range(1, len(gshape))]
+    tic = time.perf_counter()
+    eng = _parallel.CpAlsEngine(X, R, U)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - tic
+    W = max(args.warmup, 3)
+    steps = args.steps if args.steps != 200 else 20
+    for w in range(W):
+        eng.sweep(first_iter=(w == 0))
+        eng.begin_read()
+        eng.prefetch_next_sweep()
+        eng.read_fit()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = lib.skt_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    fit = 0.0
+    for _ in range(steps):
+        eng.sweep(first_iter=False)
+        eng.begin_read()
+        eng.prefetch_next_sweep()
+        fit = eng.read_fit()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / steps
+    if rank == 0:
+        hbm_peak, peak_src = measured_peaks()
+        line = {'metric': METRIC, 'value': alg / (ms_step * 1e-3) / 1e9, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': W,
+                'ms_per_step': ms_step, 'als_iters_per_sec': 1e3 / ms_step, 'higher_is_better': True,
+                'scaling': 'strong', 'dtype': 'f64', 'data': 'synthetic', 'final_fit': fit,
+                'config': {'workload': desc, 'shape': list(gshape), 'rank': R},
+                'frac_of_hbm_per_gpu': alg / (ms_step * 1e-3) / 1e9 / world / hbm_peak,
+                'host_seconds': {'generate_slab': gen_s, 'upload_sort_setup': setup_s},
+                'gpu_launches': int(lib.skt_launch_count() - launches0)}
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='dense', choices=['dense', 'sparse'])
+    ap.add_argument('--workload', default='dense', choices=['dense', 'sparse', 'cfg3', 'cfg5'])
     ap.add_argument('--nnz', type=int, default=20000000)
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
     if args.workload == 'sparse':
         return run_sparse(args)
+    if args.workload in ('cfg3', 'cfg5'):
+        return run_config(args)
     return run_gpu(args)
 
 

@@ -336,7 +336,7 @@ extern "C" size_t skt_sumsq_workspace(int64_t n) {
 
 extern "C" int skt_gram(const double *U_d, int64_t rows, int rank, double *G_d, void *ws_d, size_t ws_bytes,
                         skt_stream stream) {
-    SKT_REQUIRE(U_d && G_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
+    SKT_REQUIRE((U_d || rows == 0) && G_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
     int rc = check_rank(rank);
     if (rc) return rc;
     return launch_factor_pass(const_cast<double *>(U_d), nullptr, rows, rank, 0, 0, nullptr, G_d, nullptr, nullptr, ws_d,
@@ -346,8 +346,8 @@ extern "C" int skt_gram(const double *U_d, int64_t rows, int rank, double *G_d, 
 extern "C" int skt_normalise_gram(double *U_d, const double *colstat_d, int64_t rows, int rank, int first_iter,
                                   double *lambda_d, double *G_d, const double *Mip_d, double *ip_d, void *ws_d,
                                   size_t ws_bytes, skt_stream stream) {
-    SKT_REQUIRE(U_d && colstat_d && lambda_d && G_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
-    SKT_REQUIRE((Mip_d == nullptr) == (ip_d == nullptr), SKT_EINVAL, "Mip_d and ip_d must be given together");
+    SKT_REQUIRE((U_d || rows == 0) && colstat_d && lambda_d && G_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
+    SKT_REQUIRE((Mip_d == nullptr) == (ip_d == nullptr) || rows == 0, SKT_EINVAL, "Mip_d and ip_d must be given together");
     int rc = check_rank(rank);
     if (rc) return rc;
     return launch_factor_pass(U_d, colstat_d, rows, rank, 1, first_iter, lambda_d, G_d, Mip_d, ip_d, ws_d, ws_bytes,
@@ -356,7 +356,7 @@ extern "C" int skt_normalise_gram(double *U_d, const double *colstat_d, int64_t 
 
 extern "C" int skt_solve_stats(const double *M_d, const double *P_d, int64_t rows, int rank, int first_iter,
                                double *Unew_d, double *colstat_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
-    SKT_REQUIRE(M_d && P_d && Unew_d && colstat_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
+    SKT_REQUIRE((M_d || rows == 0) && P_d && (Unew_d || rows == 0) && colstat_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
     int rc = check_rank(rank);
     if (rc) return rc;
     const size_t need = pass_ws_bytes(rows, MAXR);
@@ -418,7 +418,7 @@ extern "C" int skt_cp_fit(const double *G_d, int ndim, int rank, const double *l
 }
 
 extern "C" int skt_sumsq(const double *x_d, int64_t n, double *out_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
-    SKT_REQUIRE(x_d && out_d && n >= 0, SKT_EINVAL, "NULL argument or negative length");
+    SKT_REQUIRE((x_d || n == 0) && out_d && n >= 0, SKT_EINVAL, "NULL argument or negative length");
     const size_t need = skt_sumsq_workspace(n);
     SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     cudaStream_t st = (cudaStream_t)stream;
@@ -433,7 +433,7 @@ extern "C" int skt_sumsq(const double *x_d, int64_t n, double *out_d, void *ws_d
 
 extern "C" int skt_weighted_dot(const double *U_d, const double *M_d, const double *lambda_d, int64_t rows, int rank,
                                 double *out_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
-    SKT_REQUIRE(U_d && M_d && out_d && rows >= 0 && rank >= 1, SKT_EINVAL, "NULL argument or bad size");
+    SKT_REQUIRE(((U_d && M_d) || rows == 0) && out_d && rows >= 0 && rank >= 1, SKT_EINVAL, "NULL argument or bad size");
     const long long n = (long long)rows * rank;
     const size_t need = skt_sumsq_workspace(n);
     SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);

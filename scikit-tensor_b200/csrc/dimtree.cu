@@ -125,6 +125,9 @@ int kr_plan(const int64_t *dims, int p, int rank, int mode, long long &In, long 
 using namespace skt;
 
 extern "C" size_t skt_kr_reduce_workspace(const int64_t *dims, int p, int rank, int mode) {
+    if (dims && p >= 2 && p <= SKT_MAX_NDIM)
+        for (int m = 0; m < p; ++m)
+            if (dims[m] == 0) return 256;
     long long In, L, Tt, chunk;
     int nsplit;
     if (kr_plan(dims, p, rank, mode, In, L, Tt, nsplit, chunk) != SKT_OK) return 0;
@@ -133,6 +136,14 @@ extern "C" size_t skt_kr_reduce_workspace(const int64_t *dims, int p, int rank, 
 
 extern "C" int skt_kr_reduce(const double *T_d, const int64_t *dims, int p, const double *const *W_d, int rank, int mode,
                              double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    if (dims && p >= 2 && p <= SKT_MAX_NDIM && mode >= 0 && mode < p && rank >= 1) {
+        bool empty = false;
+        for (int m = 0; m < p; ++m) empty = empty || dims[m] == 0;
+        if (empty) {     // empty group (a rank without rows): all zeros
+            if (dims[mode] > 0 && M_d) SKT_CUDA(cudaMemsetAsync(M_d, 0, (size_t)dims[mode] * rank * sizeof(double), (cudaStream_t)stream));
+            return SKT_OK;
+        }
+    }
     SKT_REQUIRE(T_d && W_d && M_d, SKT_EINVAL, "NULL argument");
     long long In, L, Tt, chunk;
     int nsplit;

@@ -591,7 +591,8 @@ extern "C" int skt_coo_build(const int64_t *const *subs_d, const double *vals_d,
     SKT_REQUIRE(ndim >= 2 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "ndim must be in [2, %d], got %d", SKT_MAX_NDIM, ndim);
     SKT_REQUIRE(nnz >= 0 && nnz < (1LL << 31) - 1, SKT_ESHAPE, "nnz %lld outside [0, 2^31)", (long long)nnz);
     for (int m = 0; m < ndim; ++m)
-        SKT_REQUIRE(shape[m] >= 1 && shape[m] < (1LL << 31), SKT_ESHAPE, "shape[%d] = %lld not in [1, 2^31)", m, (long long)shape[m]);
+        SKT_REQUIRE((shape[m] >= 1 || (shape[m] == 0 && nnz == 0)) && shape[m] < (1LL << 31), SKT_ESHAPE,
+                    "shape[%d] = %lld not in [1, 2^31)", m, (long long)shape[m]);
     cudaStream_t st = (cudaStream_t)stream;
     if (modes_mask == 0) modes_mask = (1u << ndim) - 1u;
 
@@ -704,9 +705,17 @@ extern "C" size_t skt_mttkrp_coo_workspace(const skt_coo *t, int rank, int mode)
 
 extern "C" int skt_mttkrp_coo(const skt_coo *t, const double *const *U_d, int rank, int mode, double *M_d, void *ws_d,
                               size_t ws_bytes, skt_stream stream) {
-    SKT_REQUIRE(t && U_d && M_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(t && U_d, SKT_EINVAL, "NULL argument");
     SKT_REQUIRE(mode >= 0 && mode < t->ndim, SKT_EINVAL, "mode %d out of range", mode);
     SKT_REQUIRE(rank >= 1, SKT_EINVAL, "rank must be >= 1");
+    if (t->nnz == 0) {   // empty tensor (a rank of a sharded run may own no non-zeros): all zeros
+        if (t->shape[mode] > 0) {
+            SKT_REQUIRE(M_d, SKT_EINVAL, "NULL output");
+            SKT_CUDA(cudaMemsetAsync(M_d, 0, (size_t)t->shape[mode] * rank * sizeof(double), (cudaStream_t)stream));
+        }
+        return SKT_OK;
+    }
+    SKT_REQUIRE(M_d, SKT_EINVAL, "NULL output");
     SKT_REQUIRE(t->built_mask & (1u << mode), SKT_EINVAL, "the sorted copy for mode %d was not built", mode);
     bool aligned = true;                     // 16-byte factor-row loads need 16-byte aligned factors
     for (int m = 0; m < t->ndim; ++m)

@@ -1005,6 +1005,9 @@ int launch_dense_nb(int nb, const DenseParams &p, int grid, cudaStream_t st) {
 using namespace skt;
 
 extern "C" size_t skt_mttkrp_dense_workspace(const int64_t *shape, int ndim, int rank, int mode) {
+    if (shape && ndim >= 1 && ndim <= SKT_MAX_NDIM)
+        for (int m = 0; m < ndim; ++m)
+            if (shape[m] == 0) return 256;   // empty tensor: nothing to stage
     // the kernel variant (TMA or cp.async) is chosen at launch from the pointer alignment: cover both plans
     size_t need = 256;
     for (int tma = 0; tma < 2; ++tma) {
@@ -1025,6 +1028,20 @@ namespace skt {
 // reduction over l, t); needs the TMA kernel.  Otherwise the MTTKRP of `mode`.
 int dense_impl(const double *X_d, const int64_t *shape, int ndim, const double *const *U_d, int rank, int mode,
                double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream, bool rows_only) {
+    // an empty tensor (a rank of a sharded run may own no rows): the MTTKRP is all zeros
+    if (shape && ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= 0 && mode < ndim && rank >= 1) {
+        bool empty = false;
+        long long rows_out = 1;
+        for (int m = 0; m < ndim; ++m) {
+            SKT_REQUIRE(shape[m] >= 0, SKT_ESHAPE, "shape[%d] = %lld", m, (long long)shape[m]);
+            if (shape[m] == 0) empty = true;
+            if (rows_only ? (m != (mode == ndim - 1 ? 0 : ndim - 1)) : (m == mode)) rows_out *= shape[m];
+        }
+        if (empty) {
+            if (rows_out > 0 && M_d) SKT_CUDA(cudaMemsetAsync(M_d, 0, (size_t)rows_out * rank * sizeof(double), (cudaStream_t)stream));
+            return SKT_OK;
+        }
+    }
     SKT_REQUIRE(X_d && U_d && M_d, SKT_EINVAL, "NULL tensor / factor list / output");
     DensePlan pl;
     int rc = make_plan(shape, ndim, rank, mode, false, pl);

@@ -44,6 +44,19 @@ def main():
     run('cp_d4_s3', dtensor(g['cp4_X']), 4, 3, init='random', max_iter=30)      # 4-way, sharded on the last mode
     subs = tuple(g['cpsp_sub%d' % m] for m in range(3))
     run('cp_sp_s1', sptensor(subs, g['cpsp_vals'], shape=(60, 50, 40)), 5, 1, init='random', max_iter=25)
+    # lopsided cuts: rank 0 owns every row of the sharded mode, all other ranks own EMPTY slabs (what happens for real
+    # when a mode is shorter than the world size, or with power-law non-zero cuts); results must not change
+    world = dist.get_world_size()
+    offs = np.array([0] + [X1.shape[1]] * world, dtype=np.int64)
+    lo, hi = int(offs[rank]), int(offs[rank + 1])
+    run('cp_cfg1_s42_lopsided', _parallel.LocalShard(dtensor(np.ascontiguousarray(X1[:, lo:hi, :])), 1, X1.shape, offs),
+        3, 42, init='random')
+    S3 = fromarray(X1 * (X1 > 0.7))
+    keep = (np.asarray(S3.subs[1]) >= lo) & (np.asarray(S3.subs[1]) < hi)
+    lsubs = tuple((np.asarray(sm)[keep] - (lo if m == 1 else 0)).astype(np.int64) for m, sm in enumerate(S3.subs))
+    lshape = (X1.shape[0], hi - lo, X1.shape[2])
+    run('cp_kat3_s42_lopsided', _parallel.LocalShard(sptensor(lsubs, np.asarray(S3.vals)[keep], shape=lshape), 1, X1.shape, offs),
+        3, 42, init='random')
     np.random.seed(42)
     _, fit, itr, _ = cp_als(dtensor(X1), 3, init='random', fit_method=None, max_iter=4)
     res['nofit'] = {'fit': float(fit), 'itr': int(itr)}

@@ -339,3 +339,34 @@ def test_dimension_tree_engine_equals_plain_sweeps():
         assert abs(res['0'][0] - res['1'][0]) < 1e-12
         for a, b in zip(res['0'][2], res['1'][2]):
             assert relerr(a, b) < 1e-9
+
+
+def test_empty_slabs_are_legal(K, dev):
+    """A rank of a sharded run may own no rows (7 rows over 8 ranks; power-law cuts): every kernel the engine
+    calls must accept zero-sized slabs and contribute exact zeros to the collectives."""
+    R = 4
+    X = dev.to_device(np.zeros((6, 5, 4, 0)))
+    U = [dev.to_device(np.random.rand(6, R)), dev.to_device(np.random.rand(5, R)), dev.to_device(np.random.rand(4, R)),
+         dev.to_device(np.zeros((0, R)))]
+    for n in range(3):
+        M = K.mttkrp_dense(X, (6, 5, 4, 0), U, R, n)
+        assert M.shape[0] == (6, 5, 4)[n] and (dev.to_host(M) == 0).all()
+    assert K.mttkrp_dense(X, (6, 5, 4, 0), U, R, 3).shape == (0, R)
+    TA = K.mttkrp_dense(X, (30, 4, 0), [None, U[2], U[3]], R, 0)
+    assert (dev.to_host(TA) == 0).all()
+    TB = dev.to_device(np.zeros((4, 0, R)))
+    assert (dev.to_host(K.kr_reduce(TB, (4, 0), [U[2], U[3]], R, 0)) == 0).all()
+    assert K.kr_reduce(TB, (4, 0), [U[2], U[3]], R, 1).shape == (0, R)
+    assert float(dev.to_host(K.sumsq(X))[0]) == 0.0
+    assert (dev.to_host(K.gram(U[3])) == 0).all()
+    P = dev.to_device(np.eye(R))
+    for first in (True, False):
+        Unew, colstat = K.solve_stats(dev.to_device(np.zeros((0, R))), P, first)
+        c = dev.to_host(colstat)
+        assert (c == 0).all() if first else (c < -1e300).all()
+        lam, G, ip = K.normalise_gram(Unew, dev.to_device(np.ones(R)), first, Mip=dev.to_device(np.zeros((0, R))))
+        assert (dev.to_host(G) == 0).all() and float(dev.to_host(ip)[0]) == 0.0
+    coo = K.CooHandle([np.zeros(0, np.int64)] * 3, np.zeros(0), (5, 0, 3))
+    Us = [dev.to_device(np.random.rand(5, R)), dev.to_device(np.zeros((0, R))), dev.to_device(np.random.rand(3, R))]
+    assert (dev.to_host(K.mttkrp_coo(coo, Us, R, 0)) == 0).all()
+    assert K.mttkrp_coo(coo, Us, R, 1).shape == (0, R)
