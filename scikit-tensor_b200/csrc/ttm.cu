@@ -9,6 +9,8 @@
 #include "common.cuh"
 
 namespace skt {
+int gram_dmma(const double *X_d, long long L, long long In, long long T, double *G_d, void *ws_d, size_t ws_bytes,
+              cudaStream_t st, size_t *need_out);
 int dense_impl(const double *X_d, const int64_t *shape, int ndim, const double *const *U_d, int rank, int mode,
                double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream, bool rows_only);
 namespace {
@@ -194,7 +196,10 @@ extern "C" size_t skt_unfold_gram_workspace(const int64_t *shape, int ndim, int 
     if (view3(shape, ndim, mode, L, In, T) != SKT_OK) return 0;
     long long nbatch, K;
     gram_view(L, In, T, nbatch, K);
-    return align_up((size_t)gram_splits(In, nbatch) * In * In * sizeof(double) + 256, 256);
+    size_t need = align_up((size_t)gram_splits(In, nbatch) * In * In * sizeof(double) + 256, 256);
+    size_t need_mma = 0;
+    if (gram_dmma(nullptr, L, In, T, nullptr, nullptr, 0, nullptr, &need_mma) == SKT_OK) need = std::max(need, need_mma);
+    return need;
 }
 
 extern "C" int skt_unfold_gram(const double *X_d, const int64_t *shape, int ndim, int mode, double *G_d, void *ws_d,
@@ -203,6 +208,9 @@ extern "C" int skt_unfold_gram(const double *X_d, const int64_t *shape, int ndim
     long long L, In, T;
     int rc = view3(shape, ndim, mode, L, In, T);
     if (rc) return rc;
+    // tensor-core route (16-byte aligned rows, I_n >= 64); anything else takes the generic strided GEMM below
+    rc = gram_dmma(X_d, L, In, T, G_d, ws_d, ws_bytes, (cudaStream_t)stream, nullptr);
+    if (rc != SKT_EUNSUPPORTED) return rc;
     long long nbatch, K;
     gram_view(L, In, T, nbatch, K);
     const int ns = gram_splits(In, nbatch);

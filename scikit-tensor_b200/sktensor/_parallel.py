@@ -123,7 +123,9 @@ class CudaBackend(object):
         return [h.numpy().copy() for h in host]
 
     # tensors
-    def upload_dense(self, X): return self.dev.to_device(np.asarray(X))
+    def upload_dense(self, X):
+        cached = getattr(X, '_dev', None)          # dtensor.cache_on_device(): reuse the resident copy
+        return cached if cached is not None else self.dev.to_device(np.asarray(X))
     def upload_coo(self, subs, vals, shape): return self.K.CooHandle(subs, vals, shape)
     # kernels
     def mttkrp_dense(self, Xd, shape, U, R, n, out): return self.K.mttkrp_dense(Xd, shape, U, R, n, out=out)

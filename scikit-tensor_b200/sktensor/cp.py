@@ -55,8 +55,16 @@ def als(X, rank, **kwargs):
         raise ValueError('Unknown keywords (%s)' % (kwargs.keys()))
 
     N = X.ndim
-    U = _init(ainit, X, N, rank, dtype)
-    eng = _parallel.CpAlsEngine(X, rank, U)
+    # one upload per call: the 'nvecs' initialisation and the sweep engine share the device copy
+    pinned_here = hasattr(X, 'cache_on_device') and getattr(X, '_dev', None) is None and ainit == 'nvecs'
+    if pinned_here:
+        X.cache_on_device()
+    try:
+        U = _init(ainit, X, N, rank, dtype)
+        eng = _parallel.CpAlsEngine(X, rank, U)
+    finally:
+        if pinned_here:
+            X.drop_device_cache()
 
     fit = 0
     exectimes = []

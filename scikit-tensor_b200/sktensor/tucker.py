@@ -42,10 +42,19 @@ def hooi(X, rank, **kwargs):
         rank = [rank] * ndims
     rank = [int(r) for r in rank]          # the reference carries floats here (tucker.py:90-91)
 
-    U = _init(ainit, X, ndims, rank, dtype)
     if isinstance(X, dtensor):
-        core, fit = _hooi_dense_device(X, rank, U, maxIter, conv)
+        # one upload per call: the 'nvecs' initialisation (hosvd) and the iteration share the device copy
+        pinned_here = getattr(X, '_dev', None) is None
+        if pinned_here:
+            X.cache_on_device()
+        try:
+            U = _init(ainit, X, ndims, rank, dtype)
+            core, fit = _hooi_dense_device(X, rank, U, maxIter, conv)
+        finally:
+            if pinned_here:
+                X.drop_device_cache()
         return core, U
+    U = _init(ainit, X, ndims, rank, dtype)
 
     # generic route for other tensor types: the reference's loop on their own ttm / nvecs
     normX = norm(X)
@@ -71,7 +80,7 @@ def _hooi_dense_device(X, rank, U, maxIter, conv):
     t = dev.torch()
     N = X.ndim
     shape = tuple(int(s) for s in X.shape)
-    Xd = dev.to_device(np.asarray(X))
+    Xd = X._device_tensor()
     normX2 = float(dev.to_host(K.sumsq(Xd))[0])
     normX = np.sqrt(normX2)
     Ud = [None if u is None else dev.to_device(u) for u in U]

@@ -373,7 +373,8 @@ def test_ttm_tensor_core_paths(K, dev, shape, p):
 
 
 @pytest.mark.parametrize('shape', [(40, 32, 32), (7, 9, 5), (384, 32, 32), (32, 384, 32), (32, 32, 384), (12, 10, 8, 6),
-                                   (1000, 24), (24, 1000), (3, 129, 2)])
+                                   (1000, 24), (24, 1000), (3, 129, 2), (200, 130, 70), (66, 300, 258), (130, 31, 64),
+                                   (5, 140, 6, 10)])
 def test_unfold_gram_all_modes(K, dev, shape):
     rng = np.random.RandomState(sum(shape))
     X = rng.rand(*shape) - 0.5
