@@ -187,6 +187,19 @@ SKT_API int skt_cp_update_cluster_fits(int64_t rows, int rank);
 SKT_API int skt_cp_update_cluster(const double *M_d, const double *P_d, int64_t rows, int rank, int ndim, int mode,
                           int first_iter, double *G_d, double *U_d, double *lambda_d, double *ip_d,
                           const double *normX2_d, double *fit_d, skt_stream stream);
+/* Exchange form of the update for a factor whose rows are spread over ranks (the sharded mode) or too tall for
+ * shared memory (sparse tensors).  skt_cp_update_exchange: Unew = M P (cp.py:147, not yet normalised) and one record
+ * ex_d = [colstat (R) | Unew^T Unew (R x R) | <Unew, M>] of skt_cp_exchange_record(R) doubles.  The ranks all-gather
+ * their records (one collective instead of three all-reduces); skt_cp_update_finish then forms, in rank order,
+ * lambda (cp.py:149-153), G[mode] = (sum_w Unew_w^T Unew_w) ./ (lambda lambda^T), <P,X>, the fit (cp.py:157-159),
+ * and divides the local rows by lambda -- skipped when every lambda is 1.  world = 1 for an unsharded factor.   */
+SKT_API size_t skt_cp_exchange_record(int rank);
+SKT_API size_t skt_cp_update_exchange_workspace(int64_t rows, int rank);
+SKT_API int skt_cp_update_exchange(const double *M_d, const double *P_d, int64_t rows, int rank, int first_iter,
+                           double *Unew_d, double *ex_d, void *ws_d, size_t ws_bytes, skt_stream stream);
+SKT_API int skt_cp_update_finish(const double *ex_all_d, int world, int first_iter, int64_t rows, int rank, int ndim,
+                         int mode, double *U_d, double *lambda_d, double *G_d, double *ip_d,
+                         const double *normX2_d, double *fit_d, skt_stream stream);
 /* Leave `n` SMs out of the persistent grids (dense MTTKRP) so that a small kernel on another stream can run
  * beside them; returns the previous value.  0 restores the full chip.                                      */
 SKT_API int skt_set_reserved_sms(int n);

@@ -277,6 +277,7 @@ struct ClusterParams {
     double *fit;
     long long rows;
     int R, ndim, mode, first_iter;
+    double *ex;   // non-NULL: phase-A mode -- write Unew (not normalised) to U and [colstat | Unew^T Unew | <Unew,M>] to ex
 };
 
 struct ClusterLayout {
@@ -396,9 +397,14 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
             const double v = remote(cst, k)[tid];
             sacc = p.first_iter ? sacc + v : fmax(sacc, v);
         }
-        const double l = p.first_iter ? sqrt(sacc) : (sacc < 1.0 ? 1.0 : sacc);   // cp.py:150 / cp.py:152-153
+        double l = p.first_iter ? sqrt(sacc) : (sacc < 1.0 ? 1.0 : sacc);   // cp.py:150 / cp.py:152-153
+        if (p.ex) {                      // phase A of a sharded update: the statistic still has to meet the other ranks'
+            if (crank == 0) p.ex[tid] = sacc;
+            l = 1.0;
+        } else if (crank == 0) {
+            p.lambda[tid] = l;
+        }
         lam[tid] = l;
-        if (crank == 0) p.lambda[tid] = l;
     }
     __syncthreads();
 
@@ -429,7 +435,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
 
     // ---- rank 0: G_n = sum of the partial Grams in rank order, <P,X>, fit
     if (crank == 0) {
-        double *Gn = p.G + (size_t)p.mode * R * R;
+        double *Gn = p.ex ? (p.ex + R) : (p.G + (size_t)p.mode * R * R);
         double *Gs = Ps;                                    // P is no longer needed
         for (int e = tid; e < R * R; e += CTH) {
             const int a = e / R, b = e - a * R;
@@ -438,14 +444,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
             Gn[e] = sum;
             Gs[e] = sum;
         }
-        if (tid == 0 && p.ip) {
+        if (tid == 0 && (p.ip || p.ex)) {
             double sum = 0.0;
             for (unsigned k = 0; k < CL; ++k) sum += remote(cst, k)[64];
-            p.ip[0] = sum;
+            if (p.ex) p.ex[R + R * R] = sum;
+            else p.ip[0] = sum;
             red[CWARPS] = sum;
         }
         __syncthreads();
-        if (p.fit) {
+        if (p.fit && !p.ex) {
             double sacc = 0.0;
             for (int e = tid; e < R * R; e += CTH) {
                 const int a = e / R, b = e - a * R;
@@ -466,6 +473,208 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
         }
     }
     cluster_sync();     // the peers' shared memory must outlive rank 0's reads
+}
+
+
+// =============================================================================================
+// Exchange form of the update, for a factor whose rows are spread over ranks (the sharded mode) or too tall for
+// shared memory (sparse tensors).  Phase A (cluster kernel above with `ex`, or solve_exchange_kernel for tall
+// factors) writes Unew = M P and ONE small record  ex = [colstat (R) | Unew^T Unew (R x R) | <Unew, M>];  the
+// ranks all-gather their records (one collective instead of three all-reduces);  cp_finish_kernel then forms,
+// in rank order,  lambda,  G_n = (sum_w Unew_w^T Unew_w) ./ (lambda lambda^T),  <P,X>,  the fit, and divides the
+// local rows by lambda -- a pass that is skipped altogether when every lambda is 1 (the usual case after the
+// first sweep, cp.py:152-153).
+// =============================================================================================
+constexpr int SXT = 256, SXROWS = 64;
+
+template <int TT>
+__global__ void __launch_bounds__(SXT) solve_exchange_kernel(const double *__restrict__ M, const double *__restrict__ P,
+                                                             long long rows, int R, int first_iter, double *Unew,
+                                                             double *ex, double *partials, unsigned int *counter) {
+    // 16 x 16 threads; thread (ty, tx) owns Unew[ty + 16a][tx + 16b] of a 64-row tile (a < 4) and, for the Gram,
+    // G[ty + 16a'][tx + 16b] (a', b < TT)
+    extern __shared__ double sxm[];
+    constexpr int PL = 16 * TT + 1;
+    double *Ps = sxm;                                  // [R][PL]
+    double *Ms = Ps + SKT_MAX_RANK * PL;               // [SXROWS][R + 1]
+    double *Us = Ms + SXROWS * (SKT_MAX_RANK + 1);     // [SXROWS][PL]
+    double *cs = Us + SXROWS * PL;                     // [16][16 * TT]
+    __shared__ double red[SXT / 32];
+    const int ML = R + 1;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int nblk = gridDim.x;
+    for (int e = tid; e < R * 16 * TT; e += SXT) {
+        const int k = e / (16 * TT), c = e % (16 * TT);
+        Ps[k * PL + c] = (c < R) ? P[k * R + c] : 0.0;
+    }
+    double stat[TT], gacc[TT][TT], ip = 0.0;
+#pragma unroll
+    for (int b = 0; b < TT; ++b) {
+        stat[b] = first_iter ? 0.0 : -DBL_MAX;
+#pragma unroll
+        for (int a = 0; a < TT; ++a) gacc[a][b] = 0.0;
+    }
+    __syncthreads();
+    const long long ntile = (rows + SXROWS - 1) / SXROWS;
+    for (long long tile = blockIdx.x; tile < ntile; tile += nblk) {
+        const long long r0 = tile * SXROWS;
+        const int nr = (int)min((long long)SXROWS, rows - r0);
+        for (int e = tid; e < SXROWS * R; e += SXT) {
+            const int i = e / R, c = e % R;
+            Ms[i * ML + c] = (i < nr) ? M[(r0 + i) * R + c] : 0.0;
+        }
+        __syncthreads();
+        double acc[4][TT];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < TT; ++b) acc[a][b] = 0.0;
+        for (int k = 0; k < R; ++k) {
+            double m[4], pv[TT];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) m[a] = Ms[(ty + 16 * a) * ML + k];
+#pragma unroll
+            for (int b = 0; b < TT; ++b) pv[b] = Ps[k * PL + tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < TT; ++b) acc[a][b] += m[a] * pv[b];
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int i = ty + 16 * a;
+#pragma unroll
+            for (int b = 0; b < TT; ++b) {
+                const int c = tx + 16 * b;
+                const bool ok = (i < nr) && (c < R);
+                const double v = ok ? acc[a][b] : 0.0;
+                Us[i * PL + c] = v;
+                if (ok) {
+                    Unew[(r0 + i) * R + c] = v;
+                    ip += v * Ms[i * ML + c];
+                    if (first_iter) stat[b] += v * v;
+                    else stat[b] = fmax(stat[b], v);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = 0; i < nr; ++i) {
+            double ua[TT], ub[TT];
+#pragma unroll
+            for (int a = 0; a < TT; ++a) ua[a] = Us[i * PL + ty + 16 * a];
+#pragma unroll
+            for (int b = 0; b < TT; ++b) ub[b] = Us[i * PL + tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < TT; ++a)
+#pragma unroll
+                for (int b = 0; b < TT; ++b) gacc[a][b] += ua[a] * ub[b];
+        }
+        __syncthreads();
+    }
+    // per-CTA record: [colstat | Gram | ip], column statistics combined over the 16 row groups in a fixed order
+#pragma unroll
+    for (int b = 0; b < TT; ++b) cs[ty * 16 * TT + tx + 16 * b] = stat[b];
+    __syncthreads();
+    const int REC = R + R * R + 1;
+    double *mine = partials + (size_t)blockIdx.x * REC;
+    if (tid < R) {
+        double sacc = first_iter ? 0.0 : -DBL_MAX;
+        for (int y = 0; y < 16; ++y) {
+            const double v = cs[y * 16 * TT + tid];
+            sacc = first_iter ? sacc + v : fmax(sacc, v);
+        }
+        mine[tid] = sacc;
+    }
+#pragma unroll
+    for (int a = 0; a < TT; ++a)
+#pragma unroll
+        for (int b = 0; b < TT; ++b) {
+            const int ra = ty + 16 * a, cb = tx + 16 * b;
+            if (ra < R && cb < R) mine[R + ra * R + cb] = gacc[a][b];
+        }
+    ip = warp_sum(ip);
+    if ((tid & 31) == 0) red[tid >> 5] = ip;
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < SXT / 32; ++w) sum += red[w];
+        mine[R + R * R] = sum;
+    }
+    if (last_block_ticket(counter, nblk)) {
+        for (int e = tid; e < REC; e += SXT) {
+            const bool is_stat = e < R;
+            double sacc = (is_stat && !first_iter) ? -DBL_MAX : 0.0;
+            for (int b = 0; b < nblk; ++b) {
+                const double v = partials[(size_t)b * REC + e];
+                sacc = (is_stat && !first_iter) ? fmax(sacc, v) : sacc + v;
+            }
+            ex[e] = sacc;
+        }
+    }
+}
+
+// Phase B.  ex_all: `world` records of R + R*R + 1 doubles (rank order).  Every CTA rebuilds lambda (cheap) and
+// divides its share of the local rows when some lambda differs from 1; CTA 0 writes lambda, G_mode, <P,X>, the fit.
+__global__ void __launch_bounds__(256) cp_finish_kernel(const double *__restrict__ ex_all, int world, int first_iter,
+                                                        long long rows, int R, int ndim, int mode, double *U, double *lambda,
+                                                        double *G, double *ip_out, const double *__restrict__ normX2,
+                                                        double *fit) {
+    __shared__ double lam[SKT_MAX_RANK];
+    __shared__ double red[8];
+    __shared__ int need_div;
+    const int tid = threadIdx.x;
+    const int REC = R + R * R + 1;
+    if (tid == 0) need_div = 0;
+    __syncthreads();
+    if (tid < R) {
+        double sacc = first_iter ? 0.0 : -DBL_MAX;
+        for (int w = 0; w < world; ++w) {
+            const double v = ex_all[(size_t)w * REC + tid];
+            sacc = first_iter ? sacc + v : fmax(sacc, v);
+        }
+        const double l = first_iter ? sqrt(sacc) : (sacc < 1.0 ? 1.0 : sacc);   // cp.py:150 / cp.py:152-153
+        lam[tid] = l;
+        if (l != 1.0) need_div = 1;
+        if (blockIdx.x == 0) lambda[tid] = l;
+    }
+    __syncthreads();
+    if (need_div) {
+        const long long n = rows * R;
+        for (long long e = blockIdx.x * 256LL + tid; e < n; e += (long long)gridDim.x * 256) U[e] = U[e] / lam[e % R];
+    }
+    if (blockIdx.x != 0) return;
+    double *Gn = G + (size_t)mode * R * R;
+    double sacc = 0.0;
+    for (int e = tid; e < R * R; e += 256) {
+        const int a = e / R, b = e - a * R;
+        double g = 0.0;
+        for (int w = 0; w < world; ++w) g += ex_all[(size_t)w * REC + R + e];
+        g = g / (lam[a] * lam[b]);
+        Gn[e] = g;
+        if (fit) {
+            double y = lam[a] * lam[b] * g;
+            for (int k = 0; k < ndim; ++k)
+                if (k != mode) y *= G[(size_t)k * R * R + e];
+            sacc += y;
+        }
+    }
+    double ip = 0.0;
+    if (tid == 0 && (ip_out || fit)) {
+        for (int w = 0; w < world; ++w) ip += ex_all[(size_t)w * REC + R + R * R];
+        if (ip_out) ip_out[0] = ip;
+    }
+    if (fit) {
+        sacc = warp_sum(sacc);
+        if ((tid & 31) == 0) red[tid >> 5] = sacc;
+        __syncthreads();
+        if (tid == 0) {
+            double normP2 = 0.0;
+            for (int w = 0; w < 8; ++w) normP2 += red[w];
+            const double nx2 = normX2[0];
+            fit[0] = 1.0 - (nx2 + normP2 - 2.0 * ip) / nx2;
+            fit[1] = normP2;
+        }
+    }
 }
 
 }  // namespace
@@ -541,8 +750,80 @@ extern "C" int skt_cp_update_cluster(const double *M_d, const double *P_d, int64
     }
     ClusterParams p;
     p.M = M_d; p.P = P_d; p.G = G_d; p.U = U_d; p.lambda = lambda_d; p.ip = ip_d; p.normX2 = normX2_d; p.fit = fit_d;
-    p.rows = rows; p.R = rank; p.ndim = ndim; p.mode = mode; p.first_iter = first_iter;
+    p.rows = rows; p.R = rank; p.ndim = ndim; p.mode = mode; p.first_iter = first_iter; p.ex = nullptr;
     cp_update_cluster_kernel<<<CL, CTH, smem, (cudaStream_t)stream>>>(p);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" size_t skt_cp_exchange_record(int rank) { return (size_t)rank + (size_t)rank * rank + 1; }
+
+extern "C" size_t skt_cp_update_exchange_workspace(int64_t rows, int rank) {
+    const long long ntile = (rows + SXROWS - 1) / SXROWS;
+    const long long nb = std::max<long long>(1, std::min<long long>(ntile, 2LL * sm_count()));
+    return 256 + align_up((size_t)nb * skt_cp_exchange_record(rank) * sizeof(double), 256);
+}
+
+extern "C" int skt_cp_update_exchange(const double *M_d, const double *P_d, int64_t rows, int rank, int first_iter,
+                                      double *Unew_d, double *ex_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    SKT_REQUIRE(P_d && ex_d && rows >= 0 && ((M_d && Unew_d) || rows == 0), SKT_EINVAL, "NULL argument or negative rows");
+    SKT_REQUIRE(rank >= 1 && rank <= SKT_MAX_RANK, SKT_EUNSUPPORTED, "rank %d outside [1, %d]", rank, SKT_MAX_RANK);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows > 0 && skt_cp_update_cluster_fits(rows, rank)) {      // small slab: the cluster kernel in phase-A mode
+        const ClusterLayout L = cluster_layout(rows, rank);
+        const size_t smem = L.total * sizeof(double);
+        static bool configured = false;
+        if (!configured) {
+            SKT_CUDA(cudaFuncSetAttribute(cp_update_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin_bytes()));
+            configured = true;
+        }
+        ClusterParams p;
+        p.M = M_d; p.P = P_d; p.G = nullptr; p.U = Unew_d; p.lambda = nullptr; p.ip = nullptr; p.normX2 = nullptr; p.fit = nullptr;
+        p.rows = rows; p.R = rank; p.ndim = 1; p.mode = 0; p.first_iter = first_iter; p.ex = ex_d;
+        cp_update_cluster_kernel<<<CL, CTH, smem, st>>>(p);
+        SKT_LAUNCH_CHECK();
+        return SKT_OK;
+    }
+    const size_t need = skt_cp_update_exchange_workspace(rows, rank);
+    SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    unsigned int *counter = (unsigned int *)ws_d;
+    double *partials = (double *)((char *)ws_d + 256);
+    SKT_CUDA(cudaMemsetAsync(counter, 0, 256, st));
+    const long long ntile = (rows + SXROWS - 1) / SXROWS;
+    const int nb = (int)std::max<long long>(1, std::min<long long>(ntile, 2LL * sm_count()));
+    const int tt = (rank + 15) / 16;
+    const size_t smem = (size_t)(SKT_MAX_RANK * (16 * tt + 1) + SXROWS * (SKT_MAX_RANK + 1) + SXROWS * (16 * tt + 1) + 16 * 16 * tt) * sizeof(double);
+#define SX(TT_)                                                                                                      \
+    do {                                                                                                             \
+        static bool cfg = false;                                                                                     \
+        if (!cfg) {                                                                                                  \
+            SKT_CUDA(cudaFuncSetAttribute(solve_exchange_kernel<TT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            cfg = true;                                                                                              \
+        }                                                                                                            \
+        solve_exchange_kernel<TT_><<<nb, SXT, smem, st>>>(M_d, P_d, rows, rank, first_iter, Unew_d, ex_d, partials, counter); \
+    } while (0)
+    switch (tt) {
+        case 1: SX(1); break;
+        case 2: SX(2); break;
+        case 3: SX(3); break;
+        default: SX(4); break;
+    }
+#undef SX
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+extern "C" int skt_cp_update_finish(const double *ex_all_d, int world, int first_iter, int64_t rows, int rank, int ndim,
+                                    int mode, double *U_d, double *lambda_d, double *G_d, double *ip_d,
+                                    const double *normX2_d, double *fit_d, skt_stream stream) {
+    SKT_REQUIRE(ex_all_d && lambda_d && G_d && world >= 1 && rows >= 0 && (U_d || rows == 0), SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(rank >= 1 && rank <= SKT_MAX_RANK, SKT_EUNSUPPORTED, "rank %d outside [1, %d]", rank, SKT_MAX_RANK);
+    SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= 0 && mode < ndim, SKT_EINVAL, "bad ndim/mode");
+    SKT_REQUIRE(fit_d == nullptr || normX2_d != nullptr, SKT_EINVAL, "the fit needs normX2_d");
+    const long long n = (long long)rows * rank;
+    const int nb = (int)std::max<long long>(1, std::min<long long>((n + 256 * 8 - 1) / (256 * 8), 4LL * sm_count()));
+    cp_finish_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(ex_all_d, world, first_iter, rows, rank, ndim, mode, U_d, lambda_d,
+                                                         G_d, ip_d, normX2_d, fit_d);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
 }

@@ -232,6 +232,28 @@ def cp_update_cluster(M, P, G, mode, first_iter, U, lam, ip=None, normX2=None, f
                                          dev.ptr(fit), dev.stream_ptr()))
 
 
+def exchange_record(rank):
+    return int(_lib.load().skt_cp_exchange_record(int(rank)))
+
+
+def cp_update_exchange(M, P, first_iter, Unew, ex):
+    """Phase A of the exchange-form update: ``Unew = M P`` and the record ``[colstat | Unew^T Unew | <Unew, M>]``."""
+    lib = _lib.load()
+    rows, R = M.shape
+    ws, wsz = dev.workspace('pass').get(lib.skt_cp_update_exchange_workspace(rows, R))
+    _lib.check(lib.skt_cp_update_exchange(dev.ptr(M), dev.ptr(P), rows, R, 1 if first_iter else 0, dev.ptr(Unew),
+                                          dev.ptr(ex), ws, wsz, dev.stream_ptr()))
+
+
+def cp_update_finish(ex_all, world, first_iter, U, lam, G, mode, ip=None, normX2=None, fit=None):
+    """Phase B: lambda, ``G[mode]``, ``<P,X>``, fit from the gathered records; divides ``U`` by lambda if needed."""
+    lib = _lib.load()
+    rows, R = U.shape
+    _lib.check(lib.skt_cp_update_finish(dev.ptr(ex_all), int(world), 1 if first_iter else 0, rows, R, int(G.shape[0]),
+                                        mode, dev.ptr(U), dev.ptr(lam), dev.ptr(G), dev.ptr(ip), dev.ptr(normX2),
+                                        dev.ptr(fit), dev.stream_ptr()))
+
+
 def set_reserved_sms(n):
     return int(_lib.load().skt_set_reserved_sms(int(n)))
 

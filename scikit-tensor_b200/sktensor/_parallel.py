@@ -167,6 +167,12 @@ class CudaBackend(object):
     def update_cluster(self, M, P, G, n, first, U, lam, ip, normX2, fit):
         return self.K.cp_update_cluster(M, P, G, n, first, U, lam, ip=ip, normX2=normX2, fit=fit)
 
+    # exchange-form update (sharded / tall factors): one record per rank, one collective, one finishing kernel
+    def exchange_record(self, R): return self.K.exchange_record(R)
+    def update_exchange(self, M, P, first, Unew, ex): return self.K.cp_update_exchange(M, P, first, Unew, ex)
+    def update_finish(self, ex_all, world, first, U, lam, G, n, ip, normX2, fit):
+        return self.K.cp_update_finish(ex_all, world, first, U, lam, G, n, ip=ip, normX2=normX2, fit=fit)
+
     def update_fused_fits(self, rows, R): return self.K.cp_update_fused_fits(rows, R)
     def update_fused(self, M, G, n, first, U, lam, info, ip, normX2, fit):
         return self.K.cp_update_fused(M, G, n, first, U, lam, info, ip=ip, normX2=normX2, fit=fit)
@@ -206,6 +212,17 @@ class _Comm(object):
     def allreduce_max(self, x):
         if self.active:
             self.dist.all_reduce(x, op=self.dist.ReduceOp.MAX)
+
+    def allgather_records(self, rec, out):
+        """``out[w] = rec`` of rank ``w`` (equal-sized records); a copy on a single rank."""
+        if not self.active:
+            out[0].copy_(rec)
+            return
+        try:
+            self.dist.all_gather_into_tensor(out.view(-1), rec)
+        except Exception:           # backends without the flat variant (older gloo)
+            parts = [out[w] for w in range(self.world)]
+            self.dist.all_gather(parts, rec)
 
     def allgather_rows(self, local, offsets, backend):
         """Concatenate the ranks' row blocks (sizes from ``offsets``) into one host array."""
@@ -306,6 +323,13 @@ class CpAlsEngine(object):
         self.Pn = [be.empty((R, R)) if self.cluster[m] else None for m in range(N)]
         self._pinv_pending = [None] * N
 
+        # ---- every other mode (sharded, or too tall for shared memory) takes the exchange form when available
+        self.exchange = hasattr(be, 'update_exchange') and os.environ.get('SKT_NO_EXCHANGE_UPDATE', '0') != '1'
+        if self.exchange:
+            rec = be.exchange_record(R)
+            self.ex = be.zeros((rec,))
+            self.ex_all = be.zeros((comm.world if comm.active else 1, rec))
+
         # ---- dimension tree (dense, N >= 3): two passes over X per sweep instead of N.  Modes [0, s) are
         # served by T_A = X contracted with U_s..U_{N-1}; modes [s, N) by T_B = X contracted with
         # U_0..U_{s-1}.  A one-mode group needs no second stage: its partial tensor IS the MTTKRP.
@@ -401,6 +425,18 @@ class CpAlsEngine(object):
                 fit_done = fit_done or last
                 continue
             be.hadamard_pinv(self.G, n, self.P, self.info[n:n + 1])
+            if self.exchange:
+                sharded = comm.active and n == self.s
+                be.update_exchange(M, self.P, first_iter, self.Ud[n], self.ex)
+                if sharded:
+                    comm.allgather_records(self.ex, self.ex_all)
+                else:
+                    self.ex_all[0].copy_(self.ex)
+                be.update_finish(self.ex_all, comm.world if sharded else 1, first_iter, self.Ud[n], self.lam, self.G, n,
+                                 self.ip if last else None, self.normX2 if last else None,
+                                 self.fitout if last else None)
+                fit_done = fit_done or last
+                continue
             be.solve_stats(M, self.P, first_iter, self.Ud[n], self.colstat)
             if comm.active and n == self.s:
                 if first_iter:

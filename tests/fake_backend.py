@@ -145,3 +145,35 @@ class NumpyBackend(object):
         self.normalise_gram(U, colstat, first, lam, G[n], M if ip is not None else None, ip)
         if fit is not None:
             self.cp_fit(G, lam, ip, normX2, fit)
+
+    # exchange-form update (cpals_fused.cu): record [colstat | Unew^T Unew | <Unew, M>], finish in rank order
+    def exchange_record(self, R):
+        return R + R * R + 1
+
+    def update_exchange(self, M, P, first, Unew, ex):
+        u = M.numpy().dot(P.numpy())
+        Unew.copy_(torch.from_numpy(u))
+        R = P.shape[0]
+        if u.shape[0] == 0:
+            stat = np.zeros(R) if first else np.full(R, -np.finfo(float).max)
+        else:
+            stat = (u ** 2).sum(axis=0) if first else u.max(axis=0)
+        rec = np.concatenate([stat, u.T.dot(u).ravel(), [float((u * M.numpy()).sum())]])
+        ex.copy_(torch.from_numpy(rec))
+
+    def update_finish(self, ex_all, world, first, U, lam, G, n, ip, normX2, fit):
+        R = G.shape[1]
+        e = ex_all.numpy()[:world]
+        stat = e[:, :R].sum(axis=0) if first else e[:, :R].max(axis=0)
+        l = np.sqrt(stat) if first else np.where(stat < 1, 1.0, stat)
+        lam.copy_(torch.from_numpy(l))
+        if U.shape[0]:
+            U.copy_(torch.from_numpy(U.numpy() / l))
+        g = e[:, R:R + R * R].sum(axis=0).reshape(R, R) / np.outer(l, l)
+        G[n].copy_(torch.from_numpy(g))
+        tot = float(e[:, R + R * R].sum())
+        if ip is not None:
+            ip[0] = tot
+        if fit is not None:
+            ipt = torch.tensor([tot], dtype=torch.float64)
+            self.cp_fit(G, lam, ipt, normX2, fit)

@@ -476,3 +476,57 @@ def test_cluster_fused_and_streaming_updates_agree():
         os.environ['SKT_NO_CLUSTER_UPDATE'] = os.environ['SKT_NO_FUSED_UPDATE'] = '0'
         assert res[0][1] == res[1][1] == res[2][1]
         assert abs(res[0][0] - res[1][0]) < 1e-10 and abs(res[0][0] - res[2][0]) < 1e-10
+
+
+@pytest.mark.parametrize('rows,R,N,world', [(512, 32, 3, 1), (100003, 16, 3, 1), (3000, 64, 4, 3), (97, 5, 3, 2),
+                                            (40000, 33, 3, 4), (6, 3, 3, 8)])
+def test_exchange_update_matches_reference_arithmetic(K, dev, rows, R, N, world):
+    """skt_cp_update_exchange (cluster or streaming phase A) per row slab + skt_cp_update_finish on the gathered
+    records == cp.py:147-159 on the whole factor; slabs emulate the ranks of a sharded mode (some may be empty)."""
+    rng = np.random.RandomState(rows + 7 * R + world)
+    F = [rng.rand(30 + 2 * m, R) for m in range(N)]
+    G = np.stack([f.T.dot(f) for f in F])
+    M = rng.rand(rows, R) * 2 - 0.6
+    normX2 = 4321.0
+    cuts = np.linspace(0, rows, world + 1).astype(int)
+    if world == 8:
+        cuts = np.array([0, 1, 1, 3, 3, 4, 6, 6, 6])          # empty slabs
+    mode = N - 1
+    for first in (True, False):
+        Gd = dev.to_device(G)
+        P, _ = K.hadamard_pinv(Gd, mode)
+        rec = K.exchange_record(R)
+        ex_all = dev.zeros((world, rec))
+        Us = []
+        for w in range(world):
+            Mw = dev.to_device(M[cuts[w]:cuts[w + 1]])
+            Uw = dev.empty(Mw.shape)
+            K.cp_update_exchange(Mw, P, first, Uw, ex_all[w])
+            Us.append(Uw)
+        lam, ip, fit = dev.empty((R,)), dev.zeros((1,)), dev.zeros((2,))
+        for w in range(world):
+            Gw = Gd if w == 0 else dev.to_device(G)
+            K.cp_update_finish(ex_all, world, first, Us[w], lam, Gw, mode, ip=ip, normX2=dev.to_device(np.array([normX2])), fit=fit)
+        Y = np.ones((R, R))
+        for m in range(N):
+            if m != mode:
+                Y = Y * G[m]
+        Unew = M.dot(pinv(Y))
+        l = np.sqrt((Unew ** 2).sum(0)) if first else np.where(Unew.max(0) < 1, 1.0, Unew.max(0))
+        Uref = Unew / l
+        tol = 1e-12 * max(1e2, np.linalg.cond(Y))
+        got = np.concatenate([dev.to_host(u) for u in Us], axis=0)
+        assert relerr(got, Uref) < tol, (rows, R, world, first)
+        assert relerr(dev.to_host(lam), l) < tol
+        Gn = dev.to_host(Gd)
+        assert relerr(Gn[mode], Uref.T.dot(Uref)) < tol
+        ipref = (l * Uref * M).sum()
+        assert abs(dev.to_host(ip)[0] - ipref) < tol * abs(ipref)
+        G2 = G.copy()
+        G2[mode] = Uref.T.dot(Uref)
+        coef = np.outer(l, l)
+        for m in range(N):
+            coef = coef * G2[m]
+        f = dev.to_host(fit)
+        assert abs(f[1] - coef.sum()) < tol * coef.sum()
+        assert abs(f[0] - (1.0 - (normX2 + coef.sum() - 2 * ipref) / normX2)) < tol * 10 * max(1.0, coef.sum() / normX2)
