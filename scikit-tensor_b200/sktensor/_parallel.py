@@ -320,7 +320,6 @@ class CpAlsEngine(object):
         # of mode n is still streaming the tensor (Y_n only needs the Grams of the other modes)
         use_cluster = use_fused and hasattr(be, 'update_cluster') and os.environ.get('SKT_NO_CLUSTER_UPDATE', '0') != '1'
         self.cluster = [bool(use_cluster and self.fused[m] and be.update_cluster_fits(self.lshape[m], R)) for m in range(N)]
-        self.Pn = [be.empty((R, R)) if self.cluster[m] else None for m in range(N)]
         self._pinv_pending = [None] * N
 
         # ---- every other mode (sharded, or too tall for shared memory) takes the exchange form when available
@@ -329,6 +328,10 @@ class CpAlsEngine(object):
             rec = be.exchange_record(R)
             self.ex = be.zeros((rec,))
             self.ex_all = be.zeros((comm.world if comm.active else 1, rec))
+        # modes whose pinv runs on the side stream: every mode that consumes a ready-made P
+        has_async = hasattr(be, 'pinv_async') and os.environ.get('SKT_NO_CLUSTER_UPDATE', '0') != '1'
+        self.apinv = [bool(has_async and (self.cluster[m] or (self.exchange and not self.fused[m]))) for m in range(N)]
+        self.Pn = [be.empty((R, R)) if self.apinv[m] else None for m in range(N)]
 
         # ---- dimension tree (dense, N >= 3): two passes over X per sweep instead of N.  Modes [0, s) are
         # served by T_A = X contracted with U_s..U_{N-1}; modes [s, N) by T_B = X contracted with
@@ -398,57 +401,58 @@ class CpAlsEngine(object):
     def sweep(self, first_iter, want_fit=True):
         be, comm, N = self.be, self.comm, self.N
         fit_done = False
+
+        def start_pinv(m):
+            # pinv(Y_m) only needs the Grams of the other modes: run it on the side stream beside the MTTKRP of mode m
+            if self.apinv[m] and self._pinv_pending[m] is None:
+                self._pinv_pending[m] = be.pinv_async(self.G, m, self.Pn[m], self.info[m:m + 1])
+
         for n in range(N):
-            if self.cluster[n] and self._pinv_pending[n] is None:      # first mode of the first sweep
-                self._pinv_pending[n] = be.pinv_async(self.G, n, self.Pn[n], self.info[n:n + 1])
+            start_pinv(n)                                   # (only the first mode of the first sweep starts here)
             if n == 0 and self._m0_ready:
                 M, self._m0_ready = self.M[0], False
             else:
                 M = self.mttkrp(n)
             last = (n == N - 1) and want_fit
-            if self.cluster[n]:
+            fit_args = (self.ip if last else None, self.normX2 if last else None, self.fitout if last else None)
+            if self.apinv[n]:
                 be.wait_pinv(self._pinv_pending[n])
                 self._pinv_pending[n] = None
-                be.update_cluster(M, self.Pn[n], self.G, n, first_iter, self.Ud[n], self.lam,
-                                  self.ip if last else None, self.normX2 if last else None,
-                                  self.fitout if last else None)
+                P = self.Pn[n]
+            elif self.cluster[n] or not self.fused[n]:
+                be.hadamard_pinv(self.G, n, self.P, self.info[n:n + 1])
+                P = self.P
+            if self.cluster[n]:
+                # small factor, replicated solve: one 8-CTA cluster does solve + normalise + Gram (+ <P,X>, fit)
+                be.update_cluster(M, P, self.G, n, first_iter, self.Ud[n], self.lam, *fit_args)
                 fit_done = fit_done or last
-                nxt = (n + 1) % N          # its Grams are final now: start the next mode's pinv beside the next MTTKRP
-                if self.cluster[nxt]:
-                    self._pinv_pending[nxt] = be.pinv_async(self.G, nxt, self.Pn[nxt], self.info[nxt:nxt + 1])
-                continue
-            if self.fused[n]:
-                # small factor, replicated solve: pinv + solve + normalise + Gram (+ <P,X>, fit) in one launch
-                be.update_fused(M, self.G, n, first_iter, self.Ud[n], self.lam, self.info[n:n + 1],
-                                self.ip if last else None, self.normX2 if last else None,
-                                self.fitout if last else None)
+            elif self.fused[n]:
+                # the same in one CTA, pinv included (no side stream)
+                be.update_fused(M, self.G, n, first_iter, self.Ud[n], self.lam, self.info[n:n + 1], *fit_args)
                 fit_done = fit_done or last
-                continue
-            be.hadamard_pinv(self.G, n, self.P, self.info[n:n + 1])
-            if self.exchange:
+            elif self.exchange:
+                # sharded mode / tall factor: one record per rank, one all-gather, one finishing kernel
                 sharded = comm.active and n == self.s
-                be.update_exchange(M, self.P, first_iter, self.Ud[n], self.ex)
+                be.update_exchange(M, P, first_iter, self.Ud[n], self.ex if sharded else self.ex_all[0])
                 if sharded:
                     comm.allgather_records(self.ex, self.ex_all)
-                else:
-                    self.ex_all[0].copy_(self.ex)
                 be.update_finish(self.ex_all, comm.world if sharded else 1, first_iter, self.Ud[n], self.lam, self.G, n,
-                                 self.ip if last else None, self.normX2 if last else None,
-                                 self.fitout if last else None)
+                                 *fit_args)
                 fit_done = fit_done or last
-                continue
-            be.solve_stats(M, self.P, first_iter, self.Ud[n], self.colstat)
-            if comm.active and n == self.s:
-                if first_iter:
-                    comm.allreduce_sum(self.colstat)
-                else:
-                    comm.allreduce_max(self.colstat)
-            be.normalise_gram(self.Ud[n], self.colstat, first_iter, self.lam, self.G[n],
-                              M if last else None, self.ip if last else None)
-            if comm.active and n == self.s:
-                comm.allreduce_sum(self.G[n])
-                if last:
-                    comm.allreduce_sum(self.ip)
+            else:
+                be.solve_stats(M, P, first_iter, self.Ud[n], self.colstat)
+                if comm.active and n == self.s:
+                    if first_iter:
+                        comm.allreduce_sum(self.colstat)
+                    else:
+                        comm.allreduce_max(self.colstat)
+                be.normalise_gram(self.Ud[n], self.colstat, first_iter, self.lam, self.G[n],
+                                  M if last else None, self.ip if last else None)
+                if comm.active and n == self.s:
+                    comm.allreduce_sum(self.G[n])
+                    if last:
+                        comm.allreduce_sum(self.ip)
+            start_pinv((n + 1) % N)                         # the Grams it needs are final now
         if want_fit and not fit_done:
             be.cp_fit(self.G, self.lam, self.ip, self.normX2, self.fitout)
 
