@@ -437,13 +437,11 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                 if (!MMAJOR) {
                     tma_load_4d(sb, &tmX, &full[stage], k0, tt * bt, it * bi, lt * bl);
                 } else {
-                    // row group j holds 16 consecutive i of one l: tile = (bl l) x (bi i), bi a multiple of 16 --
-                    // the wider the tile is in i (the contiguous axis), the longer the DRAM bursts per k
-                    const int lg_nsub = p.lg_bi - 4;
-#pragma unroll
-                    for (int j = 0; j < RG; ++j)
-                        tma_load_3d(sb + j * (TK * 128), &tmX, &full[stage], it * bi + 16 * (j & ((1 << lg_nsub) - 1)),
-                                    lt * bl + (j >> lg_nsub), k0);
+                    // tile = (bi i) x (bl l): one box (16 i, TK k, bl l) per 16-i sub-tile s -- row group rg = s*bl + l_off
+                    // holds 16 consecutive i of one l, its TK k-rows of 128 bytes laid out exactly as the consumers expect
+                    const int nsub = bi >> 4;
+                    for (int sx = 0; sx < nsub; ++sx)
+                        tma_load_3d(sb + sx * bl * (TK * 128), &tmX, &full[stage], it * bi + 16 * sx, k0, lt * bl);
                 }
             }
             if (++st.ks == p.nk) {
@@ -462,7 +460,16 @@ __global__ void __launch_bounds__(TTHREADS, 1)
     const int pg = MMAJOR ? g : (2 * (g & 3) + (g >> 2));  // tile row (within a group of 8) owned by fragment row g
     const int nbw = (C::CG == 1) ? (NB < 4 ? NB : 4) : min(4, NB - 4 * cg);  // 8-column blocks this warp computes
 
+    // tile row q -> (l, i, t).  K-major: t fastest, then i, then l.  M-major: row group rg = q >> 4 = s*bl + l_off
+    // (16-i sub-tile s, then l), row q & 15 = i within the sub-tile.
     auto decompose = [&](int q, int it, int lt, int tt, int &l, int &i, int &t) -> bool {
+        if (MMAJOR) {
+            const int rgq = q >> 4;
+            t = 0;
+            i = it * bi + 16 * (rgq >> p.lg_bl) + (q & 15);
+            l = lt * bl + (rgq & (bl - 1));
+            return (i < p.In) && (l < p.L);
+        }
         const int t_off = q & (bt - 1);
         const int i_off = (q >> p.lg_bt) & (bi - 1);
         const int l_off = q >> (p.lg_bt + p.lg_bi);
@@ -470,6 +477,11 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         i = it * bi + i_off;
         l = lt * bl + l_off;
         return (t < p.T) && (i < p.In) && (l < p.L);
+    };
+    // tile row that holds (l_off, i_off, t_off) -- the inverse of the above, used by the flush
+    auto rowof = [&](int l_off, int i_off, int t_off) -> int {
+        if (MMAJOR) return 16 * (((i_off >> 4) << p.lg_bl) + l_off) + (i_off & 15);
+        return (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
     };
 
     // acc: the running GEMM block of the current tile (registers).  The weighted sums over the tiles of a
@@ -625,7 +637,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                             double sum = 0.0;
                             for (int l_off = 0; l_off < bl; ++l_off)
                                 for (int t_off = 0; t_off < bt; ++t_off) {
-                                    const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
+                                    const int q = rowof(l_off, i_off, t_off);
                                     sum += Z[q * C::ZSTR + col];
                                 }
                             dst[(long long)i_off * p.ld + col] = sum;
@@ -640,7 +652,7 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                         double sum = 0.0;
                         for (int j = part * chunk; j < (part + 1) * chunk; ++j) {
                             const int l_off = j >> p.lg_bt, t_off = j & (bt - 1);
-                            const int q = (((l_off << p.lg_bi) + i_off) << p.lg_bt) + t_off;
+                            const int q = rowof(l_off, i_off, t_off);
                             sum += Z[q * C::ZSTR + col];
                         }
                         red[tid] = sum;
@@ -945,11 +957,11 @@ int make_tensor_map(const double *X, const DensePlan &pl, CUtensorMap &tm) {
         strides[2] = strides[1] * pl.In;
         box[0] = 16; box[1] = 1u << pl.lg_bt; box[2] = 1u << pl.lg_bi; box[3] = 1u << pl.lg_bl;
     } else {
-        rank = 3;
-        dims[0] = pl.In; dims[1] = pl.L; dims[2] = pl.Kc;
-        strides[0] = (cuuint64_t)pl.In * 8;
-        strides[1] = strides[0] * pl.L;
-        box[0] = 16; box[1] = 1; box[2] = TK;
+        rank = 3;                                       // (i, k, l): one box = 16 i x TK k x bl l
+        dims[0] = pl.In; dims[1] = pl.Kc; dims[2] = pl.L;
+        strides[0] = (cuuint64_t)pl.In * 8 * pl.L;       // k
+        strides[1] = (cuuint64_t)pl.In * 8;              // l
+        box[0] = 16; box[1] = TK; box[2] = 1u << pl.lg_bl;
     }
     const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<double *>(X), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
