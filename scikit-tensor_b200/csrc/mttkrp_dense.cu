@@ -705,14 +705,18 @@ __global__ void streamk_fixup_kernel(const double *__restrict__ slab, long long 
     const int b_first = (int)((((ta + 1) * grid) - 1) / ntiles);
     const int b_last = (int)((((tb + 1) * grid) - 1) / ntiles);
     if (b_first == b_last) return;                                         // written directly by its single owner
-    double sum = 0.0;
-    for (int b = b_first; b <= b_last; ++b) {
-        const long long t0 = (ntiles * (long long)b) / grid, t1 = (ntiles * (long long)(b + 1)) / grid;
-        const long long lo = t0 > ta ? t0 : ta, hi = t1 < tb + 1 ? t1 : tb + 1;
-        if (lo >= hi) continue;
-        const int slot = (lo == t0) ? 0 : 1;
-        sum += slab[(2LL * b + slot) * slab_stride + (long long)i_off * ld + col];
+    // grid <= ntiles: no CTA range is empty, so every b in [b_first, b_last] owns a piece of this row tile; only the
+    // first one can have started in an earlier row tile (slot 1 = "last segment of its range")
+    const long long t0_first = (ntiles * (long long)b_first) / grid;
+    const double *src = slab + (long long)i_off * ld + col;
+    double sum = src[(2LL * b_first + (t0_first >= ta ? 0 : 1)) * slab_stride];
+    int b = b_first + 1;
+    for (; b + 4 <= b_last + 1; b += 4) {            // independent loads, added in CTA order
+        const double v0 = src[(2LL * b) * slab_stride], v1 = src[(2LL * b + 2) * slab_stride];
+        const double v2 = src[(2LL * b + 4) * slab_stride], v3 = src[(2LL * b + 6) * slab_stride];
+        sum += v0; sum += v1; sum += v2; sum += v3;
     }
+    for (; b <= b_last; ++b) sum += src[(2LL * b) * slab_stride];
     M[((long long)it * bi + i_off) * ld + col] = sum;
 }
 
@@ -850,7 +854,10 @@ int make_plan_uncached(const int64_t *shape, int ndim, int rank, int mode, bool 
                                   (double)((L + bl - 1) / bl * bl);
             // prefer (slightly) boxes whose inner run is long: fewer DRAM page switches
             // K-major: long runs in t; M-major (TMA): 32 consecutive i per l measured best (sweep in profiles/r1_notes.md)
-            const int pref = pl.mmajor ? (tma ? std::abs(li - 5) : (lgbm - li)) : (lgbm - lt);
+            // K-major TMA tiles: 16 t x 16 i (x l) -- measured as fast as long t runs, and it keeps many output-row tiles
+            // (few CTAs share one under stream-K: short fix-up, one flush per CTA); the cp.async kernel keeps long t runs
+            const int kpref = tma ? (2 * std::abs(lt - 4) + std::abs(li - 4)) : (lgbm - lt);
+            const int pref = pl.mmajor ? (tma ? std::abs(li - 5) : (lgbm - li)) : kpref;
             const double score = padded * (1.0 + 1e-3 * pref + 1e-5 * ll);
             if (score < best) { best = score; bbt = lt; bbi = li; bbl = ll; }
         }
