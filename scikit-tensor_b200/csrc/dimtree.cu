@@ -54,17 +54,16 @@ __global__ void __launch_bounds__(256) kr_reduce_kernel(const __grid_constant__ 
         const double *tp = p.T + (w.space ? (i * p.Tt + j0) * p.R : (j0 * p.In + i) * p.R) + r;
         const double *wp = w.W + j0 * p.R + r;
         long long j = j0;
-        // 8 independent 8-byte loads of T per thread in flight (the weights hit L1/L2): the pass is latency-bound
-        for (; j + 8 <= j1; j += 8) {
-            double tv[8], wv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) tv[u] = __ldg(tp + u * stride);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) wv[u] = __ldg(wp + u * p.R);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) sum += tv[u] * wv[u];
-            tp += 8 * stride;
-            wp += 8 * p.R;
+        // 4 independent loads of T per thread in flight (8 measured slower: 22.6 vs 15.5 us at 512 x 512 x 32)
+        for (; j + 4 <= j1; j += 4) {
+            const double t0 = __ldg(tp), t1 = __ldg(tp + stride), t2 = __ldg(tp + 2 * stride), t3 = __ldg(tp + 3 * stride);
+            const double w0 = __ldg(wp), w1 = __ldg(wp + p.R), w2 = __ldg(wp + 2 * p.R), w3 = __ldg(wp + 3 * p.R);
+            sum += t0 * w0;
+            sum += t1 * w1;
+            sum += t2 * w2;
+            sum += t3 * w3;
+            tp += 4 * stride;
+            wp += 4 * p.R;
         }
         for (; j < j1; ++j) {
             sum += __ldg(tp) * __ldg(wp);
