@@ -200,6 +200,19 @@ SKT_API int skt_cp_update_exchange(const double *M_d, const double *P_d, int64_t
 SKT_API int skt_cp_update_finish(const double *ex_all_d, int world, int first_iter, int64_t rows, int rank, int ndim,
                          int mode, double *U_d, double *lambda_d, double *G_d, double *ip_d,
                          const double *normX2_d, double *fit_d, skt_stream stream);
+/* Fused reduce + update over NVLink peer memory.  Same as skt_cp_update_cluster / skt_cp_update_finish, but the
+ * operand that would have come out of an NCCL collective is read straight from the peers' HBM inside the kernel:
+ * Mparts_d / ex_parts_d is a DEVICE array of `nparts` pointers, entry w = rank w's buffer mapped into this process
+ * (symmetric memory; torch.distributed._symmetric_memory: handle.buffer_ptrs_dev).  The partial MTTKRPs (or exchange
+ * records) are added in rank order, so every rank gets bitwise the same factor.  The caller orders the ranks with a
+ * cross-rank barrier on the stream (handle.barrier()) before the call.                                          */
+SKT_API int skt_cp_update_cluster_parts(const double *const *Mparts_d, int nparts, const double *P_d, int64_t rows,
+                                int rank, int ndim, int mode, int first_iter, double *G_d, double *U_d,
+                                double *lambda_d, double *ip_d, const double *normX2_d, double *fit_d,
+                                skt_stream stream);
+SKT_API int skt_cp_update_finish_parts(const double *const *ex_parts_d, int world, int first_iter, int64_t rows, int rank,
+                               int ndim, int mode, double *U_d, double *lambda_d, double *G_d, double *ip_d,
+                               const double *normX2_d, double *fit_d, skt_stream stream);
 /* Leave `n` SMs out of the persistent grids (dense MTTKRP) so that a small kernel on another stream can run
  * beside them; returns the previous value.  0 restores the full chip.                                      */
 SKT_API int skt_set_reserved_sms(int n);

@@ -278,6 +278,11 @@ struct ClusterParams {
     long long rows;
     int R, ndim, mode, first_iter;
     double *ex;   // non-NULL: phase-A mode -- write Unew (not normalised) to U and [colstat | Unew^T Unew | <Unew,M>] to ex
+    // nparts > 1: M is the sum, in rank order, of the ranks' partial MTTKRPs, read straight from the peers' HBM over
+    // NVLink (symmetric memory: Mparts[w] is rank w's buffer mapped into this process) -- the all-reduce of the partial
+    // MTTKRP is fused into the staging loop of the update
+    const double *const *Mparts;
+    int nparts;
 };
 
 struct ClusterLayout {
@@ -331,6 +336,17 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
     };
 
     // ---- stage the slice of M and P (zero padded)
+    if (p.Mparts) {
+        for (int e = tid; e < per * R8; e += CTH) {
+            const int i = e / R8, c = e - i * R8;
+            double v = 0.0;
+            if (i < nr && c < R) {
+                const long long off = (long long)(r0 + i) * R + c;
+                for (int w = 0; w < p.nparts; ++w) v += p.Mparts[w][off];
+            }
+            Ms[i * LD + c] = v;
+        }
+    } else
     for (int e = tid; e < per * R8; e += CTH) {
         const int i = e / R8, c = e - i * R8;
         Ms[i * LD + c] = (i < nr && c < R) ? __ldg(p.M + (long long)(r0 + i) * R + c) : 0.0;
@@ -615,7 +631,13 @@ __global__ void __launch_bounds__(SXT) solve_exchange_kernel(const double *__res
 
 // Phase B.  ex_all: `world` records of R + R*R + 1 doubles (rank order).  Every CTA rebuilds lambda (cheap) and
 // divides its share of the local rows when some lambda differs from 1; CTA 0 writes lambda, G_mode, <P,X>, the fit.
-__global__ void __launch_bounds__(256) cp_finish_kernel(const double *__restrict__ ex_all, int world, int first_iter,
+// record w: ex_parts ? ex_parts[w] (rank w's record in symmetric memory, read over NVLink) : ex_all + w * REC
+__device__ __forceinline__ const double *finish_record(const double *ex_all, const double *const *ex_parts, int w, int REC) {
+    return ex_parts ? ex_parts[w] : ex_all + (size_t)w * REC;
+}
+
+__global__ void __launch_bounds__(256) cp_finish_kernel(const double *__restrict__ ex_all, const double *const *ex_parts,
+                                                        int world, int first_iter,
                                                         long long rows, int R, int ndim, int mode, double *U, double *lambda,
                                                         double *G, double *ip_out, const double *__restrict__ normX2,
                                                         double *fit) {
@@ -629,7 +651,7 @@ __global__ void __launch_bounds__(256) cp_finish_kernel(const double *__restrict
     if (tid < R) {
         double sacc = first_iter ? 0.0 : -DBL_MAX;
         for (int w = 0; w < world; ++w) {
-            const double v = ex_all[(size_t)w * REC + tid];
+            const double v = finish_record(ex_all, ex_parts, w, REC)[tid];
             sacc = first_iter ? sacc + v : fmax(sacc, v);
         }
         const double l = first_iter ? sqrt(sacc) : (sacc < 1.0 ? 1.0 : sacc);   // cp.py:150 / cp.py:152-153
@@ -648,7 +670,7 @@ __global__ void __launch_bounds__(256) cp_finish_kernel(const double *__restrict
     for (int e = tid; e < R * R; e += 256) {
         const int a = e / R, b = e - a * R;
         double g = 0.0;
-        for (int w = 0; w < world; ++w) g += ex_all[(size_t)w * REC + R + e];
+        for (int w = 0; w < world; ++w) g += finish_record(ex_all, ex_parts, w, REC)[R + e];
         g = g / (lam[a] * lam[b]);
         Gn[e] = g;
         if (fit) {
@@ -660,7 +682,7 @@ __global__ void __launch_bounds__(256) cp_finish_kernel(const double *__restrict
     }
     double ip = 0.0;
     if (tid == 0 && (ip_out || fit)) {
-        for (int w = 0; w < world; ++w) ip += ex_all[(size_t)w * REC + R + R * R];
+        for (int w = 0; w < world; ++w) ip += finish_record(ex_all, ex_parts, w, REC)[R + R * R];
         if (ip_out) ip_out[0] = ip;
     }
     if (fit) {
@@ -733,10 +755,10 @@ extern "C" int skt_cp_update_cluster_fits(int64_t rows, int rank) {
     return (L.total * sizeof(double) <= smem_optin_bytes()) ? 1 : 0;
 }
 
-extern "C" int skt_cp_update_cluster(const double *M_d, const double *P_d, int64_t rows, int rank, int ndim, int mode,
-                                     int first_iter, double *G_d, double *U_d, double *lambda_d, double *ip_d,
-                                     const double *normX2_d, double *fit_d, skt_stream stream) {
-    SKT_REQUIRE(M_d && P_d && G_d && U_d && lambda_d, SKT_EINVAL, "NULL argument");
+static int update_cluster_impl(const double *M_d, const double *const *Mparts_d, int nparts, const double *P_d,
+                               int64_t rows, int rank, int ndim, int mode, int first_iter, double *G_d, double *U_d,
+                               double *lambda_d, double *ip_d, const double *normX2_d, double *fit_d, skt_stream stream) {
+    SKT_REQUIRE((M_d || (Mparts_d && nparts >= 1)) && P_d && G_d && U_d && lambda_d, SKT_EINVAL, "NULL argument");
     SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= 0 && mode < ndim, SKT_EINVAL, "bad ndim/mode");
     SKT_REQUIRE(fit_d == nullptr || (ip_d != nullptr && normX2_d != nullptr), SKT_EINVAL, "the fit needs ip_d and normX2_d");
     SKT_REQUIRE(skt_cp_update_cluster_fits(rows, rank), SKT_EUNSUPPORTED,
@@ -750,7 +772,7 @@ extern "C" int skt_cp_update_cluster(const double *M_d, const double *P_d, int64
     }
     ClusterParams p;
     p.M = M_d; p.P = P_d; p.G = G_d; p.U = U_d; p.lambda = lambda_d; p.ip = ip_d; p.normX2 = normX2_d; p.fit = fit_d;
-    p.rows = rows; p.R = rank; p.ndim = ndim; p.mode = mode; p.first_iter = first_iter; p.ex = nullptr;
+    p.rows = rows; p.R = rank; p.ndim = ndim; p.mode = mode; p.first_iter = first_iter; p.ex = nullptr; p.Mparts = Mparts_d; p.nparts = nparts;
     cp_update_cluster_kernel<<<CL, CTH, smem, (cudaStream_t)stream>>>(p);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
@@ -779,7 +801,7 @@ extern "C" int skt_cp_update_exchange(const double *M_d, const double *P_d, int6
         }
         ClusterParams p;
         p.M = M_d; p.P = P_d; p.G = nullptr; p.U = Unew_d; p.lambda = nullptr; p.ip = nullptr; p.normX2 = nullptr; p.fit = nullptr;
-        p.rows = rows; p.R = rank; p.ndim = 1; p.mode = 0; p.first_iter = first_iter; p.ex = ex_d;
+        p.rows = rows; p.R = rank; p.ndim = 1; p.mode = 0; p.first_iter = first_iter; p.ex = ex_d; p.Mparts = nullptr; p.nparts = 1;
         cp_update_cluster_kernel<<<CL, CTH, smem, st>>>(p);
         SKT_LAUNCH_CHECK();
         return SKT_OK;
@@ -813,17 +835,48 @@ extern "C" int skt_cp_update_exchange(const double *M_d, const double *P_d, int6
     return SKT_OK;
 }
 
-extern "C" int skt_cp_update_finish(const double *ex_all_d, int world, int first_iter, int64_t rows, int rank, int ndim,
-                                    int mode, double *U_d, double *lambda_d, double *G_d, double *ip_d,
-                                    const double *normX2_d, double *fit_d, skt_stream stream) {
-    SKT_REQUIRE(ex_all_d && lambda_d && G_d && world >= 1 && rows >= 0 && (U_d || rows == 0), SKT_EINVAL, "NULL argument");
+static int update_finish_impl(const double *ex_all_d, const double *const *ex_parts_d, int world, int first_iter,
+                              int64_t rows, int rank, int ndim, int mode, double *U_d, double *lambda_d, double *G_d,
+                              double *ip_d, const double *normX2_d, double *fit_d, skt_stream stream) {
+    SKT_REQUIRE((ex_all_d || ex_parts_d) && lambda_d && G_d && world >= 1 && rows >= 0 && (U_d || rows == 0), SKT_EINVAL, "NULL argument");
     SKT_REQUIRE(rank >= 1 && rank <= SKT_MAX_RANK, SKT_EUNSUPPORTED, "rank %d outside [1, %d]", rank, SKT_MAX_RANK);
     SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= 0 && mode < ndim, SKT_EINVAL, "bad ndim/mode");
     SKT_REQUIRE(fit_d == nullptr || normX2_d != nullptr, SKT_EINVAL, "the fit needs normX2_d");
     const long long n = (long long)rows * rank;
     const int nb = (int)std::max<long long>(1, std::min<long long>((n + 256 * 8 - 1) / (256 * 8), 4LL * sm_count()));
-    cp_finish_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(ex_all_d, world, first_iter, rows, rank, ndim, mode, U_d, lambda_d,
+    cp_finish_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(ex_all_d, ex_parts_d, world, first_iter, rows, rank, ndim, mode, U_d, lambda_d,
                                                          G_d, ip_d, normX2_d, fit_d);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
+}
+
+extern "C" int skt_cp_update_cluster(const double *M_d, const double *P_d, int64_t rows, int rank, int ndim, int mode,
+                                     int first_iter, double *G_d, double *U_d, double *lambda_d, double *ip_d,
+                                     const double *normX2_d, double *fit_d, skt_stream stream) {
+    return update_cluster_impl(M_d, nullptr, 1, P_d, rows, rank, ndim, mode, first_iter, G_d, U_d, lambda_d, ip_d, normX2_d,
+                               fit_d, stream);
+}
+
+extern "C" int skt_cp_update_cluster_parts(const double *const *Mparts_d, int nparts, const double *P_d, int64_t rows,
+                                           int rank, int ndim, int mode, int first_iter, double *G_d, double *U_d,
+                                           double *lambda_d, double *ip_d, const double *normX2_d, double *fit_d,
+                                           skt_stream stream) {
+    SKT_REQUIRE(Mparts_d && nparts >= 1 && nparts <= 64, SKT_EINVAL, "bad partial-buffer list");
+    return update_cluster_impl(nullptr, Mparts_d, nparts, P_d, rows, rank, ndim, mode, first_iter, G_d, U_d, lambda_d, ip_d,
+                               normX2_d, fit_d, stream);
+}
+
+extern "C" int skt_cp_update_finish(const double *ex_all_d, int world, int first_iter, int64_t rows, int rank, int ndim,
+                                    int mode, double *U_d, double *lambda_d, double *G_d, double *ip_d,
+                                    const double *normX2_d, double *fit_d, skt_stream stream) {
+    return update_finish_impl(ex_all_d, nullptr, world, first_iter, rows, rank, ndim, mode, U_d, lambda_d, G_d, ip_d, normX2_d,
+                              fit_d, stream);
+}
+
+extern "C" int skt_cp_update_finish_parts(const double *const *ex_parts_d, int world, int first_iter, int64_t rows, int rank,
+                                          int ndim, int mode, double *U_d, double *lambda_d, double *G_d, double *ip_d,
+                                          const double *normX2_d, double *fit_d, skt_stream stream) {
+    SKT_REQUIRE(ex_parts_d && world >= 1 && world <= 64, SKT_EINVAL, "bad record list");
+    return update_finish_impl(nullptr, ex_parts_d, world, first_iter, rows, rank, ndim, mode, U_d, lambda_d, G_d, ip_d,
+                              normX2_d, fit_d, stream);
 }

@@ -254,6 +254,25 @@ def cp_update_finish(ex_all, world, first_iter, U, lam, G, mode, ip=None, normX2
                                         dev.ptr(fit), dev.stream_ptr()))
 
 
+def cp_update_cluster_parts(parts_dev, nparts, P, G, mode, first_iter, U, lam, ip=None, normX2=None, fit=None):
+    """``cp_update_cluster`` with M = sum over ranks of the partial MTTKRPs read from peer memory (``parts_dev``: device
+    address of the array of ``nparts`` peer pointers)."""
+    lib = _lib.load()
+    rows, R = U.shape
+    _lib.check(lib.skt_cp_update_cluster_parts(C.c_void_p(int(parts_dev)), int(nparts), dev.ptr(P), rows, R, int(G.shape[0]),
+                                               mode, 1 if first_iter else 0, dev.ptr(G), dev.ptr(U), dev.ptr(lam),
+                                               dev.ptr(ip), dev.ptr(normX2), dev.ptr(fit), dev.stream_ptr()))
+
+
+def cp_update_finish_parts(parts_dev, world, first_iter, U, lam, G, mode, ip=None, normX2=None, fit=None):
+    """``cp_update_finish`` reading every rank's exchange record from peer memory."""
+    lib = _lib.load()
+    rows, R = U.shape
+    _lib.check(lib.skt_cp_update_finish_parts(C.c_void_p(int(parts_dev)), int(world), 1 if first_iter else 0, rows, R,
+                                              int(G.shape[0]), mode, dev.ptr(U), dev.ptr(lam), dev.ptr(G), dev.ptr(ip),
+                                              dev.ptr(normX2), dev.ptr(fit), dev.stream_ptr()))
+
+
 def set_reserved_sms(n):
     return int(_lib.load().skt_set_reserved_sms(int(n)))
 

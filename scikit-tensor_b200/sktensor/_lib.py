@@ -78,6 +78,10 @@ PROTOTYPES = {
                                          c_stream]),
     'skt_cp_update_finish': (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp,
                                        c_dp, c_dp, c_dp, c_stream]),
+    'skt_cp_update_cluster_parts': (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_dp,
+                                              c_dp, c_dp, c_dp, c_dp, c_dp, c_stream]),
+    'skt_cp_update_finish_parts': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_dp, c_dp,
+                                             c_dp, c_dp, c_dp, c_dp, c_stream]),
     'skt_set_reserved_sms': (C.c_int, [C.c_int]),
     'skt_cp_fit': (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_stream]),
     'skt_ttm_dense': (C.c_int, [c_dp, c_i64p, C.c_int, c_dp, C.c_int64, C.c_int, C.c_int, c_dp, c_stream]),

@@ -173,6 +173,38 @@ class CudaBackend(object):
     def update_finish(self, ex_all, world, first, U, lam, G, n, ip, normX2, fit):
         return self.K.cp_update_finish(ex_all, world, first, U, lam, G, n, ip=ip, normX2=normX2, fit=fit)
 
+    # symmetric memory (NVLink peer access): buffers every rank can read inside a kernel
+    _SYMM = {}      # (device, shape, tag) -> (tensor, handle): the rendezvous costs ~0.1 s, so buffers outlive the engines
+
+    def symm_alloc(self, shape, tag=0):
+        """(tensor, handle) in symmetric memory, or None when the platform lacks it.  Collective: all ranks call it
+        with the same arguments in the same order.  Buffers are cached per process and reused by later calls."""
+        if os.environ.get('SKT_NO_SYMM', '0') == '1':
+            return None
+        key = (self.dev.torch().cuda.current_device(), tuple(int(d) for d in shape), tag)
+        if key in CudaBackend._SYMM:
+            return CudaBackend._SYMM[key]
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(key[1], dtype=self.dev.torch().float64, device=self.dev.device())
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+            CudaBackend._SYMM[key] = (t, hdl)
+            return t, hdl
+        except Exception:
+            CudaBackend._SYMM[key] = None
+            return None
+
+    def symm_barrier(self, hdl, channel=0):
+        hdl.barrier(channel=channel)            # cross-rank barrier on the current stream
+
+    def update_cluster_parts(self, hdl, world, P, G, n, first, U, lam, ip, normX2, fit):
+        return self.K.cp_update_cluster_parts(hdl.buffer_ptrs_dev, world, P, G, n, first, U, lam, ip=ip, normX2=normX2, fit=fit)
+
+    def update_finish_parts(self, hdl, world, first, U, lam, G, n, ip, normX2, fit):
+        return self.K.cp_update_finish_parts(hdl.buffer_ptrs_dev, world, first, U, lam, G, n, ip=ip, normX2=normX2, fit=fit)
+
     def update_fused_fits(self, rows, R): return self.K.cp_update_fused_fits(rows, R)
     def update_fused(self, M, G, n, first, U, lam, info, ip, normX2, fit):
         return self.K.cp_update_fused(M, G, n, first, U, lam, info, ip=ip, normX2=normX2, fit=fit)
@@ -328,6 +360,25 @@ class CpAlsEngine(object):
             rec = be.exchange_record(R)
             self.ex = be.zeros((rec,))
             self.ex_all = be.zeros((comm.world if comm.active else 1, rec))
+        # ---- multi-GPU: fuse the reductions into the update kernels over NVLink peer memory.  The partial MTTKRP of a
+        # small replicated-solve mode and the exchange record of the sharded mode live in symmetric memory; after a
+        # cross-rank stream barrier the update kernels add the peers' buffers themselves, in rank order (no NCCL call).
+        self.Mh = [None] * N
+        self.exh = None
+        if comm.active and hasattr(be, 'symm_alloc'):
+            ok = True
+            for m in range(N):
+                if ok and m != self.s and self.cluster[m]:
+                    got = be.symm_alloc((self.lshape[m], R), tag=m)
+                    if got is None:
+                        ok = False
+                    else:
+                        self.M[m], self.Mh[m] = got
+            if ok and self.exchange and not self.fused[self.s]:
+                got = be.symm_alloc((be.exchange_record(R),), tag='ex')
+                if got is not None:
+                    self.ex, self.exh = got
+
         # modes whose pinv runs on the side stream: every mode that consumes a ready-made P
         has_async = hasattr(be, 'pinv_async') and os.environ.get('SKT_NO_CLUSTER_UPDATE', '0') != '1'
         self.apinv = [bool(has_async and (self.cluster[m] or (self.exchange and not self.fused[m]))) for m in range(N)]
@@ -394,8 +445,8 @@ class CpAlsEngine(object):
                 be.kr_reduce(self.TB, self.lshape[s:], self.Ud[s:], self.R, n - s, self.M[n])
         else:
             be.mttkrp_dense(self.Xd, self.lshape, self.Ud, self.R, n, self.M[n])
-        if self.comm.active and n != self.s:
-            self.comm.allreduce_sum(self.M[n])
+        if self.comm.active and n != self.s and self.Mh[n] is None:
+            self.comm.allreduce_sum(self.M[n])          # (modes with a symmetric-memory M are summed inside the update kernel)
         return self.M[n]
 
     def sweep(self, first_iter, want_fit=True):
@@ -424,7 +475,11 @@ class CpAlsEngine(object):
                 P = self.P
             if self.cluster[n]:
                 # small factor, replicated solve: one 8-CTA cluster does solve + normalise + Gram (+ <P,X>, fit)
-                be.update_cluster(M, P, self.G, n, first_iter, self.Ud[n], self.lam, *fit_args)
+                if self.Mh[n] is not None:
+                    be.symm_barrier(self.Mh[n])             # every rank's partial M_n is complete and visible
+                    be.update_cluster_parts(self.Mh[n], comm.world, P, self.G, n, first_iter, self.Ud[n], self.lam, *fit_args)
+                else:
+                    be.update_cluster(M, P, self.G, n, first_iter, self.Ud[n], self.lam, *fit_args)
                 fit_done = fit_done or last
             elif self.fused[n]:
                 # the same in one CTA, pinv included (no side stream)
@@ -434,10 +489,14 @@ class CpAlsEngine(object):
                 # sharded mode / tall factor: one record per rank, one all-gather, one finishing kernel
                 sharded = comm.active and n == self.s
                 be.update_exchange(M, P, first_iter, self.Ud[n], self.ex if sharded else self.ex_all[0])
-                if sharded:
-                    comm.allgather_records(self.ex, self.ex_all)
-                be.update_finish(self.ex_all, comm.world if sharded else 1, first_iter, self.Ud[n], self.lam, self.G, n,
-                                 *fit_args)
+                if sharded and self.exh is not None:
+                    be.symm_barrier(self.exh)
+                    be.update_finish_parts(self.exh, comm.world, first_iter, self.Ud[n], self.lam, self.G, n, *fit_args)
+                else:
+                    if sharded:
+                        comm.allgather_records(self.ex, self.ex_all)
+                    be.update_finish(self.ex_all, comm.world if sharded else 1, first_iter, self.Ud[n], self.lam, self.G, n,
+                                     *fit_args)
                 fit_done = fit_done or last
             else:
                 be.solve_stats(M, P, first_iter, self.Ud[n], self.colstat)
