@@ -57,6 +57,12 @@ def main():
     lshape = (X1.shape[0], hi - lo, X1.shape[2])
     run('cp_kat3_s42_lopsided', _parallel.LocalShard(sptensor(lsubs, np.asarray(S3.vals)[keep], shape=lshape), 1, X1.shape, offs),
         3, 42, init='random')
+    if mode == 'nccl':
+        # the same run with the reductions fused into the update kernels over NVLink peer memory (default from 4 ranks up)
+        os.environ['SKT_SYMM'] = '1' if world < 4 else '0'
+        run('cp_cfg1_s42_othersymm', dtensor(X1), 3, 42, init='random')
+        run('cp_d4_s3_othersymm', dtensor(g['cp4_X']), 4, 3, init='random', max_iter=30)
+        os.environ.pop('SKT_SYMM')
     np.random.seed(42)
     _, fit, itr, _ = cp_als(dtensor(X1), 3, init='random', fit_method=None, max_iter=4)
     res['nofit'] = {'fit': float(fit), 'itr': int(itr)}
