@@ -14,6 +14,7 @@
 // fix-up kernel, always in storage order -- a segmented reduction without a single atomic and
 // with a reproducible summation order.  Rows without non-zeros are zero (M is cleared first).
 #include <algorithm>
+#include <ctime>
 #include <cstdlib>
 #include <type_traits>
 #include <cstring>
@@ -671,6 +672,15 @@ extern "C" int skt_coo_build(const int64_t *const *subs_d, const double *vals_d,
     return SKT_OK;
 }
 
+namespace {
+struct PhaseTimer {
+    bool on; double t0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+    PhaseTimer() { const char *e = getenv("SKT_COO_TRACE"); on = e && e[0] == '1'; t0 = now(); }
+    void lap(const char *what) { if (on) { cudaDeviceSynchronize(); const double t = now(); fprintf(stderr, "[coo build] %-28s %8.1f ms\n", what, (t - t0) * 1e3); t0 = t; } }
+};
+}  // namespace
+
 extern "C" int skt_coo_build_host(const int64_t *const *subs_h, const double *vals_h, int64_t nnz,
                                   const int64_t *shape, int ndim, unsigned modes_mask, skt_coo **out) {
     SKT_REQUIRE(subs_h && shape && out && (vals_h || nnz == 0), SKT_EINVAL, "NULL argument");
@@ -679,20 +689,34 @@ extern "C" int skt_coo_build_host(const int64_t *const *subs_h, const double *va
     const size_t n = (size_t)std::max<int64_t>(nnz, 1);
     long long *subs_d[SKT_MAX_NDIM] = {nullptr};
     double *vals_d = nullptr;
+    PhaseTimer pt_start;
     auto cleanup = [&]() {
         for (int m = 0; m < ndim; ++m) cudaFree(subs_d[m]);
         cudaFree(vals_d);
     };
+    // the COO arrays come from pageable NumPy memory: multi-threaded pinned staging (skt_upload, ~4x a plain cudaMemcpy)
     for (int m = 0; m < ndim; ++m) {
         cudaError_t e = cudaMalloc(&subs_d[m], n * sizeof(long long));
-        if (e == cudaSuccess && nnz > 0) e = cudaMemcpy(subs_d[m], subs_h[m], (size_t)nnz * sizeof(long long), cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "upload subscripts", __FILE__, __LINE__); }
+        if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "allocate subscripts", __FILE__, __LINE__); }
+        if (nnz > 0) {
+            const int rc = skt_upload(subs_d[m], subs_h[m], (size_t)nnz * sizeof(long long), nullptr);
+            if (rc != SKT_OK) { cleanup(); return rc; }
+        }
     }
     cudaError_t e = cudaMalloc(&vals_d, n * sizeof(double));
-    if (e == cudaSuccess && nnz > 0) e = cudaMemcpy(vals_d, vals_h, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "upload values", __FILE__, __LINE__); }
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "allocate values", __FILE__, __LINE__); }
+    if (nnz > 0) {
+        const int rc = skt_upload(vals_d, vals_h, (size_t)nnz * sizeof(double), nullptr);
+        if (rc != SKT_OK) { cleanup(); return rc; }
+    }
+    e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) { cleanup(); return cuda_fail(e, "upload", __FILE__, __LINE__); }
+    pt_start.lap("malloc + upload (host)");
+    PhaseTimer pt_after_upload;
     const int rc = skt_coo_build((const int64_t *const *)subs_d, vals_d, nnz, shape, ndim, modes_mask, nullptr, out);
+    pt_after_upload.lap("sort + gather (device)");
     cleanup();
+    pt_after_upload.lap("free staging");
     return rc;
 }
 
