@@ -1,28 +1,29 @@
 #!/usr/bin/env python
-"""Benchmark of the CP-ALS hot path (BASELINE.json: "MTTKRP GB/s (% HBM roofline) and CP-ALS
-iters/sec at 1/2/4/8 B200").
+"""Benchmark of the CP-ALS hot path (BASELINE.json: "MTTKRP GB/s (% HBM roofline) and CP-ALS iters/sec at 1/2/4/8 B200").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload dense|sparse]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload dense|sparse|cfg3|cfg5]
 
-One "step" is one full CP-ALS iteration on the workload -- for every mode the fused MTTKRP,
-the Hadamard-of-Grams pseudo-inverse, the factor update/normalisation, and the fit -- i.e. the
-loop body of the reference's cp.als (sktensor/cp.py:138-169).
+One "step" is one full CP-ALS iteration on the workload -- the MTTKRP of every mode (two dimension-tree passes over
+the tensor plus the small second-stage reductions), the Hadamard-of-Grams pseudo-inverse, the factor
+update/normalisation, and the fit -- i.e. the loop body of the reference's cp.als (sktensor/cp.py:138-169).
 
-Workload at N = 1: BASELINE.json configs[1], "cp_als dense 3-way 512x512x512 rank 32, FP64".
-For N > 1 (launched by torch.distributed.run, one rank per GPU, NCCL) the tensor is
-(512 N) x 512 x 512, cut along mode 0 so that every GPU keeps a 512^3 slab: weak scaling.
+Workload at N = 1: BASELINE.json configs[1], "cp_als dense 3-way 512x512x512 rank 32, FP64".  For N > 1 (launched by
+torch.distributed.run, one rank per GPU, NCCL) the tensor is (512 N) x 512 x 512, cut along mode 0 so that every GPU
+keeps a 512^3 slab: weak scaling.
 
-`value` (GB/s) = algorithmic MTTKRP bytes of one iteration, sum over modes of
-8 (prod I + R sum I), summed over all ranks' slabs, divided by the time of the WHOLE iteration
-(solves and fit included), tensor resident in HBM.  `als_iters_per_sec` is the same clock.
-`e2e` is the same metric through the public API, cp_als(dtensor(host ndarray), ...): host
-tensor upload, initial factor upload, per-iteration fit read-back and final factor download
-all inside the timed region.  `roofline` describes the dominant kernel (the dense MTTKRP),
-timed with CUDA events around each of its launches inside the timed iterations.
+`value` (GB/s) = algorithmic MTTKRP bytes of one iteration -- the reference's three MTTKRPs, sum over modes of
+8 (prod I + R sum I), summed over all ranks' slabs -- divided by the time of the WHOLE iteration (solves and fit
+included), tensor resident in HBM.  `als_iters_per_sec` is the same clock.  `e2e` is the same metric through the
+public API, cp_als(dtensor(host ndarray), ...): host tensor upload, initial factor upload, per-iteration fit read-back
+and final factor download all inside the timed region (median of three whole calls).  `roofline` describes the
+dominant kernel (the dense MTTKRP pass), timed with CUDA events around each of its launches inside the timed
+iterations; at rank 32 it is bound by the FP64 tensor pipe, whose peak is probed live (MEASURED_PEAKS.json has no
+FP64 figure), and the HBM fraction is reported beside it.
 
-`--impl reference` times the reference's own algorithm (the NumPy restatement in oracle/, the
-reference being pure Python that cannot travel to the GPU box) on the host cores, on a
-bounded 256^3 sub-cube of the same workload, reported in the same unit.
+`--impl reference` times the reference's own algorithm (the NumPy restatement in oracle/, the reference being pure
+Python that cannot travel to the GPU box) on the host cores, on a bounded 256^3 sub-cube of the same workload,
+reported in the same unit.  `--workload cfg3|cfg5` run the sharded sparse / 4-way configurations of BASELINE.json
+(secondary lines, see run_config); `--workload sparse` times the three sparse MTTKRPs alone.
 """
 import argparse
 import json
