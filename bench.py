@@ -412,7 +412,7 @@ def run_config(args):
 
       --workload cfg3 : cp_als on the sparse 10M x 1M x 100K power-law tensor, --nnz non-zeros in total (200 M =
                         configs[2]), rank 16, cut along mode 0 into equal-nnz row ranges, one per GPU
-      --workload cfg5 : cp_als on the dense 160^4 tensor, rank 64, cut along mode 0 (configs[4]; strong scaling)
+      --workload cfg5 : cp_als on the dense 160^4 tensor, rank 64, cut along a middle mode (configs[4]; strong scaling)
 
     Every rank generates only its own slab (same distribution as SURVEY 8(d): mode-0 subscripts are drawn by
     inverse-CDF sampling inside the rank's quantile range).  Prints one JSON line on rank 0.
@@ -445,11 +445,14 @@ def run_config(args):
         desc = 'cp_als sparse 10Mx1Mx100K power-law, %d nnz, rank 16 (BASELINE.json configs[2]), mode-0 equal-nnz cuts' % (nloc * world)
     else:
         R, gshape = 64, (160, 160, 160, 160)
-        offsets = _parallel.split_rows(gshape[0], world)
+        smode = _parallel.shard_mode(gshape, dense=True)          # a middle mode: both passes keep their full GEMM K
+        offsets = _parallel.split_rows(gshape[smode], world)
         rows = int(offsets[rank + 1] - offsets[rank])
-        X = _parallel.LocalShard(dtensor(rng.random((rows,) + gshape[1:])), 0, gshape, offsets)
+        lsh = list(gshape)
+        lsh[smode] = rows
+        X = _parallel.LocalShard(dtensor(rng.random(tuple(lsh))), smode, gshape, offsets)
         alg = 4 * alg_bytes_dense(gshape, R)
-        desc = 'cp_als dense 4-way 160^4 rank 64 (BASELINE.json configs[4]), cut along mode 0 (strong scaling)'
+        desc = 'cp_als dense 4-way 160^4 rank 64 (BASELINE.json configs[4]), cut along mode %d (strong scaling)' % smode
     gen_s = time.perf_counter() - tic
     np.random.seed(1)
     U = [None] + [np.random.rand(gshape[n], R) for n in range(1, len(gshape))]

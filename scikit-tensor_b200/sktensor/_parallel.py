@@ -55,9 +55,18 @@ def split_nnz(idx, dim, world):
     return np.array(offs, dtype=np.int64)
 
 
-def shard_mode(shape):
-    """The mode to cut: the largest one (first on ties)."""
-    return int(np.argmax(np.asarray(shape)))
+def shard_mode(shape, dense=False):
+    """The mode to cut: the largest one.  Ties: the first -- except for dense tensors, where a middle mode wins: the
+    first and the last mode are the GEMM contraction modes of the two dimension-tree passes, and a slab that is thin
+    in a contraction mode leaves the tensor cores a K of a few rows per tile."""
+    shape = [int(d) for d in shape]
+    best = max(shape)
+    cands = [m for m, d in enumerate(shape) if d == best]
+    if dense:
+        mid = [m for m in cands if 0 < m < len(shape) - 1]
+        if mid:
+            return mid[0]
+    return cands[0]
 
 
 def tree_split(shape):
@@ -292,7 +301,7 @@ class CpAlsEngine(object):
             local = X.tensor
         else:
             self.shape = tuple(int(d) for d in X.shape)
-            self.s = shard_mode(self.shape) if comm.active else -1
+            self.s = shard_mode(self.shape, dense=isinstance(X, dtensor)) if comm.active else -1
             local = X
             if comm.active:
                 local, self.offsets = self._cut(X, self.s, comm)

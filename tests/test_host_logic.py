@@ -266,3 +266,14 @@ def test_tree_split():
     assert tree_split((1000, 10, 10)) == 1
     assert tree_split((10, 10, 1000)) == 2
     assert tree_split((4, 5, 6, 7, 8)) in (2, 3)
+
+
+def test_shard_mode_prefers_middle_modes_for_dense_ties():
+    from sktensor._parallel import shard_mode
+    assert shard_mode((160, 160, 160, 160)) == 0
+    assert shard_mode((160, 160, 160, 160), dense=True) == 1
+    assert shard_mode((512, 512, 512), dense=True) == 1
+    assert shard_mode((1024, 512, 512), dense=True) == 0
+    assert shard_mode((10, 11, 8), dense=True) == 1
+    assert shard_mode((10, 8, 11), dense=True) == 2
+    assert shard_mode((7, 7), dense=True) == 0
