@@ -96,6 +96,11 @@ SKT_API size_t skt_kr_reduce_workspace(const int64_t *dims, int p, int rank, int
 SKT_API int skt_kr_reduce(const double *T_d, const int64_t *dims, int p, const double *const *W_d, int rank,
                   int mode, double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream);
 
+/* The same second stage with the per-split partial slabs left un-summed in slabs_d ([*nslabs_out][dims[mode]][rank],
+ * at most skt_kr_reduce_workspace bytes); skt_cp_update_cluster_slabs adds them in split order while staging M.  */
+SKT_API int skt_kr_reduce_slabs(const double *T_d, const int64_t *dims, int p, const double *const *W_d, int rank,
+                        int mode, double *slabs_d, size_t slabs_bytes, int *nslabs_out, skt_stream stream);
+
 /* ---------------------------------------------------------------- sparse (COO) MTTKRP
  * Replaces sptensor.uttkrp (sktensor/sptensor.py:216-229) and its per-rank-column
  * ttv/_ttv_compute passes (sptensor.py:153-177: gather, unique, searchsorted, bincount).
@@ -213,6 +218,10 @@ SKT_API int skt_cp_update_cluster_parts(const double *const *Mparts_d, int npart
 SKT_API int skt_cp_update_finish_parts(const double *const *ex_parts_d, int world, int first_iter, int64_t rows, int rank,
                                int ndim, int mode, double *U_d, double *lambda_d, double *G_d, double *ip_d,
                                const double *normX2_d, double *fit_d, skt_stream stream);
+/* skt_cp_update_cluster with M given as `nslabs` local partial slabs of rows*rank doubles each (skt_kr_reduce_slabs). */
+SKT_API int skt_cp_update_cluster_slabs(const double *slabs_d, int nslabs, const double *P_d, int64_t rows, int rank,
+                                int ndim, int mode, int first_iter, double *G_d, double *U_d, double *lambda_d,
+                                double *ip_d, const double *normX2_d, double *fit_d, skt_stream stream);
 /* Leave `n` SMs out of the persistent grids (dense MTTKRP) so that a small kernel on another stream can run
  * beside them; returns the previous value.  0 restores the full chip.                                      */
 SKT_API int skt_set_reserved_sms(int n);

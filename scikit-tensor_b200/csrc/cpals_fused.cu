@@ -283,6 +283,9 @@ struct ClusterParams {
     // MTTKRP is fused into the staging loop of the update
     const double *const *Mparts;
     int nparts;
+    // nslabs >= 1 (and Mparts == NULL): M is the sum of local partial slabs M + s * slab_stride (skt_kr_reduce_slabs)
+    int nslabs;
+    long long slab_stride;
 };
 
 struct ClusterLayout {
@@ -343,6 +346,16 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
             if (i < nr && c < R) {
                 const long long off = (long long)(r0 + i) * R + c;
                 for (int w = 0; w < p.nparts; ++w) v += p.Mparts[w][off];
+            }
+            Ms[i * LD + c] = v;
+        }
+    } else if (p.nslabs > 1) {
+        for (int e = tid; e < per * R8; e += CTH) {
+            const int i = e / R8, c = e - i * R8;
+            double v = 0.0;
+            if (i < nr && c < R) {
+                const double *src = p.M + (long long)(r0 + i) * R + c;
+                for (int sl = 0; sl < p.nslabs; ++sl) v += __ldg(src + sl * p.slab_stride);
             }
             Ms[i * LD + c] = v;
         }
@@ -755,7 +768,7 @@ extern "C" int skt_cp_update_cluster_fits(int64_t rows, int rank) {
     return (L.total * sizeof(double) <= smem_optin_bytes()) ? 1 : 0;
 }
 
-static int update_cluster_impl(const double *M_d, const double *const *Mparts_d, int nparts, const double *P_d,
+static int update_cluster_impl(const double *M_d, int nslabs, const double *const *Mparts_d, int nparts, const double *P_d,
                                int64_t rows, int rank, int ndim, int mode, int first_iter, double *G_d, double *U_d,
                                double *lambda_d, double *ip_d, const double *normX2_d, double *fit_d, skt_stream stream) {
     SKT_REQUIRE((M_d || (Mparts_d && nparts >= 1)) && P_d && G_d && U_d && lambda_d, SKT_EINVAL, "NULL argument");
@@ -772,7 +785,7 @@ static int update_cluster_impl(const double *M_d, const double *const *Mparts_d,
     }
     ClusterParams p;
     p.M = M_d; p.P = P_d; p.G = G_d; p.U = U_d; p.lambda = lambda_d; p.ip = ip_d; p.normX2 = normX2_d; p.fit = fit_d;
-    p.rows = rows; p.R = rank; p.ndim = ndim; p.mode = mode; p.first_iter = first_iter; p.ex = nullptr; p.Mparts = Mparts_d; p.nparts = nparts;
+    p.rows = rows; p.R = rank; p.ndim = ndim; p.mode = mode; p.first_iter = first_iter; p.ex = nullptr; p.Mparts = Mparts_d; p.nparts = nparts; p.nslabs = nslabs; p.slab_stride = (long long)rows * rank;
     cp_update_cluster_kernel<<<CL, CTH, smem, (cudaStream_t)stream>>>(p);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
@@ -801,7 +814,7 @@ extern "C" int skt_cp_update_exchange(const double *M_d, const double *P_d, int6
         }
         ClusterParams p;
         p.M = M_d; p.P = P_d; p.G = nullptr; p.U = Unew_d; p.lambda = nullptr; p.ip = nullptr; p.normX2 = nullptr; p.fit = nullptr;
-        p.rows = rows; p.R = rank; p.ndim = 1; p.mode = 0; p.first_iter = first_iter; p.ex = ex_d; p.Mparts = nullptr; p.nparts = 1;
+        p.rows = rows; p.R = rank; p.ndim = 1; p.mode = 0; p.first_iter = first_iter; p.ex = ex_d; p.Mparts = nullptr; p.nparts = 1; p.nslabs = 1; p.slab_stride = 0;
         cp_update_cluster_kernel<<<CL, CTH, smem, st>>>(p);
         SKT_LAUNCH_CHECK();
         return SKT_OK;
@@ -853,7 +866,7 @@ static int update_finish_impl(const double *ex_all_d, const double *const *ex_pa
 extern "C" int skt_cp_update_cluster(const double *M_d, const double *P_d, int64_t rows, int rank, int ndim, int mode,
                                      int first_iter, double *G_d, double *U_d, double *lambda_d, double *ip_d,
                                      const double *normX2_d, double *fit_d, skt_stream stream) {
-    return update_cluster_impl(M_d, nullptr, 1, P_d, rows, rank, ndim, mode, first_iter, G_d, U_d, lambda_d, ip_d, normX2_d,
+    return update_cluster_impl(M_d, 1, nullptr, 1, P_d, rows, rank, ndim, mode, first_iter, G_d, U_d, lambda_d, ip_d, normX2_d,
                                fit_d, stream);
 }
 
@@ -862,7 +875,7 @@ extern "C" int skt_cp_update_cluster_parts(const double *const *Mparts_d, int np
                                            double *lambda_d, double *ip_d, const double *normX2_d, double *fit_d,
                                            skt_stream stream) {
     SKT_REQUIRE(Mparts_d && nparts >= 1 && nparts <= 64, SKT_EINVAL, "bad partial-buffer list");
-    return update_cluster_impl(nullptr, Mparts_d, nparts, P_d, rows, rank, ndim, mode, first_iter, G_d, U_d, lambda_d, ip_d,
+    return update_cluster_impl(nullptr, 1, Mparts_d, nparts, P_d, rows, rank, ndim, mode, first_iter, G_d, U_d, lambda_d, ip_d,
                                normX2_d, fit_d, stream);
 }
 
@@ -879,4 +892,12 @@ extern "C" int skt_cp_update_finish_parts(const double *const *ex_parts_d, int w
     SKT_REQUIRE(ex_parts_d && world >= 1 && world <= 64, SKT_EINVAL, "bad record list");
     return update_finish_impl(nullptr, ex_parts_d, world, first_iter, rows, rank, ndim, mode, U_d, lambda_d, G_d, ip_d,
                               normX2_d, fit_d, stream);
+}
+
+extern "C" int skt_cp_update_cluster_slabs(const double *slabs_d, int nslabs, const double *P_d, int64_t rows, int rank,
+                                           int ndim, int mode, int first_iter, double *G_d, double *U_d, double *lambda_d,
+                                           double *ip_d, const double *normX2_d, double *fit_d, skt_stream stream) {
+    SKT_REQUIRE(slabs_d && nslabs >= 1 && nslabs <= 4096, SKT_EINVAL, "bad slab list");
+    return update_cluster_impl(slabs_d, nslabs, nullptr, 1, P_d, rows, rank, ndim, mode, first_iter, G_d, U_d, lambda_d, ip_d,
+                               normX2_d, fit_d, stream);
 }

@@ -130,32 +130,52 @@ extern "C" size_t skt_kr_reduce_workspace(const int64_t *dims, int p, int rank, 
     long long In, L, Tt, chunk;
     int nsplit;
     if (kr_plan(dims, p, rank, mode, In, L, Tt, nsplit, chunk) != SKT_OK) return 0;
-    return align_up((size_t)(nsplit > 1 ? nsplit : 0) * In * rank * sizeof(double) + 256, 256);
+    return align_up((size_t)nsplit * In * rank * sizeof(double) + 256, 256);   // (also covers skt_kr_reduce_slabs with one split)
 }
+
+static int kr_reduce_impl(const double *T_d, const int64_t *dims, int p, const double *const *W_d, int rank, int mode,
+                          double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream, int *nslabs_out);
 
 extern "C" int skt_kr_reduce(const double *T_d, const int64_t *dims, int p, const double *const *W_d, int rank, int mode,
                              double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    return kr_reduce_impl(T_d, dims, p, W_d, rank, mode, M_d, ws_d, ws_bytes, stream, nullptr);
+}
+
+// Same, but the per-split partial slabs are left un-summed in slabs_d ([*nslabs_out][dims[mode]][rank], at most
+// skt_kr_reduce_workspace bytes): skt_cp_update_cluster_slabs adds them (in split order, the same arithmetic) while it
+// stages M, which saves a launch on the critical path of the sweep.
+extern "C" int skt_kr_reduce_slabs(const double *T_d, const int64_t *dims, int p, const double *const *W_d, int rank,
+                                   int mode, double *slabs_d, size_t slabs_bytes, int *nslabs_out, skt_stream stream) {
+    SKT_REQUIRE(nslabs_out != nullptr, SKT_EINVAL, "NULL argument");
+    return kr_reduce_impl(T_d, dims, p, W_d, rank, mode, nullptr, slabs_d, slabs_bytes, stream, nslabs_out);
+}
+
+static int kr_reduce_impl(const double *T_d, const int64_t *dims, int p, const double *const *W_d, int rank, int mode,
+                          double *M_d, void *ws_d, size_t ws_bytes, skt_stream stream, int *nslabs_out) {
+    const bool keep = nslabs_out != nullptr;      // leave the partial slabs in ws_d
     if (dims && p >= 2 && p <= SKT_MAX_NDIM && mode >= 0 && mode < p && rank >= 1) {
         bool empty = false;
         for (int m = 0; m < p; ++m) empty = empty || dims[m] == 0;
         if (empty) {     // empty group (a rank without rows): all zeros
-            if (dims[mode] > 0 && M_d) SKT_CUDA(cudaMemsetAsync(M_d, 0, (size_t)dims[mode] * rank * sizeof(double), (cudaStream_t)stream));
+            double *dst = keep ? (double *)ws_d : M_d;
+            if (dims[mode] > 0 && dst) SKT_CUDA(cudaMemsetAsync(dst, 0, (size_t)dims[mode] * rank * sizeof(double), (cudaStream_t)stream));
+            if (keep) *nslabs_out = 1;
             return SKT_OK;
         }
     }
-    SKT_REQUIRE(T_d && W_d && M_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(T_d && W_d && (M_d || keep), SKT_EINVAL, "NULL argument");
     long long In, L, Tt, chunk;
     int nsplit;
     int rc = kr_plan(dims, p, rank, mode, In, L, Tt, nsplit, chunk);
     if (rc != SKT_OK) return rc;
     const size_t need = skt_kr_reduce_workspace(dims, p, rank, mode);
-    SKT_REQUIRE(nsplit == 1 || (ws_d && ws_bytes >= need), SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu",
-                need, ws_bytes);
+    SKT_REQUIRE((nsplit == 1 && !keep) || (ws_d && ws_bytes >= (keep ? (size_t)nsplit * In * rank * sizeof(double) : need)),
+                SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     KrParams kp;
     kp.T = T_d;
     kp.In = In; kp.L = L; kp.Tt = Tt; kp.J = L * Tt;
     kp.chunk = chunk; kp.R = rank; kp.nsplit = nsplit;
-    kp.out = (nsplit > 1) ? (double *)ws_d : M_d;
+    kp.out = (nsplit > 1 || keep) ? (double *)ws_d : M_d;
     kp.nw = 0;
     {
         long long div = 1;
@@ -182,6 +202,10 @@ extern "C" int skt_kr_reduce(const double *T_d, const int64_t *dims, int p, cons
     if (kp.nw == 1) kr_reduce_kernel<true><<<grid, 256, 0, st>>>(kp);
     else kr_reduce_kernel<false><<<grid, 256, 0, st>>>(kp);
     SKT_LAUNCH_CHECK();
+    if (keep) {
+        *nslabs_out = nsplit;
+        return SKT_OK;
+    }
     if (nsplit > 1) {
         const long long n = In * rank;
         const int blocks = (int)std::min<long long>((n + 255) / 256, 4LL * sm_count());

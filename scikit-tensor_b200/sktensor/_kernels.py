@@ -65,6 +65,21 @@ def kr_reduce(T, dims, W, rank, mode, out=None):
     return out
 
 
+def kr_reduce_slabs(T, dims, W, rank, mode, slabs):
+    """``kr_reduce`` that leaves its per-split partial slabs in ``slabs`` (a device buffer of at least the workspace
+    size); returns the number of slabs.  ``cp_update_cluster_slabs`` adds them while staging M."""
+    lib = _lib.load()
+    d = _lib.shape_array(dims)
+    n = C.c_int(0)
+    _lib.check(lib.skt_kr_reduce_slabs(dev.ptr(T), d, len(dims), _factor_ptrs(W, mode), rank, mode, dev.ptr(slabs),
+                                       slabs.numel() * slabs.element_size(), C.byref(n), dev.stream_ptr()))
+    return n.value
+
+
+def kr_reduce_workspace(dims, rank, mode):
+    return int(_lib.load().skt_kr_reduce_workspace(_lib.shape_array(dims), len(dims), rank, mode))
+
+
 # ------------------------------------------------------------------ sparse
 class CooHandle(object):
     """Owner of a device-resident sorted COO tensor (``skt_coo*``)."""
@@ -271,6 +286,15 @@ def cp_update_finish_parts(parts_dev, world, first_iter, U, lam, G, mode, ip=Non
     _lib.check(lib.skt_cp_update_finish_parts(C.c_void_p(int(parts_dev)), int(world), 1 if first_iter else 0, rows, R,
                                               int(G.shape[0]), mode, dev.ptr(U), dev.ptr(lam), dev.ptr(G), dev.ptr(ip),
                                               dev.ptr(normX2), dev.ptr(fit), dev.stream_ptr()))
+
+
+def cp_update_cluster_slabs(slabs, nslabs, P, G, mode, first_iter, U, lam, ip=None, normX2=None, fit=None):
+    """``cp_update_cluster`` with M = sum of ``nslabs`` local partial slabs (``kr_reduce_slabs``)."""
+    lib = _lib.load()
+    rows, R = U.shape
+    _lib.check(lib.skt_cp_update_cluster_slabs(dev.ptr(slabs), int(nslabs), dev.ptr(P), rows, R, int(G.shape[0]), mode,
+                                               1 if first_iter else 0, dev.ptr(G), dev.ptr(U), dev.ptr(lam), dev.ptr(ip),
+                                               dev.ptr(normX2), dev.ptr(fit), dev.stream_ptr()))
 
 
 def set_reserved_sms(n):

@@ -39,6 +39,8 @@ PROTOTYPES = {
     'skt_kr_reduce_workspace': (C.c_size_t, [c_i64p, C.c_int, C.c_int, C.c_int]),
     'skt_kr_reduce': (C.c_int, [c_dp, c_i64p, C.c_int, c_voidpp, C.c_int, C.c_int, c_dp, C.c_void_p, C.c_size_t,
                                 c_stream]),
+    'skt_kr_reduce_slabs': (C.c_int, [c_dp, c_i64p, C.c_int, c_voidpp, C.c_int, C.c_int, c_dp, C.c_size_t,
+                                      C.POINTER(C.c_int), c_stream]),
     'skt_coo_build_host': (C.c_int, [c_voidpp, c_dp, C.c_int64, c_i64p, C.c_int, C.c_uint,
                                      C.POINTER(C.c_void_p)]),
     'skt_coo_build': (C.c_int, [c_voidpp, c_dp, C.c_int64, c_i64p, C.c_int, C.c_uint, c_stream,
@@ -82,6 +84,8 @@ PROTOTYPES = {
                                               c_dp, c_dp, c_dp, c_dp, c_dp, c_stream]),
     'skt_cp_update_finish_parts': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_dp, c_dp,
                                              c_dp, c_dp, c_dp, c_dp, c_stream]),
+    'skt_cp_update_cluster_slabs': (C.c_int, [c_dp, C.c_int, c_dp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_dp,
+                                              c_dp, c_dp, c_dp, c_dp, c_dp, c_stream]),
     'skt_set_reserved_sms': (C.c_int, [C.c_int]),
     'skt_cp_fit': (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp, c_stream]),
     'skt_ttm_dense': (C.c_int, [c_dp, c_i64p, C.c_int, c_dp, C.c_int64, C.c_int, C.c_int, c_dp, c_stream]),

@@ -140,6 +140,10 @@ class CudaBackend(object):
     def mttkrp_dense(self, Xd, shape, U, R, n, out): return self.K.mttkrp_dense(Xd, shape, U, R, n, out=out)
     def mttkrp_coo(self, coo, U, R, n, out): return self.K.mttkrp_coo(coo, U, R, n, out=out)
     def kr_reduce(self, T, dims, W, R, n, out): return self.K.kr_reduce(T, dims, W, R, n, out=out)
+    def kr_reduce_slab_buffer(self, dims, R, n): return self.empty((max(1, self.K.kr_reduce_workspace(dims, R, n) // 8),))
+    def kr_reduce_slabs(self, T, dims, W, R, n, slabs): return self.K.kr_reduce_slabs(T, dims, W, R, n, slabs)
+    def update_cluster_slabs(self, slabs, nslabs, P, G, n, first, U, lam, ip, normX2, fit):
+        return self.K.cp_update_cluster_slabs(slabs, nslabs, P, G, n, first, U, lam, ip=ip, normX2=normX2, fit=fit)
     def sumsq(self, x): return self.K.sumsq(x)
     def coo_sumsq(self, coo): return self.K.coo_sumsq(coo)
     def gram(self, U, out): return self.K.gram(U, out=out)
@@ -399,6 +403,8 @@ class CpAlsEngine(object):
         # ---- dimension tree (dense, N >= 3): two passes over X per sweep instead of N.  Modes [0, s) are
         # served by T_A = X contracted with U_s..U_{N-1}; modes [s, N) by T_B = X contracted with
         # U_0..U_{s-1}.  A one-mode group needs no second stage: its partial tensor IS the MTTKRP.
+        self.slabbuf = [None] * N        # per mode: buffer for un-summed second-stage slabs (see below)
+        self.nslabs = [0] * N
         self.tree = (not self.sparse) and N >= 3 and hasattr(be, 'kr_reduce') and \
             os.environ.get('SKT_NO_DIMTREE', '0') != '1'
         if self.tree:
@@ -409,6 +415,14 @@ class CpAlsEngine(object):
             self.shapeB = tuple(self.lshape[:s]) + (nB,)
             self.TA = self.M[0] if s == 1 else be.empty((nA, R))
             self.TB = self.M[N - 1] if s == N - 1 else be.empty((nB, R))
+            # single process: the second stage leaves its per-split slabs for the cluster update to add while it stages
+            # M (same arithmetic, one launch less on the critical path)
+            if not comm.active and hasattr(be, 'kr_reduce_slabs') and os.environ.get('SKT_NO_KR_SLABS', '0') != '1':
+                for m in range(N):
+                    two_stage = (m < s and s > 1) or (m >= s and s < N - 1)
+                    if two_stage and self.cluster[m]:
+                        dims = self.lshape[:s] if m < s else self.lshape[s:]
+                        self.slabbuf[m] = be.kr_reduce_slab_buffer(dims, R, m if m < s else m - s)
 
     @staticmethod
     def _cut(X, s, comm):
@@ -452,9 +466,15 @@ class CpAlsEngine(object):
             elif n == s:
                 self._tree_pass(1)
             if n < s and s > 1:
-                be.kr_reduce(self.TA, self.lshape[:s], self.Ud[:s], self.R, n, self.M[n])
+                if self.slabbuf[n] is not None:
+                    self.nslabs[n] = be.kr_reduce_slabs(self.TA, self.lshape[:s], self.Ud[:s], self.R, n, self.slabbuf[n])
+                else:
+                    be.kr_reduce(self.TA, self.lshape[:s], self.Ud[:s], self.R, n, self.M[n])
             elif n >= s and s < N - 1:
-                be.kr_reduce(self.TB, self.lshape[s:], self.Ud[s:], self.R, n - s, self.M[n])
+                if self.slabbuf[n] is not None:
+                    self.nslabs[n] = be.kr_reduce_slabs(self.TB, self.lshape[s:], self.Ud[s:], self.R, n - s, self.slabbuf[n])
+                else:
+                    be.kr_reduce(self.TB, self.lshape[s:], self.Ud[s:], self.R, n - s, self.M[n])
         else:
             be.mttkrp_dense(self.Xd, self.lshape, self.Ud, self.R, n, self.M[n])
         if self.comm.active and n != self.s and self.Mh[n] is None:
@@ -487,7 +507,10 @@ class CpAlsEngine(object):
                 P = self.P
             if self.cluster[n]:
                 # small factor, replicated solve: one 8-CTA cluster does solve + normalise + Gram (+ <P,X>, fit)
-                if self.Mh[n] is not None:
+                if self.slabbuf[n] is not None:
+                    be.update_cluster_slabs(self.slabbuf[n], self.nslabs[n], P, self.G, n, first_iter, self.Ud[n], self.lam,
+                                            *fit_args)
+                elif self.Mh[n] is not None:
                     be.symm_barrier(self.Mh[n])             # every rank's partial M_n is complete and visible
                     be.update_cluster_parts(self.Mh[n], comm.world, P, self.G, n, first_iter, self.Ud[n], self.lam, *fit_args)
                 else:

@@ -530,3 +530,30 @@ def test_exchange_update_matches_reference_arithmetic(K, dev, rows, R, N, world)
         f = dev.to_host(fit)
         assert abs(f[1] - coef.sum()) < tol * coef.sum()
         assert abs(f[0] - (1.0 - (normX2 + coef.sum() - 2 * ipref) / normX2)) < tol * 10 * max(1.0, coef.sum() / normX2)
+
+
+def test_kr_slabs_feed_the_cluster_update(K, dev):
+    """skt_kr_reduce_slabs + skt_cp_update_cluster_slabs == skt_kr_reduce + skt_cp_update_cluster, bit for bit."""
+    rng = np.random.RandomState(77)
+    for (A, B, R) in ((512, 512, 32), (160, 150, 64), (40, 33, 5)):
+        T = dev.to_device(rng.rand(A, B, R) - 0.4)
+        W = [dev.to_device(rng.rand(A, R)), dev.to_device(rng.rand(B, R))]
+        G = np.stack([(lambda f: f.T.dot(f))(rng.rand(50, R)) for _ in range(3)])
+        for mode in (0, 1):
+            rows = (A, B)[mode]
+            M = K.kr_reduce(T, (A, B), W, R, mode)
+            slabs = dev.empty((max(1, K.kr_reduce_workspace((A, B), R, mode) // 8),))
+            ns = K.kr_reduce_slabs(T, (A, B), W, R, mode, slabs)
+            assert ns >= 1
+            out = []
+            for use_slabs in (False, True):
+                Gd = dev.to_device(G)
+                P, _ = K.hadamard_pinv(Gd, mode)
+                U, lam, ip = dev.empty((rows, R)), dev.empty((R,)), dev.zeros((1,))
+                if use_slabs:
+                    K.cp_update_cluster_slabs(slabs, ns, P, Gd, mode, False, U, lam, ip=ip)
+                else:
+                    K.cp_update_cluster(M, P, Gd, mode, False, U, lam, ip=ip)
+                out.append((dev.to_host(U), dev.to_host(lam), dev.to_host(Gd), dev.to_host(ip)))
+            for a, b in zip(out[0], out[1]):
+                assert (a == b).all(), (A, B, R, mode)
