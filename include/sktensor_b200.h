@@ -101,6 +101,12 @@ SKT_API int skt_kr_reduce(const double *T_d, const int64_t *dims, int p, const d
 SKT_API int skt_kr_reduce_slabs(const double *T_d, const int64_t *dims, int p, const double *const *W_d, int rank,
                         int mode, double *slabs_d, size_t slabs_bytes, int *nslabs_out, skt_stream stream);
 
+/* Dense reconstruction of a Kruskal tensor, out[i_0..i_{N-1}] = sum_r lambda_r prod_m U_m[i_m, r] in C order
+ * (ktensor.toarray / totensor, sktensor/ktensor.py:152-175: `dot(lmbda, khatrirao(U).T).reshape(shape)`), without
+ * forming the Khatri-Rao matrix.  lambda_d may be NULL (ones).                                                  */
+SKT_API int skt_ktensor_full(const double *const *U_d, const double *lambda_d, const int64_t *shape, int ndim, int rank,
+                     double *out_d, skt_stream stream);
+
 /* ---------------------------------------------------------------- sparse (COO) MTTKRP
  * Replaces sptensor.uttkrp (sktensor/sptensor.py:216-229) and its per-rank-column
  * ttv/_ttv_compute passes (sptensor.py:153-177: gather, unique, searchsorted, bincount).

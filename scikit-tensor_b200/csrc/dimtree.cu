@@ -118,6 +118,48 @@ int kr_plan(const int64_t *dims, int p, int rank, int mode, long long &In, long 
     return SKT_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Dense reconstruction of a Kruskal tensor (ktensor.toarray, sktensor/ktensor.py:152-163):
+//   out[i_0..i_{N-1}] = sum_r lambda_r prod_m U_m[i_m, r]        (C order)
+// One CTA per index of all modes but the last: the R prefix products go to shared memory, the threads then sweep
+// the last mode.  The factor of the last mode (I x R) stays in L1/L2; the output is written once, coalesced.
+// ---------------------------------------------------------------------------------------------
+struct FullParams {
+    const double *U[SKT_MAX_NDIM];
+    const double *lambda;
+    long long shape[SKT_MAX_NDIM];
+    double *out;
+    long long nprefix;
+    int ndim, R;
+};
+
+__global__ void __launch_bounds__(256) ktensor_full_kernel(const __grid_constant__ FullParams p) {
+    extern __shared__ double pre[];
+    const int last = p.ndim - 1;
+    const long long K = p.shape[last];
+    for (long long q = blockIdx.x; q < p.nprefix; q += gridDim.x) {
+        __syncthreads();
+        for (int r = threadIdx.x; r < p.R; r += 256) {
+            double v = p.lambda ? p.lambda[r] : 1.0;
+            long long rem = q;
+            for (int m = last - 1; m >= 0; --m) {
+                const long long im = rem % p.shape[m];
+                rem /= p.shape[m];
+                v *= __ldg(p.U[m] + im * p.R + r);
+            }
+            pre[r] = v;
+        }
+        __syncthreads();
+        for (long long k = threadIdx.x; k < K; k += 256) {
+            const double *row = p.U[last] + k * p.R;
+            double sum = 0.0;
+            for (int r = 0; r < p.R; ++r) sum += pre[r] * __ldg(row + r);
+            p.out[q * K + k] = sum;
+        }
+    }
+}
+
 }  // namespace
 }  // namespace skt
 
@@ -212,5 +254,29 @@ static int kr_reduce_impl(const double *T_d, const int64_t *dims, int p, const d
         kr_sum_splits_kernel<<<blocks, 256, 0, st>>>((const double *)ws_d, nsplit, n, M_d);
         SKT_LAUNCH_CHECK();
     }
+    return SKT_OK;
+}
+
+extern "C" int skt_ktensor_full(const double *const *U_d, const double *lambda_d, const int64_t *shape, int ndim, int rank,
+                                double *out_d, skt_stream stream) {
+    SKT_REQUIRE(U_d && shape && out_d, SKT_EINVAL, "NULL argument");
+    SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "ndim must be in [1, %d], got %d", SKT_MAX_NDIM, ndim);
+    SKT_REQUIRE(rank >= 1 && rank <= 4096, SKT_EUNSUPPORTED, "reconstruction supports rank <= 4096, got %d", rank);
+    FullParams p;
+    p.lambda = lambda_d; p.out = out_d; p.ndim = ndim; p.R = rank;
+    long long npre = 1;
+    for (int m = 0; m < ndim; ++m) {
+        SKT_REQUIRE(shape[m] >= 0 && shape[m] < (1LL << 31), SKT_ESHAPE, "shape[%d] = %lld", m, (long long)shape[m]);
+        if (shape[m] == 0) return SKT_OK;              // empty tensor
+        SKT_REQUIRE(U_d[m] != nullptr, SKT_EINVAL, "U[%d] is NULL", m);
+        p.U[m] = U_d[m];
+        p.shape[m] = shape[m];
+        if (m < ndim - 1) npre *= shape[m];
+        SKT_REQUIRE(npre < (1LL << 46), SKT_ESHAPE, "tensor too large");
+    }
+    p.nprefix = npre;
+    const unsigned grid = (unsigned)std::min<long long>(npre, 64LL * sm_count());
+    ktensor_full_kernel<<<grid, 256, (size_t)rank * sizeof(double), (cudaStream_t)stream>>>(p);
+    SKT_LAUNCH_CHECK();
     return SKT_OK;
 }

@@ -80,6 +80,16 @@ def kr_reduce_workspace(dims, rank, mode):
     return int(_lib.load().skt_kr_reduce_workspace(_lib.shape_array(dims), len(dims), rank, mode))
 
 
+def ktensor_full(U, lam, shape):
+    """Dense C-order reconstruction ``sum_r lam_r outer(U_0[:, r], ..., U_{N-1}[:, r])`` (ktensor.py:152-163)."""
+    lib = _lib.load()
+    out = dev.empty(tuple(int(s) for s in shape))
+    R = int(U[0].shape[1])
+    _lib.check(lib.skt_ktensor_full(_factor_ptrs(U), dev.ptr(lam), _lib.shape_array(shape), len(shape), R, dev.ptr(out),
+                                    dev.stream_ptr()))
+    return out
+
+
 # ------------------------------------------------------------------ sparse
 class CooHandle(object):
     """Owner of a device-resident sorted COO tensor (``skt_coo*``)."""

@@ -41,6 +41,7 @@ PROTOTYPES = {
                                 c_stream]),
     'skt_kr_reduce_slabs': (C.c_int, [c_dp, c_i64p, C.c_int, c_voidpp, C.c_int, C.c_int, c_dp, C.c_size_t,
                                       C.POINTER(C.c_int), c_stream]),
+    'skt_ktensor_full': (C.c_int, [c_voidpp, c_dp, c_i64p, C.c_int, C.c_int, c_dp, c_stream]),
     'skt_coo_build_host': (C.c_int, [c_voidpp, c_dp, C.c_int64, c_i64p, C.c_int, C.c_uint,
                                      C.POINTER(C.c_void_p)]),
     'skt_coo_build': (C.c_int, [c_voidpp, c_dp, C.c_int64, c_i64p, C.c_int, C.c_uint, c_stream,

@@ -6,7 +6,6 @@
 """
 import numpy as np
 
-from .core import khatrirao
 from .dtensor import dtensor
 
 __all__ = ['ktensor', 'vectorized_ktensor']
@@ -84,9 +83,13 @@ class ktensor(object):
         return float(dev.to_host(K.weighted_dot(Ud[last], M, lam))[0])
 
     def toarray(self):
-        """Dense ndarray of the represented tensor (ktensor.py:152-163); host, off the path."""
-        A = np.dot(np.asarray(self.lmbda), khatrirao(tuple(self.U)).T)
-        return A.reshape(self.shape)
+        """Dense ndarray of the represented tensor (ktensor.py:152-163): reconstructed on the device without the
+        Khatri-Rao matrix (``skt_ktensor_full``), then copied back."""
+        from . import _device as dev
+        from . import _kernels as K
+        Ud = [dev.to_device(np.asarray(Um, dtype=float)) for Um in self.U]
+        lam = dev.to_device(np.asarray(self.lmbda, dtype=float))
+        return dev.to_host(K.ktensor_full(Ud, lam, self.shape))
 
     def totensor(self):
         """Dense ``dtensor`` of the represented tensor (ktensor.py:165-175)."""

@@ -557,3 +557,21 @@ def test_kr_slabs_feed_the_cluster_update(K, dev):
                 out.append((dev.to_host(U), dev.to_host(lam), dev.to_host(Gd), dev.to_host(ip)))
             for a, b in zip(out[0], out[1]):
                 assert (a == b).all(), (A, B, R, mode)
+
+
+def test_ktensor_reconstruction(K, dev):
+    """ktensor.toarray / totensor (ktensor.py:152-175) on the device: exact on integers, 1e-13 on random factors,
+    any order and rank (the reference's docstring check `np.allclose(T, P.totensor())`, cp.py:107)."""
+    from sktensor import ktensor
+    A = ktensor([np.arange(1., 7).reshape(3, 2), np.arange(1., 5).reshape(2, 2)], np.array([2., 1.])).toarray()
+    assert (A == 2 * np.outer([1, 3, 5], [1, 3]) + np.outer([2, 4, 6], [2, 4])).all()
+    rng = np.random.RandomState(8)
+    for shape, R in (((7, 5, 3), 4), ((20, 10, 14), 3), ((6, 5, 4, 3, 2), 7), ((300,), 2), ((9, 200), 150), ((64, 48, 40), 32)):
+        U = [rng.rand(s, R) - 0.3 for s in shape]
+        lam = rng.rand(R) + 0.5
+        got = ktensor(U, lam).toarray()
+        ref = orc.kruskal_toarray(U, lam)
+        assert got.shape == tuple(shape)
+        assert relerr(got, ref) < 1e-13, (shape, R)
+    T = ktensor(U).totensor()
+    assert type(T).__name__ == 'dtensor' and relerr(np.asarray(T), orc.kruskal_toarray(U, np.ones(R))) < 1e-13

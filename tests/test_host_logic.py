@@ -203,8 +203,6 @@ def test_ktensor_container():                  # ktensor.py:59-68, test_ktensor.
     assert K == v.toktensor()
     with pytest.raises(ValueError, match='Dimension mismatch'):
         ktensor([np.ones((3, 2)), np.ones((4, 3))])
-    A = ktensor([np.arange(1., 7).reshape(3, 2), np.arange(1., 5).reshape(2, 2)], np.array([2., 1.])).toarray()
-    assert np.allclose(A, 2 * np.outer([1, 3, 5], [1, 3]) + np.outer([2, 4, 6], [2, 4]))
 
 
 def test_cp_als_argument_errors_before_any_device_work():
