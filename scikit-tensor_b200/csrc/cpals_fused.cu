@@ -38,7 +38,6 @@ struct FusedParams {
     double *fit;          // out[0] = fit, out[1] = |P|^2 (may be NULL)
     long long rows;
     int R, ndim, mode, first_iter;
-    long long *trace;     // debug: clock64 at the phase boundaries (may be NULL)
 };
 
 __host__ __device__ inline int round8(int x) { return (x + 7) & ~7; }
@@ -77,8 +76,6 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
     double *Ms = fsm + L.ms, *Ps = fsm + L.ps, *cs = fsm + L.cs, *gp = fsm + L.gp, *lam = fsm + L.lam, *red = fsm + L.red;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
-#define SKT_TRACE(k) do { if (p.trace && tid == 0) p.trace[k] = clock64(); } while (0)
-    SKT_TRACE(0);
 
     // ---- stage M (zero padded to rows8 x R8) while the pseudo-inverse is being formed
     for (int e = tid; e < rows8 * R8; e += FT) {
@@ -90,7 +87,6 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
     // ---- P = pinv(Y) straight into shared memory
     const PinvShared ps = pinv_carve(fsm + L.pv, R);
     const bool bad = pinv_load_y(ps, p.G, p.ndim, R, p.mode);   // contains block barriers: Ms / Ps are visible after it
-    SKT_TRACE(1);
     if (bad) {
         // the reference raises ValueError('array must not contain infs or NaNs') inside pinv (cp.py:147)
         for (int e = tid; e < rows * R; e += FT) p.U[e] = nan("");
@@ -100,7 +96,6 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
     const int kept = block_pinv(ps, p.G, p.ndim, R, p.mode, [&](int a, int b, double v) { Ps[a * LD + b] = v; });
     if (tid == 0) p.info[0] = kept;
     __syncthreads();
-    SKT_TRACE(2);
 
     // ---- Unew = M P : 8x8 output blocks, K = R8, FP64 tensor cores; warp w owns blocks w, w+32, ...
     const int ncb = R8 >> 3, nrb = rows8 >> 3, nblk = nrb * ncb;
@@ -145,7 +140,6 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
         red[FW] = sum;
     }
 
-    SKT_TRACE(3);
     // ---- column statistics: sum of squares (first iteration) or signed maximum, in a fixed order
     {
         const int RP = (R <= 16) ? 16 : (R <= 32 ? 32 : 64);
@@ -175,7 +169,6 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
         __syncthreads();
     }
 
-    SKT_TRACE(4);
     // ---- U = Unew / lambda (shared + global)
     for (int e = tid; e < rows * R; e += FT) {
         const int i = e / R, c = e - i * R;
@@ -185,7 +178,6 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
     }
     __syncthreads();
 
-    SKT_TRACE(5);
     // ---- G_n = U^T U : 8x8 blocks x S row parts on the tensor cores, parts summed in order
     {
         const int nb2 = ncb * ncb;
@@ -232,7 +224,6 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
         }
     }
 
-    SKT_TRACE(6);
     // ---- fit (cp.py:157-159); G_n was written by this block, so it is visible to it after the barrier
     if (p.fit) {
         double sacc = 0.0;
@@ -254,7 +245,6 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
             p.fit[1] = normP2;
         }
     }
-    SKT_TRACE(7);
 }
 
 
@@ -743,21 +733,8 @@ extern "C" int skt_cp_update_fused(const double *M_d, int64_t rows, int rank, in
     FusedParams p;
     p.M = M_d; p.G = G_d; p.U = U_d; p.lambda = lambda_d; p.info = info_d; p.ip = ip_d; p.normX2 = normX2_d; p.fit = fit_d;
     p.rows = rows; p.R = rank; p.ndim = ndim; p.mode = mode; p.first_iter = first_iter;
-    p.trace = nullptr;
-    static long long *trace_d = nullptr;
-    const char *tr = getenv("SKT_FUSED_TRACE");
-    if (tr && tr[0] == '1') {
-        if (!trace_d) cudaMalloc(&trace_d, 8 * sizeof(long long));
-        p.trace = trace_d;
-    }
     cp_update_fused_kernel<<<1, FT, smem, (cudaStream_t)stream>>>(p);
     SKT_LAUNCH_CHECK();
-    if (p.trace) {
-        long long h[8];
-        cudaMemcpy(h, trace_d, sizeof(h), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "fused trace (cycles): stage+loadY %lld  pinv %lld  solve %lld  stats %lld  normalise %lld  gram %lld  fit %lld  total %lld\n",
-                h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[7] - h[0]);
-    }
     return SKT_OK;
 }
 
