@@ -303,6 +303,8 @@ class CpAlsEngine(object):
         if isinstance(X, LocalShard):
             self.shape, self.s, self.offsets = X.shape, X.mode, X.offsets
             local = X.tensor
+            if not comm.active:          # a "shard" that is the whole tensor: nothing is sharded
+                self.s = -1
         else:
             self.shape = tuple(int(d) for d in X.shape)
             self.s = shard_mode(self.shape, dense=isinstance(X, dtensor)) if comm.active else -1

@@ -275,3 +275,22 @@ def test_shard_mode_prefers_middle_modes_for_dense_ties():
     assert shard_mode((10, 11, 8), dense=True) == 1
     assert shard_mode((10, 8, 11), dense=True) == 2
     assert shard_mode((7, 7), dense=True) == 0
+
+
+def test_local_shard_on_a_single_rank_is_the_whole_tensor():
+    """A LocalShard handed to a single-process engine must not slice the given factors (regression: bench cfg5 at N=1)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fake_backend import NumpyBackend
+    from sktensor import _parallel, dtensor
+    rng = np.random.RandomState(0)
+    X = rng.rand(6, 7, 5)
+    U = [None, rng.rand(7, 3), rng.rand(5, 3)]
+    shard = _parallel.LocalShard(dtensor(X), 1, X.shape, np.array([0, 7]))
+    eng = _parallel.CpAlsEngine(shard, 3, list(U), backend=NumpyBackend())
+    assert eng.s == -1 and tuple(eng.Ud[1].shape) == (7, 3)
+    eng.sweep(first_iter=True)
+    ref = _parallel.CpAlsEngine(dtensor(X), 3, list(U), backend=NumpyBackend())
+    ref.sweep(first_iter=True)
+    assert float(eng.fitout[0]) == float(ref.fitout[0])
