@@ -68,10 +68,6 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, int 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
                  "r"(src_bytes));
 }
-// 16-byte async copy with an L2 cache-policy hint (createpolicy)
-__device__ __forceinline__ void cp_async16_hint(void *smem_dst, const void *gsrc, uint64_t pol) {
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "l"(pol));
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -131,26 +127,6 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const void *tmap, uint64_
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(tmap) : "memory");
-}
-
-// ---- L2 residency hints ---------------------------------------------------------------------
-// Factor rows are re-read hundreds of times: keep them (evict_last).  Subscript/value streams and
-// output rows are touched once: mark them evict-first (ld.global.cs / st.global.cs) so they do not
-// push the factors out of the 126 MB L2.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ double ldg_keep(const double *p, uint64_t pol) {
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;\n" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ double2 ldg_keep2(const double *p, uint64_t pol) {
-    double2 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;\n" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
-    return v;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

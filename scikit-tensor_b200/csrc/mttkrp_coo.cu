@@ -64,12 +64,12 @@ struct Vec;
 template <>
 struct Vec<1> {
     double v[1];
-    __device__ __forceinline__ void load(const double *p, uint64_t) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void load(const double *p) { v[0] = __ldg(p); }
 };
 template <>
 struct Vec<2> {
     double v[2];
-    __device__ __forceinline__ void load(const double *p, uint64_t) {
+    __device__ __forceinline__ void load(const double *p) {
         const double2 t = __ldg(reinterpret_cast<const double2 *>(p));
         v[0] = t.x; v[1] = t.y;
     }
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ 
     const long long end = min(start + (long long)S, p.nnz);
     const int R = p.R;
     constexpr unsigned FULL = 0xffffffffu;
-    const uint64_t keep = 0;   // (L2 evict_last on factor rows and evict-first streams both measured ~10% slower)
+    // (L2 evict_last on the factor rows and evict-first streams were both measured: no gain)
 
     double acc[CPL];
 #pragma unroll
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ 
                 const int mm = (NO <= 3 || m < p.nother) ? m : 0;
                 const double *rowp = p.U[mm] + (long long)((NO <= 3 || m < p.nother) ? im : 0) * R;
 #pragma unroll
-                for (int vv = 0; vv < VPL; ++vv) u[b][m][vv].load(rowp + ccol[vv], keep);
+                for (int vv = 0; vv < VPL; ++vv) u[b][m][vv].load(rowp + ccol[vv]);
             }
         }
         // phase 2: products, then the ordered run accumulation
