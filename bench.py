@@ -131,11 +131,14 @@ def cpu_sample(steps=1):
     rng = np.random.RandomState(0)
     X = rng.rand(SAMPLE_SIDE, SAMPLE_SIDE, SAMPLE_SIDE)
     np.random.seed(1)
-    _, _, _, _, ex = orc.cp_als(X, RANK, init='random', max_iter=steps, conv=0)
+    # all the host threads BLAS can use (torchrun exports OMP_NUM_THREADS=1 for N > 1: lift that for this leg)
     try:
-        from threadpoolctl import threadpool_info
-        cores = max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
-    except Exception:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        with threadpool_limits(limits=os.cpu_count()):
+            _, _, _, _, ex = orc.cp_als(X, RANK, init='random', max_iter=steps, conv=0)
+            cores = max([p.get('num_threads', 1) for p in threadpool_info()] + [1])
+    except ImportError:
+        _, _, _, _, ex = orc.cp_als(X, RANK, init='random', max_iter=steps, conv=0)
         cores = os.cpu_count()
     return np.asarray(ex), cores
 
