@@ -189,17 +189,17 @@ __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ 
             }
             if (gl < SBB) {
                 double *meta = reinterpret_cast<double *>(st + DATAB + gw * METAG + gl * 16);
-                meta[0] = r_val[buf][c];
-                reinterpret_cast<int *>(meta + 1)[0] = r_row[buf][c];
+                *reinterpret_cast<double2 *>(meta) = make_double2(r_val[buf][c], __hiloint2double(0, r_row[buf][c]));
             }
         };
         auto compute_batch = [&](int t) {
             const unsigned char *st = ring + (t % SD) * STAGEB;
 #pragma unroll
             for (int b = 0; b < SBB; ++b) {
-                const double *meta = reinterpret_cast<const double *>(st + DATAB + gw * METAG + b * 16);
-                const double v = meta[0];
-                const int row = reinterpret_cast<const int *>(meta + 1)[0];
+                // (value, row id) of the non-zero in one 16-byte broadcast load
+                const double2 mt = *reinterpret_cast<const double2 *>(st + DATAB + gw * METAG + b * 16);
+                const double v = mt.x;
+                const int row = __double2loint(mt.y);
                 double x0 = colok ? v : 0.0, x1 = x0;
 #pragma unroll
                 for (int m = 0; m < NO; ++m) {
