@@ -42,3 +42,31 @@ def test_sharded_cp_als_nccl(tmp_path, golden, world):
                 assert relerr(np.array(u), golden['%s_U%d' % (gkey, m)]) < 1e-6, (key, m)
         for res in results[1:]:                      # replicas agree bit for bit
             assert res[key]['fit'] == results[0][key]['fit']
+
+
+@pytest.mark.parametrize('world', [2, 4, 8])
+def test_cfg3_shape_ngpu_equals_1gpu(tmp_path, world):
+    """BASELINE configs[2] shape (10M x 1M x 100K power law, 2e6 nnz, rank 16): the sharded run over `world` GPUs
+    (equal-nnz cuts along mode 0, reduce-scatter of the tall partial MTTKRPs) reproduces the single-GPU run."""
+    if _ngpu() < world:
+        pytest.skip('needs %d GPUs' % world)
+    worker = os.path.join(ROOT, 'tests', '_nccl_cfg3_worker.py')
+    one = str(tmp_path / 'one.json')
+    r = subprocess.run([sys.executable, worker, one], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES='0'))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    ref = json.load(open(one + '.0'))
+    out = str(tmp_path / 'n.json')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+           '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), worker, out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    for k in range(world):
+        got = json.load(open('%s.%d' % (out, k)))
+        assert got['itr'] == ref['itr']
+        assert abs(got['fit'] - ref['fit']) < 1e-9
+        assert relerr(got['lmbda'], ref['lmbda']) < 1e-9
+        for m in range(3):
+            assert relerr(got['colsum'][m], ref['colsum'][m]) < 1e-9
+            assert relerr(np.array(got['head'][m]), np.array(ref['head'][m])) < 1e-8
+            assert abs(got['sq'][m] - ref['sq'][m]) < 1e-9 * ref['sq'][m]
