@@ -63,6 +63,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
                  "r"(src_bytes));
 }
+// same through L1 (allocates the line in L1: for gathers with a hot head)
+__device__ __forceinline__ void cp_async16_ca(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc));
+}
 // 8-byte variant for shapes whose rows are not 16-byte aligned.
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, int src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc),

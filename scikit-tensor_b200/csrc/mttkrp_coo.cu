@@ -31,6 +31,11 @@ struct skt_coo {
     // sorted copy for output mode n: idx[n][m] (nnz int32 each) and vals[n]
     int *idx[SKT_MAX_NDIM][SKT_MAX_NDIM];
     double *vals[SKT_MAX_NDIM];
+    // index-panel blocking (see skt_coo_build): the copy for output mode n is sorted by (panel of the largest
+    // gathered mode, i_n) and idx[n][n] holds the VIRTUAL row  panel * shape[n] + i_n;  npanel[n] == 1: plain sort
+    int npanel[SKT_MAX_NDIM];
+    int panel_mode[SKT_MAX_NDIM];
+    long long panel_rows[SKT_MAX_NDIM];
     size_t bytes;
 };
 
@@ -86,7 +91,7 @@ constexpr int SD = 3;             // ring depth (stages)
 template <int GS, int NO, int SBB>
 constexpr size_t staged_warp_bytes() { return (size_t)SD * ((32 / GS) * SBB * NO * GS * 16 + (32 / GS) * (SBB * 16 + 16)); }
 
-template <int GS, int VPL, int VEC, int NO, bool STAGED = false, int SBB = 8>
+template <int GS, int VPL, int VEC, int NO, bool STAGED = false, int SBB = 8, bool CA = false>
 __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ CooParams p) {
     constexpr int NG = CT / GS;       // groups per CTA
     constexpr int CPL = VPL * VEC;    // columns per lane
@@ -184,7 +189,8 @@ __global__ void __launch_bounds__(CT) mttkrp_coo_kernel(const __grid_constant__ 
                     const int im = __shfl_sync(FULL, r_idx[buf][c][m], src);
                     const int mm = (NO <= 3 || m < p.nother) ? m : 0;
                     const double *rowp = p.U[mm] + (long long)((NO <= 3 || m < p.nother) ? im : 0) * R + ccol[0];
-                    cp_async16(st + ((gw * SBB + b) * NO + m) * ROWB + gl * 16, rowp, 16);
+                    if constexpr (CA) cp_async16_ca(st + ((gw * SBB + b) * NO + m) * ROWB + gl * 16, rowp);
+                    else cp_async16(st + ((gw * SBB + b) * NO + m) * ROWB + gl * 16, rowp, 16);
                 }
             }
             if (gl < SBB) {
@@ -398,6 +404,7 @@ struct AtomicParams {
     const double *vals;
     long long nnz;
     int ndim, R, mode;
+    int vmode, vdim;    // subscripts of mode `vmode` are stored as virtual rows panel * vdim + i (-1: none)
     double *M;
 };
 __global__ void mttkrp_coo_atomic_kernel(const __grid_constant__ AtomicParams p) {
@@ -407,8 +414,9 @@ __global__ void mttkrp_coo_atomic_kernel(const __grid_constant__ AtomicParams p)
     if (z >= p.nnz) return;
     double v = p.vals[z];
     for (int m = 0; m < p.ndim; ++m)
-        if (m != p.mode) v *= p.U[m][(long long)p.idx[m][z] * p.R + r];
-    atomicAdd(&p.M[(long long)p.idx[p.mode][z] * p.R + r], v);
+        if (m != p.mode) v *= p.U[m][(long long)(m == p.vmode ? p.idx[m][z] % p.vdim : p.idx[m][z]) * p.R + r];
+    const int orow = (p.mode == p.vmode) ? p.idx[p.mode][z] % p.vdim : p.idx[p.mode][z];
+    atomicAdd(&p.M[(long long)orow * p.R + r], v);
 }
 
 // <P, X> partial sums: each thread owns (non-zero, column) pairs in a fixed stride pattern.
@@ -419,6 +427,7 @@ struct InnerParams {
     const double *lambda;
     long long nnz;
     int ndim, R;
+    int vmode, vdim;
 };
 __global__ void __launch_bounds__(CT) coo_innerprod_kernel(const __grid_constant__ InnerParams p, double *out,
                                                            double *partials, unsigned int *counter) {
@@ -429,7 +438,7 @@ __global__ void __launch_bounds__(CT) coo_innerprod_kernel(const __grid_constant
         const long long z = t / p.R;
         const int r = (int)(t % p.R);
         double v = p.vals[z] * p.lambda[r];
-        for (int m = 0; m < p.ndim; ++m) v *= p.U[m][(long long)p.idx[m][z] * p.R + r];
+        for (int m = 0; m < p.ndim; ++m) v *= p.U[m][(long long)(m == p.vmode ? p.idx[m][z] % p.vdim : p.idx[m][z]) * p.R + r];
         s += v;
     }
     s = warp_sum(s);
@@ -468,6 +477,21 @@ __global__ void gather_kernel(const T *__restrict__ src, const unsigned int *__r
         dst[i] = src[perm[i]];
 }
 
+// sort key of the panelled copy: virtual row = (subscript of the panel mode / panel_rows) * dim + output subscript
+__global__ void panel_key_kernel(const int *__restrict__ out_idx, const int *__restrict__ pan_idx, long long n, int dim,
+                                 int panel_rows, int *__restrict__ key) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        key[i] = (pan_idx[i] / panel_rows) * dim + out_idx[i];
+}
+// M = sum over the panels' slabs, in panel order (deterministic)
+__global__ void panel_sum_kernel(const double *__restrict__ slabs, long long per, int npanel, double *__restrict__ M) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+        double s = slabs[i];
+        for (int q = 1; q < npanel; ++q) s += slabs[(long long)q * per + i];
+        M[i] = s;
+    }
+}
+
 int stream_blocks(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 8LL * sm_count())); }
 
 // lanes per group / vectors per lane / vector width for rank R (16-byte vectors need aligned factor rows)
@@ -504,19 +528,22 @@ int launch_coo_no(int nother, const CooParams &p, long long nctas, cudaStream_t 
 }
 
 // cp.async-staged variant (16-byte aligned factors, even rank <= 64, at most 3 gathered modes)
-template <int GS, int NO, int SBB>
-int launch_coo_staged_one(const CooParams &p, long long nctas, cudaStream_t st) {
+template <int GS, int NO, int SBB, bool CA>
+int launch_coo_staged_ca(const CooParams &p, long long nctas, cudaStream_t st) {
     constexpr int NG = CT / GS;
     const size_t carry = (size_t)((2 * NG * sizeof(int) + 7) / 8 * 8) + (size_t)2 * NG * GS * 2 * sizeof(double);
     const size_t smem = carry + (CT / 32) * staged_warp_bytes<GS, NO, SBB>();
-    static bool configured = false;
-    if (!configured) {
-        SKT_CUDA(cudaFuncSetAttribute(mttkrp_coo_kernel<GS, 1, 2, NO, true, SBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    mttkrp_coo_kernel<GS, 1, 2, NO, true, SBB><<<(unsigned)nctas, CT, smem, st>>>(p);
+    SKT_CUDA(cudaFuncSetAttribute(mttkrp_coo_kernel<GS, 1, 2, NO, true, SBB, CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mttkrp_coo_kernel<GS, 1, 2, NO, true, SBB, CA><<<(unsigned)nctas, CT, smem, st>>>(p);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
+}
+template <int GS, int NO, int SBB>
+int launch_coo_staged_one(const CooParams &p, long long nctas, cudaStream_t st) {
+    // SKT_COO_CA=1: gather the factor rows through L1 (cp.async.ca) -- an experiment switch; the default bypasses L1
+    const char *e = getenv("SKT_COO_CA");
+    if (e && e[0] == '1') return launch_coo_staged_ca<GS, NO, SBB, true>(p, nctas, st);
+    return launch_coo_staged_ca<GS, NO, SBB, false>(p, nctas, st);
 }
 
 template <int GS>
@@ -609,11 +636,12 @@ extern "C" int skt_coo_build(const int64_t *const *subs_d, const double *vals_d,
     int *keys_out = nullptr;
     unsigned int *perm_in = nullptr, *perm_out = nullptr, *bad = nullptr;
     void *tmp = nullptr;
+    int *pkey = nullptr;
     size_t tmp_bytes = 0;
     int rc = SKT_OK;
     auto cleanup = [&]() {
         for (int m = 0; m < ndim; ++m) cudaFree(base[m]);
-        cudaFree(keys_out); cudaFree(perm_in); cudaFree(perm_out); cudaFree(bad); cudaFree(tmp);
+        cudaFree(keys_out); cudaFree(perm_in); cudaFree(perm_out); cudaFree(bad); cudaFree(tmp); cudaFree(pkey);
     };
 #define BUILD_TRY(call)                                                                \
     do {                                                                               \
@@ -646,18 +674,52 @@ extern "C" int skt_coo_build(const int64_t *const *subs_d, const double *vals_d,
                                               perm_out, (int)std::min<int64_t>(nnz, INT32_MAX), 0, 32, st));
     BUILD_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 256));
 
+    // Index-panel blocking.  A gathered factor much larger than L2 (config 3: the 10 M x 16 factor of mode 0, 1.28 GB) is
+    // re-fetched from DRAM for almost every non-zero when the copy is sorted by the output subscript alone (ncu, round 1:
+    // 37 GB of DRAM reads for 5.4 GB of algorithmic bytes on mode 2).  Sorting by (panel of that mode, output subscript)
+    // walks the big factor one L2-sized panel at a time; every panel owns a slab of M ("virtual rows"
+    // panel * I_n + i_n -- the segmented-reduction kernel is unchanged) and the slabs are summed in panel order.  The
+    // number of panels is capped so that the slab traffic stays small against the non-zero stream.
+    long long want_rows = 1LL << 19;          // 64 MB of rank-16 FP64 factor rows per panel
+    long long cap_div = 32;                   // panels * I_n <= nnz / cap_div
+    if (const char *e = getenv("SKT_COO_PANEL_ROWS")) want_rows = std::max<long long>(1, atoll(e));
+    if (const char *e = getenv("SKT_COO_PANEL_CAP")) cap_div = std::max<long long>(0, atoll(e));
+    const char *pan_off = getenv("SKT_COO_PANELS");
+    const bool panels_on = !(pan_off && pan_off[0] == '0');
     for (int nmode = 0; nmode < ndim; ++nmode) {
         if (!(modes_mask & (1u << nmode))) continue;
+        int g = -1;
+        for (int m = 0; m < ndim; ++m)
+            if (m != nmode && (g < 0 || shape[m] > shape[g])) g = m;
+        long long P = panels_on && nnz > 0 ? (shape[g] + want_rows - 1) / want_rows : 1;
+        if (cap_div > 0) P = std::min<long long>(P, (nnz / cap_div) / std::max<long long>(shape[nmode], 1));
+        P = std::min<long long>(P, ((1LL << 31) - 2) / std::max<long long>(shape[nmode], 1));
+        if (P < 2) P = 1;
+        const long long prow = (shape[g] + P - 1) / P;
+        t->npanel[nmode] = (int)P;
+        t->panel_mode[nmode] = g;
+        t->panel_rows[nmode] = prow;
         int bits = 1;
-        while ((1LL << bits) < shape[nmode]) ++bits;
+        while ((1LL << bits) < shape[nmode] * P) ++bits;
         if (nnz > 0) {
-            BUILD_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const int *)base[nmode], keys_out,
+            const int *keys_in = base[nmode];
+            if (P > 1) {
+                if (!pkey) BUILD_TRY(cudaMalloc(&pkey, n * sizeof(int)));
+                panel_key_kernel<<<stream_blocks(nnz), 256, 0, st>>>(base[nmode], base[g], nnz, (int)shape[nmode], (int)prow, pkey);
+                keys_in = pkey;
+            }
+            BUILD_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out,
                                                       (const unsigned int *)perm_in, perm_out, (int)nnz, 0, bits, st));
         }
         for (int m = 0; m < ndim; ++m) {
             BUILD_TRY(cudaMalloc(&t->idx[nmode][m], n * sizeof(int)));
             t->bytes += n * sizeof(int);
-            if (nnz > 0) gather_kernel<int><<<stream_blocks(nnz), 256, 0, st>>>(base[m], perm_out, nnz, t->idx[nmode][m]);
+            if (nnz > 0) {
+                if (m == nmode && P > 1)      // the sorted keys ARE the virtual rows
+                    BUILD_TRY(cudaMemcpyAsync(t->idx[nmode][m], keys_out, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToDevice, st));
+                else
+                    gather_kernel<int><<<stream_blocks(nnz), 256, 0, st>>>(base[m], perm_out, nnz, t->idx[nmode][m]);
+            }
         }
         BUILD_TRY(cudaMalloc(&t->vals[nmode], n * sizeof(double)));
         t->bytes += n * sizeof(double);
@@ -721,10 +783,12 @@ extern "C" int skt_coo_build_host(const int64_t *const *subs_h, const double *va
 }
 
 extern "C" size_t skt_mttkrp_coo_workspace(const skt_coo *t, int rank, int mode) {
-    (void)mode;
     if (!t || rank < 1) return 0;
     const long long nctas = coo_nctas(t, rank, false);   // the scalar layout needs the most CTAs: covers both
-    return align_up((size_t)2 * nctas * sizeof(int), 256) + align_up((size_t)2 * nctas * rank * sizeof(double), 256);
+    size_t slabs = 0;                                     // panelled copy: one slab of M per panel
+    if (mode >= 0 && mode < t->ndim && t->npanel[mode] > 1)
+        slabs = align_up((size_t)t->npanel[mode] * t->shape[mode] * rank * sizeof(double), 256);
+    return align_up((size_t)2 * nctas * sizeof(int), 256) + align_up((size_t)2 * nctas * rank * sizeof(double), 256) + slabs;
 }
 
 extern "C" int skt_mttkrp_coo(const skt_coo *t, const double *const *U_d, int rank, int mode, double *M_d, void *ws_d,
@@ -750,18 +814,21 @@ extern "C" int skt_mttkrp_coo(const skt_coo *t, const double *const *U_d, int ra
     cudaStream_t st = (cudaStream_t)stream;
     const size_t need = skt_mttkrp_coo_workspace(t, rank, mode);
     SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
-    SKT_CUDA(cudaMemsetAsync(M_d, 0, (size_t)t->shape[mode] * rank * sizeof(double), st));
-    if (t->nnz == 0) return SKT_OK;
     const long long nctas = coo_nctas(t, rank, aligned);
     const long long nctas_ws = coo_nctas(t, rank, false);
+    const int npanel = t->npanel[mode];
+    const long long per = t->shape[mode] * (long long)rank;
     CooParams p;
+    p.carry_row = (int *)ws_d;
+    p.carry_val = (double *)((char *)ws_d + align_up((size_t)2 * nctas_ws * sizeof(int), 256));
+    // panelled copy: the kernel writes virtual rows (panel * I_n + i_n) into per-panel slabs, summed below
+    double *target = npanel > 1 ? (double *)((char *)p.carry_val + align_up((size_t)2 * nctas_ws * rank * sizeof(double), 256)) : M_d;
+    SKT_CUDA(cudaMemsetAsync(target, 0, (size_t)npanel * per * sizeof(double), st));
     p.rows = t->idx[mode][mode];
     p.vals = t->vals[mode];
     p.nnz = t->nnz;
     p.R = rank;
-    p.M = M_d;
-    p.carry_row = (int *)ws_d;
-    p.carry_val = (double *)((char *)ws_d + align_up((size_t)2 * nctas_ws * sizeof(int), 256));
+    p.M = target;
     int k = 0;
     for (int m = 0; m < t->ndim; ++m) {
         if (m == mode) continue;
@@ -776,8 +843,12 @@ extern "C" int skt_mttkrp_coo(const skt_coo *t, const double *const *U_d, int ra
     if (rc) return rc;
     const long long nslots = 2 * nctas;
     const long long threads = nslots * rank;
-    coo_fixup_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p.carry_row, p.carry_val, nslots, rank, M_d);
+    coo_fixup_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p.carry_row, p.carry_val, nslots, rank, target);
     SKT_LAUNCH_CHECK();
+    if (npanel > 1) {
+        panel_sum_kernel<<<stream_blocks(per), 256, 0, st>>>(target, per, npanel, M_d);
+        SKT_LAUNCH_CHECK();
+    }
     return SKT_OK;
 }
 
@@ -798,6 +869,7 @@ extern "C" int skt_mttkrp_coo_atomic(const skt_coo *t, const double *const *U_d,
     }
     p.vals = t->vals[src];
     p.nnz = t->nnz; p.ndim = t->ndim; p.R = rank; p.mode = mode; p.M = M_d;
+    p.vmode = t->npanel[src] > 1 ? src : -1; p.vdim = (int)t->shape[src];
     const long long threads = t->nnz * rank;
     mttkrp_coo_atomic_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p);
     SKT_LAUNCH_CHECK();
@@ -825,6 +897,7 @@ extern "C" int skt_coo_innerprod(const skt_coo *t, const double *const *U_d, con
         p.U[m] = U_d[m];
     }
     p.vals = t->vals[src]; p.lambda = lambda_d; p.nnz = t->nnz; p.ndim = t->ndim; p.R = rank;
+    p.vmode = t->npanel[src] > 1 ? src : -1; p.vdim = (int)t->shape[src];
     unsigned int *counter = (unsigned int *)ws_d;
     double *partials = (double *)((char *)ws_d + 256);
     SKT_CUDA(cudaMemsetAsync(counter, 0, 256, st));
