@@ -370,3 +370,35 @@ def test_empty_slabs_are_legal(K, dev):
     Us = [dev.to_device(np.random.rand(5, R)), dev.to_device(np.zeros((0, R))), dev.to_device(np.random.rand(3, R))]
     assert (dev.to_host(K.mttkrp_coo(coo, Us, R, 0)) == 0).all()
     assert K.mttkrp_coo(coo, Us, R, 1).shape == (0, R)
+
+
+@pytest.mark.parametrize('shape,nnz,R,prow', [
+    ((100, 80, 60), 5000, 16, 8), ((1000, 50, 20), 30000, 3, 100), ((64, 64, 64), 70000, 32, 1),
+    ((50, 40, 30, 20), 8000, 8, 7), ((20000, 300, 7), 60000, 64, 4096), ((300, 200), 4000, 4, 33),
+    ((5, 200000, 3), 50000, 33, 50000),
+])
+def test_sparse_panelled_copy_vs_oracle(K, dev, shape, nnz, R, prow, sparse_path, monkeypatch):
+    """Index-panel blocking (skt_coo_build sorts by (panel of the largest gathered mode, output subscript) and the
+    kernel writes one slab of M per panel): forced on small tensors, every mode against the oracle; the atomic
+    check kernel, <P,X> and the norm read the same panelled copy."""
+    monkeypatch.setenv('SKT_COO_PANEL_ROWS', str(prow))
+    monkeypatch.setenv('SKT_COO_PANEL_CAP', '0')
+    g = np.random.default_rng(abs(hash((shape, nnz, R, prow))) % (2 ** 31))
+    subs = [np.minimum((I * g.random(nnz) ** 2.0).astype(np.int64), I - 1) for I in shape]
+    vals = g.random(nnz) - 0.25
+    U = [g.random((I, R)) - 0.5 for I in shape]
+    coo = K.CooHandle(subs, vals, shape)
+    Ud = [dev.to_device(u) for u in U]
+    for n in range(len(shape)):
+        ref = orc.mttkrp_coo(tuple(subs), vals, shape, U, n)
+        got = dev.to_host(K.mttkrp_coo(coo, Ud, R, n))
+        assert relerr(got, ref) < TOL, (shape, n)
+        assert relerr(dev.to_host(K.mttkrp_coo(coo, Ud, R, n, atomic=True)), ref) < TOL, (shape, n)
+        again = dev.to_host(K.mttkrp_coo(coo, Ud, R, n))
+        assert (got == again).all()
+    lam = g.random(R)
+    ip = float(dev.to_host(K.coo_innerprod(coo, Ud, dev.to_device(lam), R))[0])
+    ref_ip = float(np.ravel(orc.kruskal_innerprod_coo(U, lam, tuple(subs), vals, shape))[0])
+    assert abs(ip - ref_ip) < 1e-10 * max(abs(ref_ip), 1.0)
+    assert abs(float(dev.to_host(K.coo_sumsq(coo))[0]) - float(np.sum(vals ** 2))) < 1e-10 * float(np.sum(vals ** 2))
+    coo.close()
