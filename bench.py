@@ -426,39 +426,103 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def device_powerlaw_coo(torch, shape, nnz, seed=0, lo_hi=None):
+    """BASELINE configs[2] generator (subscript = min(int(I * u^3), I - 1), u uniform) drawn on the device
+    with torch's generator -- same distribution as the host generator of the parity tests, no 6.4 GB host round trip."""
+    g = torch.Generator(device='cuda')
+    g.manual_seed(seed)
+    subs = []
+    for m, I in enumerate(shape):
+        u = torch.rand(nnz, dtype=torch.float64, device='cuda', generator=g)
+        if m == 0 and lo_hi is not None:                 # a rank's quantile range of the sharded mode
+            u = lo_hi[0] + u * (lo_hi[1] - lo_hi[0])
+        subs.append(torch.clamp((I * u ** 3.0).to(torch.int64), max=I - 1))
+        del u
+    vals = torch.rand(nnz, dtype=torch.float64, device='cuda', generator=g)
+    return subs, vals
+
+
+def time_sparse_mttkrp(torch, K, dev, coo, U, R, n, steps):
+    M = dev.empty((coo.shape[n], R))
+    for _ in range(3):
+        K.mttkrp_coo(coo, U, R, n, out=M)
+    ts = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        K.mttkrp_coo(coo, U, R, n, out=M)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def sparse_roofline(torch, K, dev, nnz, steps, variants=False):
+    """The three MTTKRPs of configs[2] (10M x 1M x 100K power law, rank 16) at `nnz` non-zeros: ms per mode, algorithmic
+    GB/s (nnz (4N + 8) + 8 R sum I bytes per mode) against measured HBM, and against the L2->SM gather
+    bound (every non-zero pulls two 128-byte factor rows through L2: 99 % of the index pairs are distinct)."""
+    R = 16
+    hbm_peak, peak_src = measured_peaks()
+    subs, vals = device_powerlaw_coo(torch, SPARSE_SHAPE, nnz)
+    torch.cuda.synchronize()
+    tic = time.perf_counter()
+    coo = K.CooHandle.from_device(subs, vals, SPARSE_SHAPE)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - tic
+    g = torch.Generator(device='cuda')
+    g.manual_seed(1)
+    U = [torch.rand(s, R, dtype=torch.float64, device='cuda', generator=g) for s in SPARSE_SHAPE]
+    b = alg_bytes_sparse(SPARSE_SHAPE, nnz, R)
+    gather_bytes = float(nnz) * 2 * 8 * R + float(nnz) * (4 * 3 + 8)
+    traffic = {}
+    prof = os.path.join(ROOT, 'profiles', 'sparse_mttkrp_traffic.json')
+    if os.path.exists(prof):
+        with open(prof) as f:
+            traffic = json.load(f)
+    out = {'kernel': 'mttkrp_coo_kernel (segmented reduction over the mode-sorted copy, cp.async-staged factor-row gathers)',
+           'bound': 'hbm', 'unit': UNIT, 'peak': hbm_peak, 'peak_source': peak_src, 'nnz': nnz, 'rank': R,
+           'shape': list(SPARSE_SHAPE), 'alg_bytes_per_launch': b, 'build_seconds_device_arrays': build_s,
+           'device_bytes': coo.device_bytes(), 'modes': {},
+           'l2_gather_bound': {'bytes_per_launch': gather_bytes,
+                               'note': 'bytes that must cross L2->SM per launch (two uncorrelated 128-byte factor rows + 20 '
+                                       'bytes of subscripts/value per non-zero); at the measured L2->SM ceiling of ~10-12 TB/s '
+                                       'this, not HBM, bounds the launch'}}
+    for n in range(3):
+        ms, best = time_sparse_mttkrp(torch, K, dev, coo, U, R, n, steps)
+        out['modes'][str(n)] = {'ms': ms, 'ms_best': best, 'achieved': b / ms / 1e6, 'frac': b / ms / 1e6 / hbm_peak,
+                                'l2_gather_TBps': gather_bytes / ms / 1e9,
+                                'traffic': (traffic.get(str(nnz), {}) or {}).get(str(n))}
+    if variants:
+        os.environ['SKT_COO_CA'] = '1'
+        out['variant_ca'] = {str(n): time_sparse_mttkrp(torch, K, dev, coo, U, R, n, steps)[0] for n in range(3)}
+        os.environ['SKT_COO_CA'] = '0'
+        coo.close()
+        os.environ['SKT_COO_PANELS'] = '0'
+        coo = K.CooHandle.from_device(subs, vals, SPARSE_SHAPE)
+        out['variant_no_panels'] = {str(n): time_sparse_mttkrp(torch, K, dev, coo, U, R, n, steps)[0] for n in range(3)}
+        os.environ['SKT_COO_PANELS'] = '1'
+        for rows in (1 << 18, 1 << 20):
+            coo.close()
+            os.environ['SKT_COO_PANEL_ROWS'] = str(rows)
+            coo = K.CooHandle.from_device(subs, vals, SPARSE_SHAPE)
+            out['variant_panel_rows_%d' % rows] = {str(n): time_sparse_mttkrp(torch, K, dev, coo, U, R, n, steps)[0] for n in range(3)}
+        os.environ.pop('SKT_COO_PANEL_ROWS')
+    coo.close()
+    del subs, vals, U
+    torch.cuda.empty_cache()
+    fr = [out['modes'][str(n)]['frac'] for n in range(3)]
+    out['achieved'] = float(np.mean([out['modes'][str(n)]['achieved'] for n in range(3)]))
+    out['frac'] = float(np.mean(fr))
+    return out
+
+
 def run_sparse(args):
     """Secondary bench (not the driver's line): BASELINE.json configs[2] generator, scaled by --nnz."""
     import torch
     from sktensor import _kernels as K
     from sktensor import _device as dev
-    nnz, R = args.nnz, 16
-    rng = np.random.default_rng(0)
-    subs = [np.minimum((I * rng.random(nnz) ** 3.0).astype(np.int64), I - 1) for I in SPARSE_SHAPE]
-    vals = rng.random(nnz)
-    tic = time.perf_counter()
-    coo = K.CooHandle(subs, vals, SPARSE_SHAPE)
-    torch.cuda.synchronize()
-    build_s = time.perf_counter() - tic
-    U = [torch.rand(s, R, dtype=torch.float64, device='cuda') for s in SPARSE_SHAPE]
-    hbm_peak, peak_src = measured_peaks()
-    out = {'metric': 'sparse_mttkrp_GBps', 'unit': UNIT, 'nnz': nnz, 'rank': R, 'shape': list(SPARSE_SHAPE),
-           'build_seconds': build_s, 'device_bytes': coo.device_bytes(), 'modes': {}}
-    for n in range(3):
-        M = dev.empty((SPARSE_SHAPE[n], R))
-        for _ in range(3):
-            K.mttkrp_coo(coo, U, R, n, out=M)
-        ts = []
-        for _ in range(args.steps):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            K.mttkrp_coo(coo, U, R, n, out=M)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = float(np.median(ts))
-        b = alg_bytes_sparse(SPARSE_SHAPE, nnz, R)
-        out['modes'][str(n)] = {'ms': ms, 'GBps_algorithmic': b / ms / 1e6, 'frac_of_hbm': b / ms / 1e6 / hbm_peak,
-                                'Mnnz_per_s': nnz / ms / 1e3}
+    out = sparse_roofline(torch, K, dev, args.nnz, args.steps if args.steps != 200 else 10, variants=args.variants)
+    out['metric'] = 'sparse_mttkrp_GBps'
     print(json.dumps(out))
 
 
@@ -565,6 +629,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='dense', choices=['dense', 'sparse', 'cfg3', 'cfg5'])
     ap.add_argument('--nnz', type=int, default=20000000)
+    ap.add_argument('--variants', action='store_true', help='sparse workload: also time the experiment switches')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

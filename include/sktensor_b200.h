@@ -228,6 +228,17 @@ SKT_API int skt_cp_update_finish_parts(const double *const *ex_parts_d, int worl
 SKT_API int skt_cp_update_cluster_slabs(const double *slabs_d, int nslabs, const double *P_d, int64_t rows, int rank,
                                 int ndim, int mode, int first_iter, double *G_d, double *U_d, double *lambda_d,
                                 double *ip_d, const double *normX2_d, double *fit_d, skt_stream stream);
+/* ---------------------------------------------------------------- symmetric eigensolver (nvecs)
+ * The `rank` leading eigenvectors of a symmetric n x n matrix (row-major, both triangles stored), eigenvalues in
+ * DESCENDING order, each column sign-fixed so that its largest-magnitude entry is positive when `flipsign` != 0:
+ * the arithmetic of sktensor.core.nvecs after the Gram product (sktensor/core.py:284-293: scipy.linalg.eigh with
+ * eigvals=(N-rank, N-1), columns reversed, then flipsign, core.py:297-306).  One kernel on one thread-block cluster:
+ * Householder tridiagonalisation with the matrix in distributed shared memory, Sturm multisection, inverse iteration,
+ * back-transformation.  W_d (k eigenvalues) and info_d (0 ok, -1 non-finite input) may be NULL.  n <= 2048.        */
+SKT_API size_t skt_symeig_workspace(int n, int k);
+SKT_API int skt_symeig_top(const double *A_d, int n, int k, int flipsign, double *W_d, double *U_d, int *info_d,
+                   void *ws_d, size_t ws_bytes, skt_stream stream);
+
 /* Leave `n` SMs out of the persistent grids (dense MTTKRP) so that a small kernel on another stream can run
  * beside them; returns the previous value.  0 restores the full chip.                                      */
 SKT_API int skt_set_reserved_sms(int n);

@@ -680,7 +680,7 @@ extern "C" int skt_coo_build(const int64_t *const *subs_d, const double *vals_d,
     // walks the big factor one L2-sized panel at a time; every panel owns a slab of M ("virtual rows"
     // panel * I_n + i_n -- the segmented-reduction kernel is unchanged) and the slabs are summed in panel order.  The
     // number of panels is capped so that the slab traffic stays small against the non-zero stream.
-    long long want_rows = 1LL << 19;          // 64 MB of rank-16 FP64 factor rows per panel
+    long long want_rows = 1LL << 18;          // 32 MB of rank-16 FP64 factor rows per panel (measured: 2^18 5.56 ms, 2^19 5.74, 2^20 6.13, none 6.99 on mode 2 of config 3)
     long long cap_div = 32;                   // panels * I_n <= nnz / cap_div
     if (const char *e = getenv("SKT_COO_PANEL_ROWS")) want_rows = std::max<long long>(1, atoll(e));
     if (const char *e = getenv("SKT_COO_PANEL_CAP")) cap_div = std::max<long long>(0, atoll(e));

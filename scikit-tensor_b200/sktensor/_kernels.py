@@ -110,6 +110,23 @@ class CooHandle(object):
         self.h = h
         self._subs = self._vals = None   # host copies are not retained
 
+    @classmethod
+    def from_device(cls, subs_d, vals_d, shape, modes_mask=0):
+        """Build from int64 subscript / float64 value tensors that already live on the device (``skt_coo_build``)."""
+        lib = _lib.load()
+        dev.require_cuda()
+        self = cls.__new__(cls)
+        self.shape = tuple(int(s) for s in shape)
+        self.ndim = len(self.shape)
+        self.nnz = int(vals_d.shape[0])
+        self._subs = self._vals = None
+        h = C.c_void_p()
+        ptrs = _lib.ptr_array([s.data_ptr() if self.nnz else None for s in subs_d])
+        _lib.check(lib.skt_coo_build(ptrs, dev.ptr(vals_d) if self.nnz else None, self.nnz, _lib.shape_array(self.shape),
+                                     self.ndim, modes_mask, dev.stream_ptr(), C.byref(h)))
+        self.h = h
+        return self
+
     def device_bytes(self):
         return int(_lib.load().skt_coo_device_bytes(self.h))
 
@@ -351,6 +368,27 @@ def unfold_gram(Xd, shape, mode):
     ws, wsz = dev.workspace('reduce').get(lib.skt_unfold_gram_workspace(shp, len(shape), mode))
     _lib.check(lib.skt_unfold_gram(dev.ptr(Xd), shp, len(shape), mode, dev.ptr(G), ws, wsz, dev.stream_ptr()))
     return G
+
+
+SYMEIG_MAX_N = 2048
+
+
+def symeig_top(G, k, flipsign=True, want_values=False):
+    """Leading ``k`` eigenvectors of the symmetric device matrix ``G`` (n x n), descending, sign-fixed
+    (core.py:284-306) -> device (n x k) [and the k eigenvalues].  One cluster kernel, no host synchronisation."""
+    lib = _lib.load()
+    n = int(G.shape[0])
+    k = int(k)
+    need = lib.skt_symeig_workspace(n, k)
+    if need == 0:
+        _lib.check(-6 if n > SYMEIG_MAX_N else -1)
+    U = dev.empty((n, k))
+    W = dev.empty((k,)) if want_values else None
+    info = dev.empty((1,), np.int32)
+    ws, wsz = dev.workspace('eig').get(need)
+    _lib.check(lib.skt_symeig_top(dev.ptr(G), n, k, 1 if flipsign else 0, dev.ptr(W), dev.ptr(U), dev.ptr(info), ws, wsz,
+                                  dev.stream_ptr()))
+    return (U, W, info) if want_values else (U, info)
 
 
 def probe_fp64_peaks():

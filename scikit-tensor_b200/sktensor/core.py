@@ -133,11 +133,12 @@ def nvecs(X, n, rank, do_flipsign=True, dtype=float):
     """Leading ``rank`` eigenvectors of ``X_(n) X_(n)^T`` in descending order (core.py:275-294).
 
     Dense tensors: the I_n x I_n Gram is accumulated on the device straight from the
-    C-order tensor (``skt_unfold_gram``; no unfolding copy) and the small symmetric
-    eigenproblem is solved there (cuSOLVER through ``torch.linalg.eigh`` -- a library
-    eigensolver stands in for the reference's LAPACK call).  Sparse tensors follow the
-    reference's ARPACK route on the host (core.py:280-283); that branch is not on the
-    accelerated path yet.
+    C-order tensor (``skt_unfold_gram``; no unfolding copy) and its leading eigenvectors
+    come from the cluster eigensolver ``skt_symeig_top`` (tridiagonalisation in distributed
+    shared memory, Sturm multisection, inverse iteration; order and sign fixed on the
+    device).  Modes longer than 2048 exceed that kernel's shared-memory design and take the
+    library eigensolver instead.  Sparse tensors follow the reference's ARPACK route on the
+    host (core.py:280-283); that branch is not on the accelerated path yet.
     """
     from .dtensor import dtensor
     rank = int(rank)
@@ -146,9 +147,7 @@ def nvecs(X, n, rank, do_flipsign=True, dtype=float):
         from . import _kernels as K
         Xd = X._device_tensor()
         G = K.unfold_gram(Xd, X.shape, n)
-        t = dev.torch()
-        _, V = t.linalg.eigh(G)
-        U = dev.to_host(V[:, -rank:].flip(1).contiguous())
+        return np.array(dev.to_host(device_nvecs(G, rank, do_flipsign)), dtype=float)
     else:
         from scipy.sparse import csr_matrix
         from scipy.sparse.linalg import eigsh
@@ -157,6 +156,24 @@ def nvecs(X, n, rank, do_flipsign=True, dtype=float):
         U = np.array(V[:, ::-1])
     U = np.array(U, dtype=float)
     return flipsign(U) if do_flipsign else U
+
+
+def device_nvecs(G, rank, do_flipsign=True):
+    """Leading eigenvectors of the symmetric device matrix ``G`` -> device (n x rank), descending, sign-fixed."""
+    from . import _device as dev
+    from . import _kernels as K
+    n = int(G.shape[0])
+    if n <= K.SYMEIG_MAX_N:
+        U, info = K.symeig_top(G, rank, flipsign=do_flipsign)
+        return U
+    t = dev.torch()
+    _, V = t.linalg.eigh(G)
+    V = V[:, -rank:].flip(1).contiguous()
+    if do_flipsign:
+        rows = V.abs().argmax(dim=0)
+        sgn = t.where(V[rows, t.arange(V.shape[1], device=V.device)] < 0, -1.0, 1.0)
+        V = V * sgn
+    return V
 
 
 def center_matrix(X):

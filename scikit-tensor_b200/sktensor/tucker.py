@@ -4,15 +4,16 @@ Same signature, defaults (note ``maxIter``, not ``max_iter``) and return value `
 as the reference (tucker.py:36-123).  For dense tensors the whole loop stays on the device:
 the tensor is uploaded once, every TTM of the chain is one ``skt_ttm_dense`` call on the
 free (L, I_n, T) view (no transpose/reshape copies), the Gram of the small projected
-tensor comes from ``skt_unfold_gram`` and only its symmetric eigenproblem goes to a library
-eigensolver.
+tensor comes from ``skt_unfold_gram`` and its leading eigenvectors from the cluster
+eigensolver ``skt_symeig_top``; the factors stay on the device between modes and the host
+reads one scalar (the core's norm) per iteration.
 """
 import logging
 import time
 
 import numpy as np
 
-from .core import flipsign, norm, nvecs, ttm
+from .core import device_nvecs, flipsign, norm, nvecs, ttm
 from .dtensor import dtensor
 from .pyutils import is_number
 
@@ -106,10 +107,7 @@ def _hooi_dense_device(X, rank, U, maxIter, conv):
                     Yd, yshape = K.ttm_dense(Yd, yshape, Ud[m], layout.index(m), True)
             # U_n = leading eigenvectors of Utilde_(n) Utilde_(n)^T, descending, sign-fixed (core.py:275-306)
             G = K.unfold_gram(Yd, yshape, layout.index(n))
-            _, V = t.linalg.eigh(G)
-            Un = flipsign(np.array(dev.to_host(V[:, -rank[n]:].flip(1).contiguous())))
-            U[n] = Un
-            Ud[n] = dev.to_device(Un)
+            Ud[n] = device_nvecs(G, rank[n])
         core_d, core_shape = K.ttm_dense(Yd, yshape, Ud[N - 1], layout.index(N - 1), True)
         normcore2 = float(dev.to_host(K.sumsq(core_d))[0])
         fit = 1 - (np.sqrt(max(normX2 - normcore2, 0.0)) / normX)
@@ -117,6 +115,9 @@ def _hooi_dense_device(X, rank, U, maxIter, conv):
         _log.debug('[%3d] fit: %.5f | delta: %7.1e | secs: %.5f' % (itr, fit, fitchange, time.perf_counter() - tic))
         if itr > 1 and fitchange < conv:
             break
+    for n in range(N):                       # the caller's list is filled in place, like the reference's U[n] = ...
+        if Ud[n] is not None:
+            U[n] = np.array(dev.to_host(Ud[n]), dtype=float)
     # back to the reference's mode order (the last sweep's chain left the modes rotated)
     core = np.ascontiguousarray(np.transpose(dev.to_host(core_d), [layout.index(m) for m in range(N)]))
     return dtensor(core), fit
