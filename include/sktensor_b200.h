@@ -38,7 +38,9 @@ extern "C" {
 #endif
 
 #define SKT_MAX_NDIM 8
-#define SKT_MAX_RANK 64          /* solve / update kernels; MTTKRP kernels accept any rank */
+#define SKT_MAX_RANK 64          /* single-CTA / cluster solve and update kernels                                    */
+#define SKT_MAX_WIDE_RANK 512    /* generic solve path (skt_gram / skt_hadamard_pinv / skt_solve_stats /
+                                    skt_normalise_gram / skt_cp_fit) assembled from the large-matrix kernels       */
 
 #define SKT_OK            0
 #define SKT_EINVAL       -1      /* bad argument (NULL, ndim, mode, rank ...)          */

@@ -9,6 +9,17 @@
 #include "pinv.cuh"
 
 namespace skt {
+// rank > SKT_MAX_RANK: the generic path of cpals_wide.cu behind the same entry points
+size_t wide_gram_ws(long long rows, int R);
+size_t wide_pass_ws(long long rows, int R);
+int wide_check_rank(int R);
+int wide_gram(const double *U, long long rows, int R, double *G, void *ws, size_t ws_bytes, cudaStream_t st);
+int wide_hadamard_pinv(const double *G, int ndim, int R, int mode, double *P, int *info, cudaStream_t st);
+int wide_solve_stats(const double *M, const double *P, long long rows, int R, int first_iter, double *Unew, double *colstat,
+                     void *ws, size_t ws_bytes, cudaStream_t st);
+int wide_normalise_gram(double *U, const double *colstat, long long rows, int R, int first_iter, double *lambda, double *G,
+                        const double *Mip, double *ip, void *ws, size_t ws_bytes, cudaStream_t st);
+
 namespace {
 
 constexpr int ROWS = 64;        // factor rows staged per tile
@@ -326,9 +337,15 @@ int launch_factor_pass(double *U, const double *colstat, long long rows, int R, 
 
 using namespace skt;
 
-extern "C" size_t skt_gram_workspace(int64_t rows, int rank) { (void)rank; return pass_ws_bytes(rows, MAXR * MAXR + 1); }
-extern "C" size_t skt_normalise_gram_workspace(int64_t rows, int rank) { (void)rank; return pass_ws_bytes(rows, MAXR * MAXR + 1); }
-extern "C" size_t skt_solve_stats_workspace(int64_t rows, int rank) { (void)rank; return pass_ws_bytes(rows, MAXR); }
+extern "C" size_t skt_gram_workspace(int64_t rows, int rank) {
+    return rank > MAXR ? wide_gram_ws(rows, rank) : pass_ws_bytes(rows, MAXR * MAXR + 1);
+}
+extern "C" size_t skt_normalise_gram_workspace(int64_t rows, int rank) {
+    return rank > MAXR ? std::max(wide_gram_ws(rows, rank), wide_pass_ws(rows, rank)) : pass_ws_bytes(rows, MAXR * MAXR + 1);
+}
+extern "C" size_t skt_solve_stats_workspace(int64_t rows, int rank) {
+    return rank > MAXR ? wide_pass_ws(rows, rank) : pass_ws_bytes(rows, MAXR);
+}
 extern "C" size_t skt_sumsq_workspace(int64_t n) {
     (void)n;
     return 256 + align_up((size_t)4 * sm_count() * sizeof(double), 256);
@@ -337,6 +354,10 @@ extern "C" size_t skt_sumsq_workspace(int64_t n) {
 extern "C" int skt_gram(const double *U_d, int64_t rows, int rank, double *G_d, void *ws_d, size_t ws_bytes,
                         skt_stream stream) {
     SKT_REQUIRE((U_d || rows == 0) && G_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
+    if (rank > MAXR) {
+        const int rcw = wide_check_rank(rank);
+        return rcw ? rcw : wide_gram(U_d, rows, rank, G_d, ws_d, ws_bytes, (cudaStream_t)stream);
+    }
     int rc = check_rank(rank);
     if (rc) return rc;
     return launch_factor_pass(const_cast<double *>(U_d), nullptr, rows, rank, 0, 0, nullptr, G_d, nullptr, nullptr, ws_d,
@@ -348,6 +369,11 @@ extern "C" int skt_normalise_gram(double *U_d, const double *colstat_d, int64_t 
                                   size_t ws_bytes, skt_stream stream) {
     SKT_REQUIRE((U_d || rows == 0) && colstat_d && lambda_d && G_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
     SKT_REQUIRE((Mip_d == nullptr) == (ip_d == nullptr) || rows == 0, SKT_EINVAL, "Mip_d and ip_d must be given together");
+    if (rank > MAXR) {
+        const int rcw = wide_check_rank(rank);
+        return rcw ? rcw : wide_normalise_gram(U_d, colstat_d, rows, rank, first_iter, lambda_d, G_d, Mip_d, ip_d, ws_d, ws_bytes,
+                                               (cudaStream_t)stream);
+    }
     int rc = check_rank(rank);
     if (rc) return rc;
     return launch_factor_pass(U_d, colstat_d, rows, rank, 1, first_iter, lambda_d, G_d, Mip_d, ip_d, ws_d, ws_bytes,
@@ -357,6 +383,10 @@ extern "C" int skt_normalise_gram(double *U_d, const double *colstat_d, int64_t 
 extern "C" int skt_solve_stats(const double *M_d, const double *P_d, int64_t rows, int rank, int first_iter,
                                double *Unew_d, double *colstat_d, void *ws_d, size_t ws_bytes, skt_stream stream) {
     SKT_REQUIRE((M_d || rows == 0) && P_d && (Unew_d || rows == 0) && colstat_d && rows >= 0, SKT_EINVAL, "NULL argument or negative rows");
+    if (rank > MAXR) {
+        const int rcw = wide_check_rank(rank);
+        return rcw ? rcw : wide_solve_stats(M_d, P_d, rows, rank, first_iter, Unew_d, colstat_d, ws_d, ws_bytes, (cudaStream_t)stream);
+    }
     int rc = check_rank(rank);
     if (rc) return rc;
     const size_t need = pass_ws_bytes(rows, MAXR);
@@ -392,6 +422,10 @@ extern "C" int skt_hadamard_pinv(const double *G_d, int ndim, int rank, int mode
                                  skt_stream stream) {
     SKT_REQUIRE(G_d && P_d && info_d, SKT_EINVAL, "NULL argument");
     SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM && mode >= -1 && mode < ndim, SKT_EINVAL, "bad ndim/mode");
+    if (rank > MAXR) {
+        const int rcw = wide_check_rank(rank);
+        return rcw ? rcw : wide_hadamard_pinv(G_d, ndim, rank, mode, P_d, info_d, (cudaStream_t)stream);
+    }
     int rc = check_rank(rank);
     if (rc) return rc;
     const size_t smem = pinv_smem_doubles(rank) * sizeof(double);
@@ -410,7 +444,7 @@ extern "C" int skt_cp_fit(const double *G_d, int ndim, int rank, const double *l
                           const double *normX2_d, double *out_d, skt_stream stream) {
     SKT_REQUIRE(G_d && lambda_d && ip_d && normX2_d && out_d, SKT_EINVAL, "NULL argument");
     SKT_REQUIRE(ndim >= 1 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "bad ndim");
-    int rc = check_rank(rank);
+    int rc = wide_check_rank(rank);          // the fit kernel loops over R x R: any rank the solve path accepts
     if (rc) return rc;
     cp_fit_kernel<<<1, NT, 0, (cudaStream_t)stream>>>(G_d, ndim, rank, lambda_d, ip_d, normX2_d, out_d);
     SKT_LAUNCH_CHECK();

@@ -45,6 +45,7 @@ struct EigParams {
     double *Ag;       // [C][ncl * n] column blocks when they do not fit shared memory (else null)
     double *Fg;       // [C][kc * fslot] factor arrays when they do not fit shared memory (else null)
     int C, ncl, kc, L, ldv, z_smem, iters;
+    unsigned long long *prof;   // optional phase timestamps (globaltimer ns) written by CTA 0, SKT_EIG_PROF=1
 };
 
 // shared-memory layout in doubles (host and device agree through this function)
@@ -95,6 +96,13 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
     const int c = (int)crank;
 
+    auto stamp = [&](int slot) {
+        if (p.prof && c == 0 && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+            p.prof[slot] = t;
+        }
+    };
     auto cluster_sync = [&]() {
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -136,6 +144,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     __syncthreads();
     cluster_sync();                       // every CTA is resident before the first remote store
 
+    stamp(0);
     bool has_pend = false;
     for (int kk = 0; kk + 1 < n; ++kk) {
         const int cur = kk & 1, prev = cur ^ 1;
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
             }
             for (int i = kk + 1 + tid; i < n; i += ET) {
                 const double v = (i == kk + 1) ? 1.0 : col[i] * scal;
-                p.Vg[(size_t)kk * p.ldv + i] = v;
+                col[i] = v;                                // the reflector replaces the eliminated column (dumped to Vg below)
                 for (int r = 0; r < C; ++r) remote(vc, r)[i] = v;
             }
             if (tid < C) {
@@ -210,6 +219,12 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
         }
         __syncthreads();
     }
+    // the reflectors, kept in place in their owners' columns, go to global memory for the back-transformation
+    for (int t = warp; t < ncl; t += EW) {
+        const int j = c + C * t;
+        if (j >= n - 1) break;
+        for (int i = j + 1 + lane; i < n; i += 32) p.Vg[(size_t)j * p.ldv + i] = Ablk[(size_t)t * n + i];
+    }
     // last diagonal entry (the final step's reflector is always the identity, so nothing is pending)
     if (c == (n - 1) % C && tid < C) {
         const double dl = Ablk[(size_t)((n - 1) / C) * n + (n - 1)];
@@ -217,6 +232,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
         if (n >= 1) { remote(ee, tid)[n - 1] = 0.0; remote(tt, tid)[n - 1] = 0.0; }
     }
     cluster_sync();
+    stamp(1);
 
     // ================================================================== 2. eigenvalues (multisection on Sturm counts)
     const double EPS = DBL_EPSILON, SAFMIN = DBL_MIN;
@@ -281,6 +297,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     }
     __threadfence();
     cluster_sync();
+    stamp(2);
     for (int j = tid; j < k; j += ET) lam[j] = __ldcg(p.lamg + j);
     __syncthreads();
     const double onenrm = fmax(bnorm, SAFMIN);
@@ -299,8 +316,9 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     const int fslot = fslot_doubles(n);
     double *Freg = p.Fg ? p.Fg + (size_t)c * kc * fslot : big;
     double *Zs = p.z_smem ? big + (p.Fg ? 0 : (size_t)kc * fslot) : p.Zg;     // CTA 0's orthogonalisation copy
+    const int myk = (k > c) ? (k - c + C - 1) / C : 0;                        // eigenvalues owned by this CTA: q = c + C s
     double alast = 0.0;
-    if (tid < kc && c + C * tid < k) {
+    if (tid < myk) {
         // ---- dlagtf: T - lambda I = P L U, one thread per eigenvalue
         const int q = c + C * tid;
         double *ra = Freg + (size_t)tid * fslot, *bb = ra + n, *cc = bb + n, *d2 = cc + n;
@@ -330,20 +348,36 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
         amax = fmax(amax, fabs(ai));
         alast = fabs(ai);
         const double tol = (amax == 0.0) ? EPS : fmax(amax * EPS, SAFMIN / EPS);
-        for (int i = 0; i < n; ++i) {
+        // pivots below tol are replaced by +-tol (dlagts, job = -1); the reciprocals are taken by a whole warp below
+        d2[n - 1] = tol;                        // (d2 has n slots, U uses the first n - 2): parked for that pass
+    }
+    __syncthreads();
+    // reciprocal pivots and start vectors: every thread, warp per eigenvalue
+    for (int s = warp; s < myk; s += EW) {
+        const int q = c + C * s;
+        double *ra = Freg + (size_t)s * fslot, *d2 = ra + 3 * n, *z = ra + 4 * n;
+        const double tol = d2[n - 1];
+        for (int i = lane; i < n; i += 32) {
             const double a = ra[i];
             ra[i] = 1.0 / (fabs(a) < tol ? (a < 0.0 ? -tol : tol) : a);
+            z[i] = hash_uniform((unsigned long long)i, (unsigned long long)q);
         }
-        double *z = d2 + n;
-        for (int i = 0; i < n; ++i) z[i] = hash_uniform((unsigned long long)i, (unsigned long long)q);
     }
+    __syncthreads();
+    stamp(3);
     for (int it = 0; it < p.iters; ++it) {
-        if (tid < kc && c + C * tid < k) {
-            const int q = c + C * tid;
+        for (int s = warp; s < myk; s += EW) {
+            const double *z = Freg + (size_t)s * fslot + 4 * n;
+            double a = 0.0;
+            for (int i = lane; i < n; i += 32) a += fabs(z[i]);
+            a = warp_sum(a);
+            if (lane == 0) wb[s] = a;            // wb (2n doubles, free after phase 1) as per-eigenvalue scratch: kc <= n
+        }
+        __syncthreads();
+        if (tid < myk) {
             double *ra = Freg + (size_t)tid * fslot, *bb = ra + n, *cc = bb + n, *d2 = cc + n, *z = d2 + n;
             const unsigned char *sw = reinterpret_cast<const unsigned char *>(d2 + 2 * n);
-            double nrm1 = 0.0;
-            for (int i = 0; i < n; ++i) nrm1 += fabs(z[i]);
+            const double nrm1 = wb[tid];
             const double scl = n * onenrm * fmax(EPS, alast) / (nrm1 == 0.0 ? 1.0 : nrm1);
             // forward: apply P L
             double yp = z[0] * scl;
@@ -369,9 +403,15 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
                 y2 = y1; y1 = t;
                 zmax = fmax(zmax, fabs(t));
             }
-            const double sc = (zmax > 0.0 && zmax < DBL_MAX) ? 1.0 / zmax : 1.0;
+            wb[tid] = (zmax > 0.0 && zmax < DBL_MAX) ? 1.0 / zmax : 1.0;
+        }
+        __syncthreads();
+        for (int s = warp; s < myk; s += EW) {
+            const int q = c + C * s;
+            const double *z = Freg + (size_t)s * fslot + 4 * n;
+            const double sc = wb[s];
             double *zg = p.Zg + (size_t)q * n;
-            for (int i = 0; i < n; ++i) zg[i] = z[i] * sc;
+            for (int i = lane; i < n; i += 32) zg[i] = z[i] * sc;
         }
         __threadfence();
         cluster_sync();
@@ -414,12 +454,16 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
         }
         __threadfence();
         cluster_sync();
-        if (it + 1 < p.iters && tid < kc && c + C * tid < k) {
-            const int q = c + C * tid;
-            double *z = Freg + (size_t)tid * fslot + 4 * n;
-            const double *zg = p.Zg + (size_t)q * n;
-            for (int i = 0; i < n; ++i) z[i] = __ldcg(zg + i);
+        if (it + 1 < p.iters) {
+            for (int s = warp; s < myk; s += EW) {
+                const int q = c + C * s;
+                double *z = Freg + (size_t)s * fslot + 4 * n;
+                const double *zg = p.Zg + (size_t)q * n;
+                for (int i = lane; i < n; i += 32) z[i] = __ldcg(zg + i);
+            }
+            __syncthreads();
         }
+        stamp(4 + it);
     }
 
     // ================================================================== 4. back-transformation, order, sign
@@ -434,6 +478,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
             if (q >= k) break;
             for (int i = tid; i < n; i += ET) zv[(size_t)s * n + i] = __ldcg(p.Zg + (size_t)q * n + i);
         }
+        __syncthreads();
         const int nref = n - 2;                          // reflectors 0 .. n-3 (the last step's is the identity)
         const int nchunk = nref > 0 ? (nref + RB - 1) / RB : 0;
         auto issue_chunk = [&](int ch) {                 // chunk ch holds reflectors hi .. hi-RB+1, hi = nref-1 - ch*RB
@@ -500,6 +545,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
         }
         if (p.info && bad && lane == 0) atomicExch(p.info, -1);
     }
+    stamp(9);
     cluster_sync();          // peers' shared memory stays mapped until every remote access has completed
 }
 
@@ -609,6 +655,13 @@ extern "C" int skt_symeig_top(const double *A_d, int n, int k, int flipsign, dou
     p.C = pl.C; p.ncl = pl.ncl; p.kc = pl.kc; p.L = pl.L; p.ldv = pl.ldv; p.z_smem = pl.z_smem;
     p.iters = 3;
     if (const char *e = getenv("SKT_EIG_ITERS")) p.iters = std::max(1, atoi(e));
+    p.prof = nullptr;
+    const char *pe = getenv("SKT_EIG_PROF");
+    const bool prof = pe && pe[0] == '1';
+    if (prof) {
+        SKT_CUDA(cudaMalloc((void **)&p.prof, 16 * sizeof(unsigned long long)));
+        SKT_CUDA(cudaMemset(p.prof, 0, 16 * sizeof(unsigned long long)));
+    }
     if (info_d) SKT_CUDA(cudaMemsetAsync(info_d, 0, sizeof(int), st));
     SKT_CUDA(cudaFuncSetAttribute(symeig_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin_bytes()));
     if (pl.C > 8) SKT_CUDA(cudaFuncSetAttribute(symeig_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -623,5 +676,15 @@ extern "C" int skt_symeig_top(const double *A_d, int n, int k, int flipsign, dou
     cfg.attrs = at; cfg.numAttrs = 1;
     SKT_CUDA(cudaLaunchKernelEx(&cfg, symeig_cluster_kernel, p));
     SKT_LAUNCH_CHECK();
+    if (prof) {      // debugging aid: phase timestamps of CTA 0 (synchronises)
+        unsigned long long h[16];
+        SKT_CUDA(cudaStreamSynchronize(st));
+        SKT_CUDA(cudaMemcpy(h, p.prof, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(p.prof);
+        fprintf(stderr, "[symeig n=%d k=%d C=%d L=%d] tridiag %.1f us | eigenvalues %.1f | factor %.1f | iterations", n, k, pl.C,
+                pl.L, (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3);
+        for (int i = 0; i < p.iters && i < 5; ++i) fprintf(stderr, " %.1f", (h[4 + i] - h[3 + i]) * 1e-3);
+        fprintf(stderr, " | back-transform %.1f us\n", (h[9] - h[3 + std::min(p.iters, 5)]) * 1e-3);
+    }
     return SKT_OK;
 }

@@ -298,6 +298,8 @@ class CpAlsEngine(object):
         self.R = R = int(rank)
         if R < 1:
             raise ValueError('rank must be a positive integer')
+        if R > 512:
+            raise ValueError('rank %d is beyond the 512 components the solve kernels of this build support' % R)
 
         # ---- which slab is ours
         if isinstance(X, LocalShard):
@@ -372,8 +374,10 @@ class CpAlsEngine(object):
         self.cluster = [bool(use_cluster and self.fused[m] and be.update_cluster_fits(self.lshape[m], R)) for m in range(N)]
         self._pinv_pending = [None] * N
 
-        # ---- every other mode (sharded, or too tall for shared memory) takes the exchange form when available
-        self.exchange = hasattr(be, 'update_exchange') and os.environ.get('SKT_NO_EXCHANGE_UPDATE', '0') != '1'
+        # ---- every other mode (sharded, or too tall for shared memory) takes the exchange form when available; ranks
+        # beyond the single-CTA solve kernels (> 64) run the generic gram / pinv / solve / normalise entry points instead
+        self.exchange = hasattr(be, 'update_exchange') and os.environ.get('SKT_NO_EXCHANGE_UPDATE', '0') != '1' and \
+            R <= getattr(be, 'max_exchange_rank', 64)
         if self.exchange:
             rec = be.exchange_record(R)
             self.ex = be.zeros((rec,))
