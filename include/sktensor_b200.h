@@ -230,6 +230,21 @@ SKT_API int skt_cp_update_finish_parts(const double *const *ex_parts_d, int worl
 SKT_API int skt_cp_update_cluster_slabs(const double *slabs_d, int nslabs, const double *P_d, int64_t rows, int rank,
                                 int ndim, int mode, int first_iter, double *G_d, double *U_d, double *lambda_d,
                                 double *ip_d, const double *normX2_d, double *fit_d, skt_stream stream);
+/* ---------------------------------------------------------------- COO de-duplication (accumfun)
+ * sptensor(subs, vals, accumfun=...) merges duplicate coordinates (sktensor/sptensor.py:80-84 -> utils.accum,
+ * sktensor/utils.py:5-26: lexsort with the LAST mode most significant, `func` over every run).  Host arrays in, host
+ * arrays out: the distinct coordinates come back as linear keys  sum_m (sub_m - base_m) * prod_{m' < m} extent_m'
+ * in ascending order (the reference's output order) with the reduced values; op 0 = sum, 1 = max, 2 = min, applied
+ * in storage order.  out_keys_h / out_vals_h must hold nnz entries.                                              */
+SKT_API int skt_coo_accumulate_host(const int64_t *const *subs_h, const double *vals_h, int64_t nnz, const int64_t *base,
+                            const int64_t *extent, int ndim, int op, uint64_t *out_keys_h, double *out_vals_h,
+                            int64_t *out_nnz);
+/* ids_d[i] = rank of keys_d[i] among the distinct keys (ascending); *ndistinct = their number.  Used to number the
+ * non-empty columns of a sparse unfolding (sptensor.unfold, sktensor/sptensor.py:197-214) for the sparse nvecs
+ * operator.  Synchronises the stream.                                                                         */
+SKT_API int skt_compact_keys(const uint64_t *keys_d, int64_t n, int key_bits, int32_t *ids_d, int64_t *ndistinct,
+                     skt_stream stream);
+
 /* ---------------------------------------------------------------- symmetric eigensolver (nvecs)
  * The `rank` leading eigenvectors of a symmetric n x n matrix (row-major, both triangles stored), eigenvalues in
  * DESCENDING order, each column sign-fixed so that its largest-magnitude entry is positive when `flipsign` != 0:

@@ -32,6 +32,7 @@ constexpr int ET = 512;          // threads per CTA
 constexpr int EW = ET / 32;
 constexpr int RB = 8;            // reflectors per chunk of the back-transformation ring
 constexpr int EIG_MAX_N = 2048;
+constexpr int ZCAP_MAX = 64;      // vectors per back-transformation pass (sizes the small WY scratch)
 
 struct EigParams {
     const double *A;
@@ -44,13 +45,13 @@ struct EigParams {
     double *lamg;     // [k]
     double *Ag;       // [C][ncl * n] column blocks when they do not fit shared memory (else null)
     double *Fg;       // [C][kc * fslot] factor arrays when they do not fit shared memory (else null)
-    int C, ncl, kc, L, ldv, z_smem, iters;
+    int C, ncl, kc, L, ldv, z_smem, iters, zcap;
     unsigned long long *prof;   // optional phase timestamps (globaltimer ns) written by CTA 0, SKT_EIG_PROF=1
 };
 
 // shared-memory layout in doubles (host and device agree through this function)
 struct EigLayout {
-    int vb, wb, pb, dd, ee, tt, lam, grp, red, nbs, big;
+    int vb, wb, pb, dd, ee, tt, lam, grp, red, nbs, wy, big;
     size_t big_doubles;      // capacity of the phase-overlaid region
     size_t total_bytes;
 };
@@ -68,6 +69,7 @@ __host__ __device__ inline EigLayout eig_layout(int n, int k, size_t big_doubles
     L.grp = o; o += (k + 1) / 2 + 1;        // ints
     L.red = o; o += 2 * EW + 2;
     L.nbs = o; o += (ET + 1) / 2 + 1;       // ints (one per multisection slot)
+    L.wy = o; o += 2 * RB * RB + 2 * RB * ZCAP_MAX;   // compact-WY scratch: G, T, V^T z, y
     o = (o + 1) & ~1;                       // 16-byte alignment of the big region
     L.big = o;
     L.big_doubles = big_doubles;
@@ -82,6 +84,19 @@ __device__ __forceinline__ double hash_uniform(unsigned long long i, unsigned lo
     h ^= h >> 32;
     return (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0;
 }
+
+// 1 / x from the hardware approximation and two Newton steps (full precision, not correctly rounded): the Sturm and
+// LU recurrences are chains of dependent divisions, and an IEEE division costs ~200 cycles of latency per step
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;\n" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_constant__ EigParams p) {
     extern __shared__ __align__(16) double esm[];
@@ -145,42 +160,52 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     cluster_sync();                       // every CTA is resident before the first remote store
 
     stamp(0);
+    // wb doubles as the second p buffer: the rank-2 update of step kk-1, A -= v w^T + w v^T with w = p + al v, is applied
+    // on the fly from (v, p, al) during step kk's pass, so w is never materialised and no CTA-wide reduction is needed
     bool has_pend = false;
+    double alo = 0.0;                              // al of the pending update (identical in every thread)
     for (int kk = 0; kk + 1 < n; ++kk) {
         const int cur = kk & 1, prev = cur ^ 1;
-        double *vc = vb + cur * n, *vo = vb + prev * n, *wo = wb + prev * n;
+        double *vc = vb + cur * n, *vo = vb + prev * n;
+        double *pc = wb + cur * n, *po = wb + prev * n;
         if (c == kk % C) {
             double *col = Ablk + (size_t)(kk / C) * n;
-            const double wk = has_pend ? wo[kk] : 0.0, vk = has_pend ? vo[kk] : 0.0;
-            double part = 0.0;
-            for (int i = kk + tid; i < n; i += ET) {
-                double a = col[i];
-                if (has_pend) {
-                    a -= vo[i] * wk + wo[i] * vk;
-                    col[i] = a;
+            if (warp == 0) {
+                // one warp owns the column: update it, form the reflector (warp reductions only)
+                const double vk = has_pend ? vo[kk] : 0.0, wk = has_pend ? po[kk] + alo * vo[kk] : 0.0;
+                double part = 0.0;
+                for (int i = kk + lane; i < n; i += 32) {
+                    double a = col[i];
+                    if (has_pend) {
+                        a -= vo[i] * wk + (po[i] + alo * vo[i]) * vk;
+                        col[i] = a;
+                    }
+                    if (i >= kk + 2) part += a * a;
                 }
-                if (i >= kk + 2) part += a * a;
+                const double xnorm2 = warp_sum(part);
+                __syncwarp();
+                const double alpha = col[kk + 1], dk = col[kk];
+                double tau, ek, scal;
+                if (xnorm2 == 0.0) {
+                    tau = 0.0; ek = alpha; scal = 0.0;
+                } else {
+                    const double beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+                    tau = (beta - alpha) * fast_rcp(beta);
+                    scal = fast_rcp(alpha - beta);
+                    ek = beta;
+                }
+                __syncwarp();
+                for (int i = kk + 1 + lane; i < n; i += 32) col[i] = (i == kk + 1) ? 1.0 : col[i] * scal;   // reflector in place
+                if (lane < C) {
+                    remote(dd, lane)[kk] = dk;
+                    remote(ee, lane)[kk] = ek;
+                    remote(tt, lane)[kk] = tau;
+                }
             }
-            const double xnorm2 = block_sum(part);        // (its barriers also publish col[])
-            const double alpha = col[kk + 1], dk = col[kk];
-            double tau, ek, scal;
-            if (xnorm2 == 0.0) {
-                tau = 0.0; ek = alpha; scal = 0.0;
-            } else {
-                const double beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
-                tau = (beta - alpha) / beta;
-                scal = 1.0 / (alpha - beta);
-                ek = beta;
-            }
-            for (int i = kk + 1 + tid; i < n; i += ET) {
-                const double v = (i == kk + 1) ? 1.0 : col[i] * scal;
-                col[i] = v;                                // the reflector replaces the eliminated column (dumped to Vg below)
+            __syncthreads();
+            for (int i = kk + 1 + tid; i < n; i += ET) {          // broadcast: every CTA's copy of v (DSMEM stores)
+                const double v = col[i];
                 for (int r = 0; r < C; ++r) remote(vc, r)[i] = v;
-            }
-            if (tid < C) {
-                remote(dd, tid)[kk] = dk;
-                remote(ee, tid)[kk] = ek;
-                remote(tt, tid)[kk] = tau;
             }
         }
         cluster_sync();
@@ -192,32 +217,30 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
                 const int j = c + C * t;
                 if (j >= n) break;
                 double *col = Ablk + (size_t)t * n;
-                const double wj = has_pend ? wo[j] : 0.0, vj = has_pend ? vo[j] : 0.0;
+                const double vj = has_pend ? vo[j] : 0.0, wj = has_pend ? po[j] + alo * vo[j] : 0.0;
                 double acc = 0.0;
                 for (int i = kk + 1 + lane; i < n; i += 32) {
                     double a = col[i];
                     if (has_pend) {
-                        a -= vo[i] * wj + wo[i] * vj;
+                        const double voi = vo[i];
+                        a -= voi * wj + (po[i] + alo * voi) * vj;
                         col[i] = a;
                     }
                     acc += a * vc[i];
                 }
                 acc = warp_sum(acc) * tau;
-                if (lane < C) remote(pb, lane)[j] = acc;
+                if (lane < C) remote(pc, lane)[j] = acc;
             }
         }
         cluster_sync();
         if (tau != 0.0) {
-            double part = 0.0;
-            for (int i = kk + 1 + tid; i < n; i += ET) part += pb[i] * vc[i];
-            const double al = -0.5 * tau * block_sum(part);
-            double *wc = wb + cur * n;
-            for (int i = kk + 1 + tid; i < n; i += ET) wc[i] = pb[i] + al * vc[i];
+            double part = 0.0;                      // al = -tau/2 p.v, by every warp for itself (same order everywhere)
+            for (int i = kk + 1 + lane; i < n; i += 32) part += pc[i] * vc[i];
+            alo = -0.5 * tau * warp_sum(part);
             has_pend = true;
         } else {
             has_pend = false;
         }
-        __syncthreads();
     }
     // the reflectors, kept in place in their owners' columns, go to global memory for the back-transformation
     for (int t = warp; t < ncl; t += EW) {
@@ -245,6 +268,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
             hi = fmax(hi, dd[i] + el + er);
             em = fmax(em, er * er);
         }
+        for (int i = tid; i + 1 < n; i += ET) pb[i] = ee[i] * ee[i];       // e^2 for the Sturm recurrence
         gu = block_max(hi);
         gl = -block_max(-lo);
         em = block_max(em);
@@ -273,8 +297,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
                 if (fabs(qv) < pivmin) qv = -pivmin;
                 int cnt = qv < 0.0;
                 for (int i = 1; i < n; ++i) {
-                    const double e1 = ee[i - 1];
-                    qv = dd[i] - x - e1 * e1 / qv;
+                    qv = (dd[i] - x) - pb[i - 1] * fast_rcp(qv);          // pb holds e^2 (filled above)
                     if (fabs(qv) < pivmin) qv = -pivmin;
                     cnt += qv < 0.0;
                 }
@@ -317,46 +340,53 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     double *Freg = p.Fg ? p.Fg + (size_t)c * kc * fslot : big;
     double *Zs = p.z_smem ? big + (p.Fg ? 0 : (size_t)kc * fslot) : p.Zg;     // CTA 0's orthogonalisation copy
     const int myk = (k > c) ? (k - c + C - 1) / C : 0;                        // eigenvalues owned by this CTA: q = c + C s
-    double alast = 0.0;
-    if (tid < myk) {
-        // ---- dlagtf: T - lambda I = P L U, one thread per eigenvalue
-        const int q = c + C * tid;
-        double *ra = Freg + (size_t)tid * fslot, *bb = ra + n, *cc = bb + n, *d2 = cc + n;
+    // One WARP per eigenvalue.  The recurrences are sequential in the row index, so every lane runs the same chain on
+    // operands that the lanes fetched 32 rows at a time (coalesced shared-memory loads) and hand round by shuffles; lane t
+    // keeps the outputs of row t and the chunk is stored coalesced.  (One thread per eigenvalue walking shared memory
+    // took ~300 cycles per row.)
+    auto alast_of = [&](int s) -> double { return fabs(Freg[(size_t)s * fslot + 3 * n + (n - 1)]); };   // parked |U_nn|, see below
+    for (int s = warp; s < myk; s += EW) {
+        // ---- dlagtf: T - lambda I = P L U
+        const int q = c + C * s;
+        double *ra = Freg + (size_t)s * fslot, *bb = ra + n, *cc = bb + n, *d2 = cc + n, *z = d2 + n;
         unsigned char *sw = reinterpret_cast<unsigned char *>(d2 + 2 * n);
         const double lq = lam[q];
         double ai = dd[0] - lq, bi = n > 1 ? ee[0] : 0.0, amax = 0.0;
         double scale1 = fabs(ai) + fabs(bi);
-        for (int i = 0; i + 1 < n; ++i) {
-            const double ci = ee[i], a1 = dd[i + 1] - lq, b1 = (i + 2 < n) ? ee[i + 1] : 0.0;
-            const double scale2 = fabs(ci) + fabs(a1) + fabs(b1);
-            const bool noswap = (ci == 0.0) || (ai != 0.0 && fabs(ci) * scale1 <= fabs(ai) * scale2);
-            double m, ui, bo, di, an, bn;
-            if (noswap) {
-                m = (ci == 0.0) ? 0.0 : ci / ai;
-                ui = ai; bo = bi; di = 0.0;
-                an = a1 - m * bi; bn = b1;
-            } else {
-                m = ai / ci;
-                ui = ci; bo = a1; di = b1;
-                an = bi - m * a1; bn = -m * b1;
+        for (int i0 = 0; i0 + 1 < n; i0 += 32) {
+            const int il = i0 + lane;
+            const double l_ci = (il + 1 < n) ? ee[il] : 0.0;
+            const double l_a1 = (il + 1 < n) ? dd[il + 1] - lq : 0.0;
+            const double l_b1 = (il + 2 < n) ? ee[il + 1] : 0.0;
+            double k_ui = 0.0, k_bo = 0.0, k_m = 0.0, k_di = 0.0;
+            unsigned char k_sw = 0;
+            const int cnt = min(32, n - 1 - i0);
+            for (int t = 0; t < cnt; ++t) {
+                const double ci = shfl_d(l_ci, t), a1 = shfl_d(l_a1, t), b1 = shfl_d(l_b1, t);
+                const double scale2 = fabs(ci) + fabs(a1) + fabs(b1);
+                const bool noswap = (ci == 0.0) || (ai != 0.0 && fabs(ci) * scale1 <= fabs(ai) * scale2);
+                double m, ui, bo, di, an, bn;
+                if (noswap) {
+                    m = (ci == 0.0) ? 0.0 : ci * fast_rcp(ai);
+                    ui = ai; bo = bi; di = 0.0;
+                    an = a1 - m * bi; bn = b1;
+                } else {
+                    m = ai * fast_rcp(ci);
+                    ui = ci; bo = a1; di = b1;
+                    an = bi - m * a1; bn = -m * b1;
+                }
+                if (lane == t) { k_ui = ui; k_bo = bo; k_m = m; k_di = di; k_sw = noswap ? 0 : 1; }
+                amax = fmax(amax, fmax(fabs(ui), fmax(fabs(bo), fabs(di))));
+                ai = an; bi = bn; scale1 = scale2;
             }
-            ra[i] = ui; bb[i] = bo; cc[i] = m; d2[i] = di; sw[i] = noswap ? 0 : 1;
-            amax = fmax(amax, fmax(fabs(ui), fmax(fabs(bo), fabs(di))));
-            ai = an; bi = bn; scale1 = scale2;
+            if (il + 1 < n) { ra[il] = k_ui; bb[il] = k_bo; cc[il] = k_m; d2[il] = k_di; sw[il] = k_sw; }
         }
-        ra[n - 1] = ai;
         amax = fmax(amax, fabs(ai));
-        alast = fabs(ai);
         const double tol = (amax == 0.0) ? EPS : fmax(amax * EPS, SAFMIN / EPS);
-        // pivots below tol are replaced by +-tol (dlagts, job = -1); the reciprocals are taken by a whole warp below
-        d2[n - 1] = tol;                        // (d2 has n slots, U uses the first n - 2): parked for that pass
-    }
-    __syncthreads();
-    // reciprocal pivots and start vectors: every thread, warp per eigenvalue
-    for (int s = warp; s < myk; s += EW) {
-        const int q = c + C * s;
-        double *ra = Freg + (size_t)s * fslot, *d2 = ra + 3 * n, *z = ra + 4 * n;
-        const double tol = d2[n - 1];
+        __syncwarp();
+        if (lane == 0) { ra[n - 1] = ai; d2[n - 1] = ai; }     // d2 has n slots, U uses n - 2: |U_nn| parked for the scaling
+        __syncwarp();
+        // pivots below tol are replaced by +-tol (dlagts, job = -1) and inverted once; start vector
         for (int i = lane; i < n; i += 32) {
             const double a = ra[i];
             ra[i] = 1.0 / (fabs(a) < tol ? (a < 0.0 ? -tol : tol) : a);
@@ -367,49 +397,56 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     stamp(3);
     for (int it = 0; it < p.iters; ++it) {
         for (int s = warp; s < myk; s += EW) {
-            const double *z = Freg + (size_t)s * fslot + 4 * n;
-            double a = 0.0;
-            for (int i = lane; i < n; i += 32) a += fabs(z[i]);
-            a = warp_sum(a);
-            if (lane == 0) wb[s] = a;            // wb (2n doubles, free after phase 1) as per-eigenvalue scratch: kc <= n
-        }
-        __syncthreads();
-        if (tid < myk) {
-            double *ra = Freg + (size_t)tid * fslot, *bb = ra + n, *cc = bb + n, *d2 = cc + n, *z = d2 + n;
+            const int q = c + C * s;
+            double *ra = Freg + (size_t)s * fslot, *bb = ra + n, *cc = bb + n, *d2 = cc + n, *z = d2 + n;
             const unsigned char *sw = reinterpret_cast<const unsigned char *>(d2 + 2 * n);
-            const double nrm1 = wb[tid];
-            const double scl = n * onenrm * fmax(EPS, alast) / (nrm1 == 0.0 ? 1.0 : nrm1);
-            // forward: apply P L
+            double nrm1 = 0.0;
+            for (int i = lane; i < n; i += 32) nrm1 += fabs(z[i]);
+            nrm1 = warp_sum(nrm1);
+            const double scl = n * onenrm * fmax(EPS, alast_of(s)) / (nrm1 == 0.0 ? 1.0 : nrm1);
+            // forward: apply P L   (y_{i-1} is final once row i has been seen)
             double yp = z[0] * scl;
-            for (int i = 1; i < n; ++i) {
-                const double yi = z[i] * scl, m = cc[i - 1];
-                if (sw[i - 1]) {
-                    z[i - 1] = yi;
-                    yp = yp - m * yi;
-                } else {
-                    z[i - 1] = yp;
-                    yp = yi - m * yp;
+            for (int i0 = 1; i0 < n; i0 += 32) {
+                const int il = i0 + lane;
+                const double l_z = il < n ? z[il] * scl : 0.0;
+                const double l_m = il < n ? cc[il - 1] : 0.0;
+                const int l_s = il < n ? sw[il - 1] : 0;
+                double keep = 0.0;
+                const int cnt = min(32, n - i0);
+                for (int t = 0; t < cnt; ++t) {
+                    const double yi = shfl_d(l_z, t), m = shfl_d(l_m, t);
+                    const int sflag = __shfl_sync(0xffffffffu, l_s, t);
+                    double out;
+                    if (sflag) { out = yi; yp = yp - m * yi; } else { out = yp; yp = yi - m * yp; }
+                    if (lane == t) keep = out;
                 }
+                __syncwarp();
+                if (il < n) z[il - 1] = keep;
             }
-            z[n - 1] = yp;
+            __syncwarp();
+            if (lane == 0) z[n - 1] = yp;
+            __syncwarp();
             // backward: U x = y
             double y1 = 0.0, y2 = 0.0, zmax = 0.0;
-            for (int i = n - 1; i >= 0; --i) {
-                double t = z[i];
-                if (i + 1 < n) t -= bb[i] * y1;
-                if (i + 2 < n) t -= d2[i] * y2;
-                t *= ra[i];
-                z[i] = t;
-                y2 = y1; y1 = t;
-                zmax = fmax(zmax, fabs(t));
+            for (int ih = n - 1; ih >= 0; ih -= 32) {
+                const int il = ih - lane;
+                const double l_z = il >= 0 ? z[il] : 0.0;
+                const double l_b = (il >= 0 && il + 1 < n) ? bb[il] : 0.0;
+                const double l_d = (il >= 0 && il + 2 < n) ? d2[il] : 0.0;
+                const double l_r = il >= 0 ? ra[il] : 0.0;
+                double keep = 0.0;
+                const int cnt = min(32, ih + 1);
+                for (int t = 0; t < cnt; ++t) {
+                    double v = shfl_d(l_z, t) - shfl_d(l_b, t) * y1 - shfl_d(l_d, t) * y2;
+                    v *= shfl_d(l_r, t);
+                    if (lane == t) keep = v;
+                    y2 = y1; y1 = v;
+                    zmax = fmax(zmax, fabs(v));
+                }
+                if (il >= 0) z[il] = keep;
             }
-            wb[tid] = (zmax > 0.0 && zmax < DBL_MAX) ? 1.0 / zmax : 1.0;
-        }
-        __syncthreads();
-        for (int s = warp; s < myk; s += EW) {
-            const int q = c + C * s;
-            const double *z = Freg + (size_t)s * fslot + 4 * n;
-            const double sc = wb[s];
+            __syncwarp();
+            const double sc = (zmax > 0.0 && zmax < DBL_MAX) ? 1.0 / zmax : 1.0;
             double *zg = p.Zg + (size_t)q * n;
             for (int i = lane; i < n; i += 32) zg[i] = z[i] * sc;
         }
@@ -467,81 +504,124 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     }
 
     // ================================================================== 4. back-transformation, order, sign
+    // X = H_0 H_1 ... H_{n-3} Z, RB reflectors at a time in compact WY form: H_lo ... H_hi = I - V T V^T (dlarft, forward
+    // column-wise).  Per chunk: all dot products V^T V and V^T z in parallel over the warps, T and y = T V^T z by a few
+    // threads, then one rank-RB update of every vector -- three block barriers per RB reflectors instead of a dependent
+    // dot / update chain per reflector.  Vectors are processed `zcap` at a time when they do not all fit.
     {
-        // big region: [kc][n] vectors, then the reflector ring [2][RB][ldv]
         const int ldv = p.ldv;
-        double *zv = big;
-        double *ring = big + (((size_t)kc * n + 1) & ~(size_t)1);
-        __syncthreads();
-        for (int s = 0; s < kc; ++s) {
-            const int q = c + C * s;
-            if (q >= k) break;
-            for (int i = tid; i < n; i += ET) zv[(size_t)s * n + i] = __ldcg(p.Zg + (size_t)q * n + i);
-        }
-        __syncthreads();
         const int nref = n - 2;                          // reflectors 0 .. n-3 (the last step's is the identity)
         const int nchunk = nref > 0 ? (nref + RB - 1) / RB : 0;
-        auto issue_chunk = [&](int ch) {                 // chunk ch holds reflectors hi .. hi-RB+1, hi = nref-1 - ch*RB
-            double *dst = ring + (size_t)(ch & 1) * RB * ldv;
-            const int hi = nref - 1 - ch * RB;
-            const int per = ldv / 2;                     // 16-byte pieces per column
-            for (int e = tid; e < RB * per; e += ET) {
-                const int b = e / per, piece = e - b * per;
-                const int kk = hi - b;
-                if (kk >= 0) cp_async16(dst + (size_t)b * ldv + 2 * piece, p.Vg + (size_t)kk * ldv + 2 * piece, 16);
-            }
-            cp_async_commit();
-        };
-        if (nchunk > 0) issue_chunk(0);
-        for (int ch = 0; ch < nchunk; ++ch) {
-            if (ch + 1 < nchunk) issue_chunk(ch + 1); else cp_async_commit();
-            cp_async_wait<1>();
-            __syncthreads();
-            const double *src = ring + (size_t)(ch & 1) * RB * ldv;
-            const int hi = nref - 1 - ch * RB;
-            for (int s = warp; s < kc; s += EW) {
-                if (c + C * s >= k) break;
-                double *z = zv + (size_t)s * n;
-                for (int b = 0; b < RB; ++b) {
-                    const int kk = hi - b;
-                    if (kk < 0) break;
-                    const double tau = tt[kk];
-                    if (tau == 0.0) continue;
-                    const double *v = src + (size_t)b * ldv;
-                    double dot = 0.0;
-                    for (int i = kk + 1 + lane; i < n; i += 32) dot += v[i] * z[i];
-                    dot = warp_sum(dot) * tau;
-                    for (int i = kk + 1 + lane; i < n; i += 32) z[i] -= dot * v[i];
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-        }
-        cp_async_wait<0>();
+        double *ring = big;                              // [2][RB][ldv]
+        double *zv = big + (size_t)2 * RB * ldv;         // [zcap][n]
+        double *Gs = esm + Lo.wy;                        // [RB][RB] V^T V
+        double *Ts = Gs + RB * RB;                       // [RB][RB]
+        double *ws = Ts + RB * RB;                       // [zcap][RB] V^T z
+        double *ys = ws + RB * ZCAP_MAX;                 // [zcap][nb] y = T V^T z
+        const int zcap = p.zcap;
         bool bad = false;
-        for (int s = warp; s < kc; s += EW) {
-            const int q = c + C * s;
-            if (q >= k) break;
-            double *z = zv + (size_t)s * n;
-            double nn = 0.0, best = -1.0;
-            int bi = 0;
-            for (int i = lane; i < n; i += 32) {
-                const double v = z[i];
-                nn += v * v;
-                if (fabs(v) > best) { best = fabs(v); bi = i; }
+        for (int s0 = 0; s0 < myk; s0 += zcap) {
+            const int nz = min(zcap, myk - s0);
+            __syncthreads();
+            for (int s = 0; s < nz; ++s) {
+                const int q = c + C * (s0 + s);
+                for (int i = tid; i < n; i += ET) zv[(size_t)s * n + i] = __ldcg(p.Zg + (size_t)q * n + i);
             }
-            nn = warp_sum(nn);
+            auto issue_chunk = [&](int ch) {             // chunk ch holds reflectors lo .. lo+nb-1 (slot j = kk - lo)
+                double *dst = ring + (size_t)(ch & 1) * RB * ldv;
+                const int hi = nref - 1 - ch * RB, lo = max(hi - RB + 1, 0);
+                const int per = ldv / 2;                 // 16-byte pieces per column
+                for (int e = tid; e < (hi - lo + 1) * per; e += ET) {
+                    const int j = e / per, piece = e - j * per;
+                    cp_async16(dst + (size_t)j * ldv + 2 * piece, p.Vg + (size_t)(lo + j) * ldv + 2 * piece, 16);
+                }
+                cp_async_commit();
+            };
+            if (nchunk > 0) issue_chunk(0);
+            for (int ch = 0; ch < nchunk; ++ch) {
+                if (ch + 1 < nchunk) issue_chunk(ch + 1); else cp_async_commit();
+                cp_async_wait<1>();
+                __syncthreads();
+                const double *V = ring + (size_t)(ch & 1) * RB * ldv;
+                const int hi = nref - 1 - ch * RB, lo = max(hi - RB + 1, 0), nb = hi - lo + 1;
+                // ---- A. dot products: pairs (a < b) of reflectors, and (reflector, vector); rows below a reflector's
+                // start hold stale memory and are never read (v_j lives on rows >= lo + j + 1, v_j[lo + j + 1] = 1)
+                const int npair = nb * (nb - 1) / 2, ntask = npair + nb * nz;
+                for (int task = warp; task < ntask; task += EW) {
+                    if (task < npair) {
+                        int a_ = 0, rem = task;
+                        while (rem >= nb - 1 - a_) { rem -= nb - 1 - a_; ++a_; }
+                        const int b_ = a_ + 1 + rem;
+                        const double *va = V + (size_t)a_ * ldv, *vb_ = V + (size_t)b_ * ldv;
+                        double d = 0.0;
+                        for (int i = lo + b_ + 1 + lane; i < n; i += 32) d += va[i] * vb_[i];
+                        d = warp_sum(d);
+                        if (lane == 0) Gs[a_ * RB + b_] = d;
+                    } else {
+                        const int t2 = task - npair, s = t2 / nb, j = t2 - s * nb;
+                        const double *vj = V + (size_t)j * ldv, *z = zv + (size_t)s * n;
+                        double d = 0.0;
+                        for (int i = lo + j + 1 + lane; i < n; i += 32) d += vj[i] * z[i];
+                        d = warp_sum(d);
+                        if (lane == 0) ws[s * RB + j] = d;
+                    }
+                }
+                __syncthreads();
+                // ---- B. coefficients of the rank-nb update without forming T: applying H_hi first, then H_hi-1, ...,
+                // s_j = tau_j v_j^T (z - sum_{i > j} s_i v_i) = tau_j (w_j - sum_{i > j} s_i G[j][i]); one thread per vector
+                if (tid < nz) {
+                    double sv[RB];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {               // arg-max |v|, first occurrence on ties
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    for (int j = RB - 1; j >= 0; --j) {
+                        if (j < nb) {
+                            double acc = ws[tid * RB + j];
+#pragma unroll
+                            for (int i = j + 1; i < RB; ++i)
+                                if (i < nb) acc -= sv[i] * Gs[j * RB + i];
+                            sv[j] = tt[lo + j] * acc;
+                            ys[tid * nb + j] = sv[j];
+                        } else {
+                            sv[j] = 0.0;
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- C. z -= V y
+                for (int e = tid; e < nz * (n - lo - 1); e += ET) {
+                    const int s = e / (n - lo - 1), i = lo + 1 + (e - s * (n - lo - 1));
+                    const double *y = ys + s * nb;
+                    double acc = 0.0;
+                    for (int j = 0; j < nb; ++j)
+                        if (i >= lo + j + 1) acc += V[(size_t)j * ldv + i] * y[j];
+                    zv[(size_t)s * n + i] -= acc;
+                }
+                __syncthreads();
             }
-            double f = nn > 0.0 ? rsqrt(nn) : 0.0;
-            if (p.flip && z[bi] < 0.0) f = -f;
-            if (!(nn == nn) || !(fabs(lam[q]) <= DBL_MAX)) bad = true;
-            const int colo = k - 1 - q;
-            for (int i = lane; i < n; i += 32) p.U[(size_t)i * k + colo] = z[i] * f;
+            cp_async_wait<0>();
+            __syncthreads();
+            for (int s = warp; s < nz; s += EW) {
+                const int q = c + C * (s0 + s);
+                double *z = zv + (size_t)s * n;
+                double nn = 0.0, best = -1.0;
+                int bi = 0;
+                for (int i = lane; i < n; i += 32) {
+                    const double v = z[i];
+                    nn += v * v;
+                    if (fabs(v) > best) { best = fabs(v); bi = i; }
+                }
+                nn = warp_sum(nn);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {               // arg-max |v|, first occurrence on ties
+                    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+                double f = nn > 0.0 ? rsqrt(nn) : 0.0;
+                if (p.flip && z[bi] < 0.0) f = -f;
+                if (!(nn == nn) || !(fabs(lam[q]) <= DBL_MAX)) bad = true;
+                const int colo = k - 1 - q;
+                for (int i = lane; i < n; i += 32) p.U[(size_t)i * k + colo] = z[i] * f;
+            }
         }
         if (p.info && bad && lane == 0) atomicExch(p.info, -1);
     }
@@ -550,7 +630,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
 }
 
 struct EigPlan {
-    int C, ncl, kc, L, ldv, z_smem;
+    int C, ncl, kc, L, ldv, z_smem, zcap;
     bool a_smem, f_smem;
     size_t smem_bytes, ws_bytes;
     size_t off_V, off_Z, off_lam, off_A, off_F;
@@ -604,8 +684,10 @@ int eig_plan(int n, int k, EigPlan &pl) {
     const size_t needA = (size_t)pl.ncl * n;
     const size_t needF = (size_t)pl.kc * fslot_doubles(n);
     const size_t needZ = (size_t)k * n;
-    const size_t need4 = (((size_t)pl.kc * n + 1) & ~(size_t)1) + (size_t)2 * RB * pl.ldv;
-    SKT_REQUIRE(need4 <= avail, SKT_EUNSUPPORTED, "n = %d, k = %d too large for the back-transformation buffers", n, k);
+    const size_t ringd = (size_t)2 * RB * pl.ldv;
+    SKT_REQUIRE(ringd + (size_t)n <= avail, SKT_EUNSUPPORTED, "n = %d too large for the back-transformation buffers", n);
+    pl.zcap = (int)std::min<size_t>(std::min<size_t>((size_t)pl.kc, ZCAP_MAX), (avail - ringd) / (size_t)n);
+    const size_t need4 = ringd + (size_t)pl.zcap * n;
     pl.a_smem = needA <= avail;
     pl.f_smem = needF <= avail;
     pl.z_smem = ((pl.f_smem ? needF : 0) + needZ <= avail) ? 1 : 0;
@@ -652,8 +734,8 @@ extern "C" int skt_symeig_top(const double *A_d, int n, int k, int flipsign, dou
     p.lamg = (double *)(ws + pl.off_lam);
     p.Ag = pl.a_smem ? nullptr : (double *)(ws + pl.off_A);
     p.Fg = pl.f_smem ? nullptr : (double *)(ws + pl.off_F);
-    p.C = pl.C; p.ncl = pl.ncl; p.kc = pl.kc; p.L = pl.L; p.ldv = pl.ldv; p.z_smem = pl.z_smem;
-    p.iters = 3;
+    p.C = pl.C; p.ncl = pl.ncl; p.kc = pl.kc; p.L = pl.L; p.ldv = pl.ldv; p.z_smem = pl.z_smem; p.zcap = pl.zcap;
+    p.iters = 2;        // inverse iterations (tools/symeig_model.py: two reach the residual floor on every spectrum tried)
     if (const char *e = getenv("SKT_EIG_ITERS")) p.iters = std::max(1, atoi(e));
     p.prof = nullptr;
     const char *pe = getenv("SKT_EIG_PROF");

@@ -142,6 +142,45 @@ class CooHandle(object):
             pass
 
 
+_ACCUM_OPS = {'sum': 0, 'max': 1, 'min': 2}
+
+
+def coo_accumulate(subs, vals, op):
+    """Merge duplicate coordinates on the device (``utils.accum``, utils.py:5-26 with func = sum / max / min).
+
+    Returns ``(vals, subs)`` with the distinct coordinates in the reference's order (lexsort: last mode most
+    significant); values come back as float64 like the reference's ``np.zeros`` accumulator."""
+    lib = _lib.load()
+    dev.require_cuda()
+    nd = len(subs)
+    S = [np.ascontiguousarray(s, dtype=np.int64) for s in subs]
+    v = np.ascontiguousarray(vals, dtype=np.float64)
+    nnz = int(v.shape[0])
+    base = [int(s.min()) for s in S]
+    extent = [int(s.max()) - b + 1 for s, b in zip(S, base)]
+    keys = np.empty(nnz, dtype=np.uint64)
+    ovals = np.empty(nnz, dtype=np.float64)
+    n_out = C.c_int64(0)
+    ptrs = _lib.ptr_array([s.ctypes.data for s in S])
+    _lib.check(lib.skt_coo_accumulate_host(ptrs, C.c_void_p(v.ctypes.data), nnz, _lib.shape_array(base),
+                                           _lib.shape_array(extent), nd, _ACCUM_OPS[op], C.c_void_p(keys.ctypes.data),
+                                           C.c_void_p(ovals.ctypes.data), C.byref(n_out)))
+    m = n_out.value
+    idx = np.unravel_index(keys[:m].astype(np.int64), tuple(extent), order='F')
+    out_subs = tuple(np.asarray(ix, dtype=S[d].dtype) + base[d] for d, ix in enumerate(idx))
+    return ovals[:m].copy(), out_subs
+
+
+def compact_keys(keys_d, key_bits):
+    """ids of ``keys_d`` (uint64 device tensor) among its distinct values -> (int32 device tensor, count)."""
+    lib = _lib.load()
+    n = int(keys_d.shape[0])
+    ids = dev.empty((n,), np.int32)
+    nd = C.c_int64(0)
+    _lib.check(lib.skt_compact_keys(dev.ptr(keys_d), n, int(key_bits), dev.ptr(ids), C.byref(nd), dev.stream_ptr()))
+    return ids, int(nd.value)
+
+
 def mttkrp_coo(coo, U, rank, mode, out=None, atomic=False):
     """``sptensor.uttkrp`` on device factors (sptensor.py:216-229)."""
     lib = _lib.load()

@@ -137,8 +137,10 @@ def nvecs(X, n, rank, do_flipsign=True, dtype=float):
     come from the cluster eigensolver ``skt_symeig_top`` (tridiagonalisation in distributed
     shared memory, Sturm multisection, inverse iteration; order and sign fixed on the
     device).  Modes longer than 2048 exceed that kernel's shared-memory design and take the
-    library eigensolver instead.  Sparse tensors follow the reference's ARPACK route on the
-    host (core.py:280-283); that branch is not on the accelerated path yet.
+    library eigensolver instead.  Sparse tensors (the reference's ``eigsh`` route, core.py:280-283)
+    apply ``X_(n) X_(n)^T`` through the sparse MTTKRP kernel on the 2-way view of the non-zeros:
+    short modes assemble the Gram for the same eigensolver, long ones run a restarted block
+    Lanczos iteration (``sktensor/_eigs.py``).
     """
     from .dtensor import dtensor
     rank = int(rank)
@@ -148,14 +150,11 @@ def nvecs(X, n, rank, do_flipsign=True, dtype=float):
         Xd = X._device_tensor()
         G = K.unfold_gram(Xd, X.shape, n)
         return np.array(dev.to_host(device_nvecs(G, rank, do_flipsign)), dtype=float)
-    else:
-        from scipy.sparse import csr_matrix
-        from scipy.sparse.linalg import eigsh
-        Xn = csr_matrix(X.unfold(n), dtype=dtype)
-        _, V = eigsh(Xn.dot(Xn.T), rank, which='LM')
-        U = np.array(V[:, ::-1])
-    U = np.array(U, dtype=float)
-    return flipsign(U) if do_flipsign else U
+    from .sptensor import sptensor
+    if isinstance(X, sptensor):
+        from ._eigs import sparse_nvecs
+        return sparse_nvecs(X, n, rank, do_flipsign)
+    raise ValueError('nvecs() needs a dtensor or sptensor (%s)' % type(X))
 
 
 def device_nvecs(G, rank, do_flipsign=True):

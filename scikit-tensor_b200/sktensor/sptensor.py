@@ -9,7 +9,6 @@ host bookkeeping and not part of the accelerated path.
 """
 import numpy as np
 from scipy.sparse import coo_matrix
-from scipy.sparse import issparse as issparse_mat
 
 from .core import tensor_mixin
 from .dtensor import unfolded_dtensor
@@ -47,7 +46,7 @@ class sptensor(tensor_mixin):
                 raise ValueError('Subscripts must be integers')
         vals = np.array(vals, dtype=dtype)
         if accumfun is not None:
-            vals, subs = accum(subs, vals, issorted=False, with_subs=True, func=accumfun)
+            vals, subs = _accumulate(subs, vals, accumfun)
         self.subs = subs
         self.vals = vals
         self.dtype = dtype
@@ -173,18 +172,49 @@ class sptensor(tensor_mixin):
         self.drop_device_cache()
 
     def _ttm_compute(self, V, mode, transp):
-        # sparse TTM through the unfolding (sptensor.py:139-151); host SciPy, off the accelerated path
-        Z = self.unfold(mode, transp=True).tocsr()
-        if transp:
-            V = V.T
-        Z = Z.dot(V.T)
-        shape = list(self.shape)
-        shape[mode] = V.shape[0]
-        if issparse_mat(Z):
-            Z = Z.tocoo()
-            rd = [m for m in range(self.ndim) if m != mode][::-1]
-            return unfolded_sptensor((Z.data, (Z.row, Z.col)), None, rd, [mode], shape).fold()
-        return unfolded_dtensor(Z.T, mode, shape).fold()
+        """Sparse tensor times matrix (sptensor.py:139-151): the result is dense in the multiplied mode.
+
+        ``Y[.., j, ..] = sum_i X[.., i, ..] V[j, i]`` is a segmented reduction over the non-zeros grouped by their
+        other subscripts -- the sparse MTTKRP kernel on the 2-way view (row = linear index of the other modes,
+        column = i_mode) with the single "factor" ``V^T``: no unfolding matrix, no SciPy product.  The dense result
+        is returned as a ``dtensor`` whose device copy is kept, so the rest of a TTM chain (tucker.hooi on a sparse
+        tensor, tucker.py:103) continues on the device without a re-upload."""
+        from . import _device as dev
+        from . import _kernels as K
+        from .dtensor import dtensor
+        V = np.asarray(V, dtype=np.float64)
+        mode = int(mode)
+        if V.ndim != 2 or (V.shape[0] if transp else V.shape[1]) != self.shape[mode]:
+            raise ValueError('shapes %s and %s not aligned' % (V.shape, self.shape))
+        Vt = V if transp else V.T                       # (I_mode x p): row i holds V[:, i]
+        p = int(Vt.shape[1])
+        others = [m for m in range(self.ndim) if m != mode]
+        oshape = tuple(self.shape[m] for m in others)
+        nrows = int(np.prod(oshape)) if others else 1
+        if nrows >= 2 ** 31 - 1:
+            raise ValueError('the dense result of this sparse ttm (%d x %d) is too large' % (nrows, p))
+        if len(self.vals) == 0:
+            shape = list(self.shape)
+            shape[mode] = p
+            return dtensor(np.zeros(shape))
+        rows = np.ravel_multi_index(tuple(np.asarray(self.subs[m]) for m in others), oshape) if others else \
+            np.zeros(len(self.vals), dtype=np.int64)
+        coo2 = K.CooHandle([np.asarray(rows, dtype=np.int64), np.asarray(self.subs[mode], dtype=np.int64)],
+                           np.asarray(self.vals, dtype=np.float64), (nrows, self.shape[mode]), modes_mask=1)
+        if p <= 128:
+            M = K.mttkrp_coo(coo2, [None, dev.to_device(np.ascontiguousarray(Vt))], p, 0)
+        else:                                           # the sparse kernel holds at most 128 columns per pass
+            t = dev.torch()
+            M = t.cat([K.mttkrp_coo(coo2, [None, dev.to_device(np.ascontiguousarray(Vt[:, c0:c0 + 128]))],
+                                    min(128, p - c0), 0) for c0 in range(0, p, 128)], dim=1)
+        coo2.close()
+        Yd = M.reshape(oshape + (p,))
+        if mode != self.ndim - 1:                       # the new mode goes back to its position (a device copy)
+            perm = list(range(mode)) + [self.ndim - 1] + list(range(mode, self.ndim - 1))
+            Yd = Yd.permute(perm).contiguous()
+        Y = dtensor(dev.to_host(Yd))
+        Y._dev = Yd
+        return Y
 
     def unfold(self, rdims, cdims=None, transp=False):
         """Matricise: modes ``rdims`` index the rows, ``cdims`` the columns (sptensor.py:197-214)."""
@@ -253,6 +283,28 @@ class unfolded_sptensor(coo_matrix):
             for m, ix in zip(self.cdims, np.unravel_index(self.col, tuple(self.ten_shape[self.cdims]))):
                 subs[m] = np.asarray(ix, dtype=np.int64)
         return sptensor(tuple(subs), self.data, tuple(int(s) for s in self.ten_shape))
+
+
+_DEVICE_ACCUM_MIN = 4096       # below this, sorting a handful of coordinates is host bookkeeping, not a kernel's job
+
+
+def _accumulate(subs, vals, func):
+    """Merge duplicate coordinates (sptensor.py:80-84 -> utils.accum).  The sum / max / min reducers run on the
+    device (radix sort of the linear keys + one pass over the runs, ``skt_coo_accumulate_host``); arbitrary Python
+    callables cannot, and keep the reference's host loop."""
+    op = None
+    if func in (np.sum, sum):
+        op = 'sum'
+    elif func in (np.max, np.amax, max):
+        op = 'max'
+    elif func in (np.min, np.amin, min):
+        op = 'min'
+    subs = tuple(np.asarray(s) for s in subs)
+    if op is None or len(vals) < _DEVICE_ACCUM_MIN or any(s.dtype.kind != 'i' for s in subs) or \
+            np.asarray(vals).dtype.kind not in 'fiub':
+        return accum(subs, vals, issorted=False, with_subs=True, func=func)
+    from . import _kernels as K
+    return K.coo_accumulate(subs, vals, op)
 
 
 def fromarray(A):

@@ -164,13 +164,14 @@ def test_sptensor_unfold_fold(rand5):          # test_sptensor.py:57-93
         assert S.unfold([i]).fold() == S
 
 
-def test_sptensor_ttm_host(T):                 # test_sptensor.py:96-100 (sparse TTM stays on the host)
-    Y = np.zeros((2, 4, 2))
-    Y[:, :, 0] = [[22, 49, 76, 103], [28, 64, 100, 136]]
-    Y[:, :, 1] = [[130, 157, 184, 211], [172, 208, 244, 280]]
+def test_sptensor_ttm_needs_the_device(T):     # sparse TTM runs on the sparse MTTKRP kernel: no host route is left
+    import torch
     S = sptensor(T.nonzero(), T.flatten(), T.shape)
-    Y2 = S.ttm(np.array([[1, 3, 5], [2, 4, 6]]), 0)
-    assert (2, 4, 2) == Y2.shape and (Y == Y2).all()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            S.ttm(np.array([[1, 3, 5], [2, 4, 6]]), 0)
+    with pytest.raises(ValueError):             # argument checks come first (dtensor.py:62 analogue)
+        S.ttm(np.ones((2, 7)), 0)
 
 
 def test_sptensor_getitem_sub_toarray():       # test_sptensor.py:152-183

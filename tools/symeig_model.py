@@ -164,7 +164,7 @@ def lcg_uniform(n, k):
     return (h >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
 
 
-def tridiag_eigenvectors(d, e, lam, bnorm, iters=3):
+def tridiag_eigenvectors(d, e, lam, bnorm, iters=2):
     """Inverse iteration for all shifts together; modified Gram-Schmidt inside groups of close eigenvalues
     (gap < 1e-3 * ||T||, dstein's ortol) in ascending order after every solve."""
     n, k = len(d), len(lam)
@@ -211,7 +211,7 @@ def back_transform(V, tau, Z):
     return X
 
 
-def symeig_top(A, k, iters=3, lanes=32):
+def symeig_top(A, k, iters=2, lanes=32):
     """(w, U): the k largest eigenvalues (descending) and eigenvectors of symmetric A, columns sign-fixed."""
     A = np.asarray(A, dtype=float)
     n = A.shape[0]
