@@ -143,6 +143,24 @@ def cpu_sample(steps=1):
     return np.asarray(ex), cores
 
 
+def cpu_baseline_full():
+    """cpu_baseline of the GPU arm: 2 iterations of the unmodified reference on the full 512^3 workload (~25 s of host
+    time), run as `bench.py --impl reference` in its own process (the reference's package is also called `sktensor`);
+    the oracle port on a 256^3 sample when that fails."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '2', '--warmup', '0'],
+                           capture_output=True, text=True, timeout=900,
+                           env={k: v for k, v in os.environ.items() if k not in ('OMP_NUM_THREADS', 'RANK', 'WORLD_SIZE')})
+        lines = [l for l in r.stdout.splitlines() if l.strip().startswith('{')]
+        cb = json.loads(lines[-1])['cpu_baseline']
+        if cb.get('value'):
+            return cb
+    except Exception:
+        pass
+    ex, cores = cpu_sample(2)
+    return cpu_baseline_obj(ex, cores)
+
+
 def cpu_baseline_obj(ex, cores):
     per = float(np.mean(ex))
     b = 3 * alg_bytes_dense((SAMPLE_SIDE,) * 3, RANK)
@@ -254,7 +272,14 @@ def run_gpu(args):
     lshape = (SIDE, SIDE, SIDE)
     offsets = np.arange(world + 1, dtype=np.int64) * SIDE
     rng = np.random.RandomState(1000 + rank)
-    Xh = rng.rand(*lshape)                                  # this rank's slab (host, pageable like a user's array)
+    # this rank's slab in page-locked host memory (the e2e contract: "host->device copy ... from pinned host memory"):
+    # skt_upload then DMAs it in place.  SKT_BENCH_PAGEABLE=1 uses an ordinary NumPy array (multi-threaded staging).
+    if os.environ.get('SKT_BENCH_PAGEABLE', '0') == '1':
+        Xh = rng.rand(*lshape)
+    else:
+        Xpin = torch.empty(lshape, dtype=torch.float64, pin_memory=True)
+        Xh = Xpin.numpy()
+        Xh[...] = rng.rand(*lshape)
 
     def make_input():
         if world == 1:
@@ -393,16 +418,23 @@ def run_gpu(args):
                'd2h_bytes_per_step': d2h, 'als_iters_per_sec': K2 / e2e_s, 'iterations': K2,
                'call': "cp_als(dtensor(X_host), 32, init='random', max_iter=%d, conv=0)" % K2,
                'runs_s': [float(x) for x in e2e_runs],
-               'note': 'median of 3 whole calls, each: pageable-host tensor upload (once per call), factor upload, per-iteration '
+               'note': 'median of 3 whole calls, each: tensor upload from %s host memory (once per call), factor upload, per-iteration ' % ('pageable' if os.environ.get('SKT_BENCH_PAGEABLE', '0') == '1' else 'page-locked') +
                        'fit read-back, final factor download; bytes are per iteration (upload amortised over '
                        '%d iterations)' % K2}
 
+    extras = {}
+    if not args.no_extras:
+        try:
+            extras = secondary_configs(torch, dist, world, rank, args.steps)
+        except Exception as e:                      # the headline line must survive a failure of a secondary run
+            extras = {'extras_error': '%s: %s' % (type(e).__name__, e)}
+            if world > 1:
+                raise
     if rank == 0:
         # the CPU baseline is taken at N = 1 only (torchrun pins OMP_NUM_THREADS=1 for N > 1, which would misstate it)
         cpu_obj = None
         if world == 1:
-            ex, cores = cpu_sample(2)
-            cpu_obj = cpu_baseline_obj(ex, cores)
+            cpu_obj = cpu_baseline_full()
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': W,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -419,6 +451,7 @@ def run_gpu(args):
             'clocks': clocks, 'e2e': e2e_obj, 'gpu_launches': int(launches),
             'roofline': roofline, 'cpu_baseline': cpu_obj,
         }
+        line.update(extras)
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + '\n').encode())
     if world > 1:
@@ -513,6 +546,166 @@ def sparse_roofline(torch, K, dev, nnz, steps, variants=False):
     fr = [out['modes'][str(n)]['frac'] for n in range(3)]
     out['achieved'] = float(np.mean([out['modes'][str(n)]['achieved'] for n in range(3)]))
     out['frac'] = float(np.mean(fr))
+    return out
+
+
+def timed_sweeps(torch, dist, world, eng, steps, warm):
+    """ms per ALS iteration of an engine (device events, max over ranks), after `warm` untimed iterations."""
+    for w in range(warm):
+        eng.sweep(first_iter=(w == 0))
+        eng.begin_read()
+        eng.prefetch_next_sweep()
+        eng.read_fit()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    fit = 0.0
+    for _ in range(steps):
+        eng.sweep(first_iter=False)
+        eng.begin_read()
+        eng.prefetch_next_sweep()
+        fit = eng.read_fit()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / steps, fit
+
+
+def device_shard_cfg5(torch, _parallel, dtensor, world, rank):
+    """This rank's slab of the dense 160^4 tensor (BASELINE configs[4]), generated on the device."""
+    gshape = (160, 160, 160, 160)
+    smode = _parallel.shard_mode(gshape, dense=True)
+    offsets = _parallel.split_rows(gshape[smode], world)
+    lsh = list(gshape)
+    lsh[smode] = int(offsets[rank + 1] - offsets[rank])
+    g = torch.Generator(device='cuda')
+    g.manual_seed(2000 + rank)
+    Xd = torch.rand(tuple(lsh), dtype=torch.float64, device='cuda', generator=g)
+    Xl = dtensor(np.broadcast_to(np.zeros(1), tuple(lsh)))      # shape carrier only: the data lives in Xl._dev
+    Xl._dev = Xd
+    return _parallel.LocalShard(Xl, smode, gshape, offsets), gshape, smode
+
+
+def device_shard_cfg3(torch, K, _parallel, sptensor, world, rank, nnz):
+    """This rank's equal-nnz row range of the sparse configs[2] tensor, generated and sorted on the device."""
+    gshape = SPARSE_SHAPE
+    I0 = gshape[0]
+    offsets = np.array([int(np.ceil(I0 * (r / float(world)) ** 3.0)) for r in range(world)] + [I0], dtype=np.int64)
+    nloc = nnz // world
+    subs, vals = device_powerlaw_coo(torch, gshape, nloc, seed=3000 + rank, lo_hi=(rank / float(world), (rank + 1) / float(world)))
+    subs[0] = torch.clamp(subs[0], min=int(offsets[rank]), max=int(offsets[rank + 1]) - 1) - int(offsets[rank])
+    lshape = (int(offsets[rank + 1] - offsets[rank]),) + tuple(gshape[1:])
+    coo = K.CooHandle.from_device(subs, vals, lshape)
+    del subs, vals
+    torch.cuda.empty_cache()
+    S = sptensor(tuple(np.zeros(0, dtype=np.int64) for _ in gshape), np.zeros(0), shape=lshape)
+    S._coo = coo                                               # the engine uses the sorted device copies as they are
+    return _parallel.LocalShard(S, 0, gshape, offsets), gshape, nloc * world
+
+
+def secondary_configs(torch, dist, world, rank, steps):
+    """The other BASELINE.json configurations at this GPU count, as extra keys of the default line:
+    strong scaling of configs[4] (dense 160^4 rank 64) and configs[2] (sparse 200 M nnz rank 16), and -- on one GPU --
+    the sparse MTTKRP roofline, the whole tucker_hooi call of configs[3] and the launch-latency case configs[0]."""
+    from sktensor import _kernels as K, _parallel, cp_als, dtensor, sptensor, tucker_hooi
+    from sktensor import _device as dev
+    out = {}
+    hbm_peak, _ = measured_peaks()
+    strong = {}
+    # ---- configs[4]
+    X, gshape, smode = device_shard_cfg5(torch, _parallel, dtensor, world, rank)
+    np.random.seed(1)
+    U = [None] + [np.random.rand(gshape[n], 64) for n in range(1, 4)]
+    eng = _parallel.CpAlsEngine(X, 64, U)
+    ms, fit = timed_sweeps(torch, dist, world, eng, max(3, min(steps, 10)), 3)
+    alg = 4 * alg_bytes_dense(gshape, 64)
+    strong['cfg5_dense_160^4_rank64'] = {'ms_per_iteration': ms, 'als_iters_per_sec': 1e3 / ms, 'GBps_algorithmic': alg / ms / 1e6,
+                                         'sharded_mode': smode, 'final_fit': fit,
+                                         'flops_per_iteration_reference': 4 * 2.0 * 64 * 160.0 ** 4}
+    del eng, X
+    torch.cuda.empty_cache()
+    # ---- configs[2]
+    X, gshape, nnz = device_shard_cfg3(torch, K, _parallel, sptensor, world, rank, 200000000)
+    np.random.seed(1)
+    U = [None] + [np.random.rand(gshape[n], 16) for n in range(1, 3)]
+    eng = _parallel.CpAlsEngine(X, 16, U)
+    ms, fit = timed_sweeps(torch, dist, world, eng, max(3, min(steps, 10)), 3)
+    alg = 3 * alg_bytes_sparse(gshape, nnz, 16)
+    strong['cfg3_sparse_200Mnnz_rank16'] = {'ms_per_iteration': ms, 'als_iters_per_sec': 1e3 / ms, 'GBps_algorithmic': alg / ms / 1e6,
+                                            'frac_of_hbm_per_gpu': alg / ms / 1e6 / world / hbm_peak, 'final_fit': fit}
+    coo = X.tensor._coo
+    del eng, X
+    coo.close()
+    torch.cuda.empty_cache()
+    out['strong_scaling'] = strong
+    if world > 1 or rank != 0:
+        return out
+    # ---- one GPU only from here
+    out['roofline_sparse'] = sparse_roofline(torch, K, dev, 200000000, 5)
+    out['roofline_sparse_20M'] = {k: v for k, v in sparse_roofline(torch, K, dev, 20000000, 5).items()
+                                  if k in ('modes', 'achieved', 'frac', 'nnz')}
+    # configs[3]: tucker_hooi(384^3, [32, 32, 32]) -- the whole public call, host tensor in, host core/factors out
+    Xh = dtensor(np.random.RandomState(0).rand(384, 384, 384))
+    hooi = {}
+    for init in ('random', 'nvecs'):
+        secs = {}
+        for it in (5, 20):
+            np.random.seed(0)
+            tucker_hooi(Xh, [32, 32, 32], init=init, maxIter=2, conv=0)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                np.random.seed(0)
+                tic = time.perf_counter()
+                tucker_hooi(Xh, [32, 32, 32], init=init, maxIter=it, conv=0)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - tic)
+            secs[it] = float(np.median(ts))
+        hooi[init] = {'whole_call_its_per_sec_20_iterations': 20 / secs[20], 'whole_call_seconds_20_iterations': secs[20],
+                      'ms_per_iteration_steady': (secs[20] - secs[5]) / 15.0 * 1e3}
+    # share of the symmetric eigensolver (own cluster kernel) in one iteration: 3 calls of n = 384, k = 32
+    Yg = np.random.RandomState(1).rand(384, 1024)
+    G = dev.to_device(Yg.dot(Yg.T))
+    for _ in range(3):
+        K.symeig_top(G, 32)
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        K.symeig_top(G, 32)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    eig_ms = float(np.median(ts))
+    hooi['eigensolver'] = {'kernel': 'symeig_cluster_kernel (own code, no cuSOLVER)', 'ms_per_call_n384_k32': eig_ms,
+                           'share_of_iteration': 3 * eig_ms / hooi['nvecs']['ms_per_iteration_steady']}
+    out['cfg4_hooi_384^3_rank32'] = hooi
+    del Xh, G
+    torch.cuda.empty_cache()
+    # configs[0]: cp_als 10x11x8 rank 3 -- pure launch latency; next to the CPU port on the same input
+    rng = np.random.RandomState(0)
+    X1 = rng.rand(10, 11, 8)
+    lat = []
+    for _ in range(7):
+        np.random.seed(42)
+        tic = time.perf_counter()
+        P, fit1, itr1, _ = cp_als(dtensor(X1), 3, init='random')
+        lat.append(time.perf_counter() - tic)
+    from oracle import sktensor_oracle as orc
+    cpu = []
+    for _ in range(5):
+        np.random.seed(42)
+        tic = time.perf_counter()
+        _, _, fo, io, _ = orc.cp_als(X1, 3, init='random')
+        cpu.append(time.perf_counter() - tic)
+    out['cfg1_latency'] = {'gpu_whole_call_ms': float(np.median(lat[2:])) * 1e3, 'iterations': int(itr1) + 1, 'fit': float(fit1),
+                           'cpu_port_whole_call_ms': float(np.median(cpu)) * 1e3, 'cpu_port_fit': float(np.ravel(fo)[0]),
+                           'note': '880-element tensor: launch-latency bound on the GPU; reported, not a target'}
     return out
 
 
@@ -629,6 +822,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='dense', choices=['dense', 'sparse', 'cfg3', 'cfg5'])
     ap.add_argument('--nnz', type=int, default=20000000)
+    ap.add_argument('--no-extras', action='store_true', help='default workload: skip the secondary configurations')
     ap.add_argument('--variants', action='store_true', help='sparse workload: also time the experiment switches')
     args = ap.parse_args()
     if args.impl == 'reference':

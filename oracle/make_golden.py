@@ -273,6 +273,28 @@ for m in range(3):
     put('hooi_b_U%d' % m, Uh[m])
 J['hooi_b'] = {'core_norm': float(np.linalg.norm(core))}
 
+# ---------------------------------------------------------------- RESCAL-ALS (rescal.py:41-265)
+from scipy.sparse import csr_matrix  # noqa: E402
+from sktensor import rescal as ref_rescal  # noqa: E402
+
+rs = np.random.RandomState(77)
+J['rescal_cases'] = {}
+for name, (n_, k_, r_, la_, lr_, dens_) in {'a': (40, 3, 4, 0.1, 0.2, 0.10), 'b': (60, 2, 5, 0.0, 0.0, 0.08),
+                                            'c': (25, 4, 3, 1.0, 0.0, 0.15)}.items():
+    Xs = [(rs.rand(n_, n_) < dens_) * rs.rand(n_, n_) for _ in range(k_)]
+    for i_, Xi_ in enumerate(Xs):
+        put('rescal_%s_X%d' % (name, i_), Xi_)
+    np.random.seed(5)
+    A_, R_, f_, itr_, _ = ref_rescal.als([csr_matrix(Xi_) for Xi_ in Xs], r_, init='random', lambda_A=la_, lambda_R=lr_)
+    put('rescal_%s_A' % name, A_)
+    put('rescal_%s_R' % name, np.array(R_))
+    J['rescal_cases'][name] = {'n': n_, 'k': k_, 'rank': r_, 'lambda_A': la_, 'lambda_R': lr_, 'seed': 5, 'itr': int(itr_),
+                               'f': float(f_)}
+    # default init ('nvecs' through ARPACK: column signs are arbitrary) -> record the sign-invariant reconstruction
+    A_, R_, f_, itr_, _ = ref_rescal.als([csr_matrix(Xi_) for Xi_ in Xs], r_, lambda_A=la_, lambda_R=lr_)
+    put('rescal_%s_nvecs_recon' % name, np.array([A_.dot(Rk_).dot(A_.T) for Rk_ in R_]))
+    J['rescal_cases'][name]['itr_nvecs'] = int(itr_)
+
 J['versions'] = {'numpy': np.__version__, 'scipy': __import__('scipy').__version__,
                  'python': sys.version.split()[0]}
 

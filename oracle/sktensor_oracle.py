@@ -429,3 +429,57 @@ def hooi(X, rank, init='nvecs', maxIter=500, conv=1e-7, trace=None):
         if itr > 1 and abs(fitold - fit) < conv:
             break
     return core, U, fit, itr
+
+
+# ----------------------------------------------------------------------------
+# RESCAL-ALS (rescal.py:41-265); X is a list of (sparse or dense) n x n frontal slices
+# ----------------------------------------------------------------------------
+def rescal_update_a(X, A, R, lmbda_a):
+    """A <- [sum_k X_k A R_k^T + X_k^T A R_k] [lambda I + sum_k R_k A^T A R_k^T + R_k^T A^T A R_k]^-1 (rescal.py:212-232)."""
+    rank = A.shape[1]
+    F = np.zeros(A.shape)
+    E = np.zeros((rank, rank))
+    AtA = A.T.dot(A)
+    for Xk, Rk in zip(X, R):
+        F += Xk.dot(A.dot(Rk.T)) + Xk.T.dot(A.dot(Rk))
+        E += Rk.dot(AtA).dot(Rk.T) + Rk.T.dot(AtA).dot(Rk)
+    return np.linalg.solve(lmbda_a * np.eye(rank) + E.T, F.T).T
+
+
+def rescal_update_r(X, A, lmbda_r):
+    """R_k from the thin SVD of A (rescal.py:235-246)."""
+    rank = A.shape[1]
+    U, S, Vt = np.linalg.svd(A, full_matrices=False)
+    Shat = np.kron(S, S)
+    Shat = (Shat / (Shat ** 2 + lmbda_r)).reshape(rank, rank)
+    return [Vt.T.dot(Shat * U.T.dot(Xk.dot(U))).dot(Vt) for Xk in X]
+
+
+def rescal_fval(X, A, R, lmbda_a, lmbda_r, normX):
+    """Objective the reference monitors for convergence (rescal.py:265-271, `_compute_fval`)."""
+    f = lmbda_a * np.linalg.norm(A) ** 2
+    for Xk, Rk, nk in zip(X, R, normX):
+        D = (Xk.toarray() if hasattr(Xk, 'toarray') else np.asarray(Xk)) - A.dot(Rk).dot(A.T)
+        f += np.linalg.norm(D) ** 2 / nk + lmbda_r * np.linalg.norm(Rk) ** 2
+    return f
+
+
+def rescal_als(X, rank, A0, maxIter=100, conv=1e-4, lambda_A=0.0, lambda_R=0.0, trace=None):
+    """RESCAL-ALS without attributes, from the initial factor ``A0`` (rescal.py:166-208; the reference draws A0 with
+    ``numpy.random.rand`` or from ``eigsh``).  Returns ``(A, R, fval_of_last_iteration, iterations)`` -- the reference's
+    third return value is the never-assigned ``f = 0`` (rescal.py:170,208)."""
+    A = np.array(A0, dtype=float)
+    R = rescal_update_r(X, A, lambda_R)
+    normX = [float(((Xk.data if hasattr(Xk, 'data') and not isinstance(Xk, np.ndarray) else np.asarray(Xk)) ** 2).sum()) for Xk in X]
+    fit = 0
+    itr = 0
+    for itr in range(maxIter):
+        fitold = fit
+        A = rescal_update_a(X, A, R, lambda_A)
+        R = rescal_update_r(X, A, lambda_R)
+        fit = rescal_fval(X, A, R, lambda_A, lambda_R, normX)
+        if trace is not None:
+            trace.append(float(fit))
+        if itr > 0 and abs(fitold - fit) < conv:
+            break
+    return A, R, fit, itr + 1

@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
             p.prof[slot] = t;
         }
     };
+    auto cluster_arrive = [&]() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); };
+    auto cluster_wait = [&]() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); };
     auto cluster_sync = [&]() {
         asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -170,67 +172,68 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
         double *pc = wb + cur * n, *po = wb + prev * n;
         if (c == kk % C) {
             double *col = Ablk + (size_t)(kk / C) * n;
-            if (warp == 0) {
-                // one warp owns the column: update it, form the reflector (warp reductions only)
-                const double vk = has_pend ? vo[kk] : 0.0, wk = has_pend ? po[kk] + alo * vo[kk] : 0.0;
-                double part = 0.0;
-                for (int i = kk + lane; i < n; i += 32) {
-                    double a = col[i];
-                    if (has_pend) {
-                        a -= vo[i] * wk + (po[i] + alo * vo[i]) * vk;
-                        col[i] = a;
-                    }
-                    if (i >= kk + 2) part += a * a;
+            // every thread owns one row of the column: update it, form the reflector, broadcast it
+            const double vk = has_pend ? vo[kk] : 0.0, wk = has_pend ? po[kk] + alo * vo[kk] : 0.0;
+            double part = 0.0;
+            for (int i = kk + tid; i < n; i += ET) {
+                double a = col[i];
+                if (has_pend) {
+                    a -= vo[i] * wk + (po[i] + alo * vo[i]) * vk;
+                    col[i] = a;
                 }
-                const double xnorm2 = warp_sum(part);
-                __syncwarp();
-                const double alpha = col[kk + 1], dk = col[kk];
-                double tau, ek, scal;
-                if (xnorm2 == 0.0) {
-                    tau = 0.0; ek = alpha; scal = 0.0;
-                } else {
-                    const double beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
-                    tau = (beta - alpha) * fast_rcp(beta);
-                    scal = fast_rcp(alpha - beta);
-                    ek = beta;
-                }
-                __syncwarp();
-                for (int i = kk + 1 + lane; i < n; i += 32) col[i] = (i == kk + 1) ? 1.0 : col[i] * scal;   // reflector in place
-                if (lane < C) {
-                    remote(dd, lane)[kk] = dk;
-                    remote(ee, lane)[kk] = ek;
-                    remote(tt, lane)[kk] = tau;
-                }
+                if (i >= kk + 2) part += a * a;
             }
-            __syncthreads();
-            for (int i = kk + 1 + tid; i < n; i += ET) {          // broadcast: every CTA's copy of v (DSMEM stores)
-                const double v = col[i];
+            const double xnorm2 = block_sum(part);        // (its barriers also publish col[])
+            const double alpha = col[kk + 1], dk = col[kk];
+            double tau, ek, scal;
+            if (xnorm2 == 0.0) {
+                tau = 0.0; ek = alpha; scal = 0.0;
+            } else {
+                const double beta = -copysign(sqrt(alpha * alpha + xnorm2), alpha);
+                tau = (beta - alpha) * fast_rcp(beta);
+                scal = fast_rcp(alpha - beta);
+                ek = beta;
+            }
+            __syncthreads();                              // alpha / dk were read by everyone before col[kk + 1] changes
+            for (int i = kk + 1 + tid; i < n; i += ET) {
+                const double v = (i == kk + 1) ? 1.0 : col[i] * scal;
+                col[i] = v;                                // the reflector replaces the eliminated column (dumped to Vg below)
                 for (int r = 0; r < C; ++r) remote(vc, r)[i] = v;
             }
+            if (tid < C) {
+                remote(dd, tid)[kk] = dk;
+                remote(ee, tid)[kk] = ek;
+                remote(tt, tid)[kk] = tau;
+            }
+            cluster_arrive();                             // v is on its way; the local update below overlaps the barrier
         }
-        cluster_sync();
-        const double tau = tt[kk];
-        // previous step's rank-2 update fused with this step's p = tau A v on the columns this CTA owns
-        {
-            const int t0 = (kk + 1 - c + C - 1) / C;      // first local column with j >= kk + 1  (j = c + C t)
-            for (int t = max(t0, 0) + warp; t < ncl; t += EW) {
+        // previous step's rank-2 update on the columns this CTA owns.  It needs nothing from the current step, so the
+        // other CTAs do it WHILE the owner forms the reflector, and the owner between its arrive and its wait.
+        const int t0 = max((kk + 1 - c + C - 1) / C, 0);  // first local column with j >= kk + 1  (j = c + C t)
+        if (has_pend) {
+            for (int t = t0 + warp; t < ncl; t += EW) {
                 const int j = c + C * t;
                 if (j >= n) break;
                 double *col = Ablk + (size_t)t * n;
-                const double vj = has_pend ? vo[j] : 0.0, wj = has_pend ? po[j] + alo * vo[j] : 0.0;
-                double acc = 0.0;
+                const double vj = vo[j], wj = po[j] + alo * vo[j];
                 for (int i = kk + 1 + lane; i < n; i += 32) {
-                    double a = col[i];
-                    if (has_pend) {
-                        const double voi = vo[i];
-                        a -= voi * wj + (po[i] + alo * voi) * vj;
-                        col[i] = a;
-                    }
-                    acc += a * vc[i];
+                    const double voi = vo[i];
+                    col[i] -= voi * wj + (po[i] + alo * voi) * vj;
                 }
-                acc = warp_sum(acc) * tau;
-                if (lane < C) remote(pc, lane)[j] = acc;
             }
+        }
+        if (c != kk % C) cluster_arrive();
+        cluster_wait();
+        const double tau = tt[kk];
+        // this step's p = tau A v on the same columns (same warp, same lanes: no barrier in between)
+        for (int t = t0 + warp; t < ncl; t += EW) {
+            const int j = c + C * t;
+            if (j >= n) break;
+            const double *col = Ablk + (size_t)t * n;
+            double acc = 0.0;
+            for (int i = kk + 1 + lane; i < n; i += 32) acc += col[i] * vc[i];
+            acc = warp_sum(acc) * tau;
+            if (lane < C) remote(pc, lane)[j] = acc;
         }
         cluster_sync();
         if (tau != 0.0) {

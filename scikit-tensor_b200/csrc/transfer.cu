@@ -115,6 +115,17 @@ extern "C" int skt_upload(void *dst_d, const void *src_h, size_t nbytes, skt_str
         SKT_CUDA(cudaStreamSynchronize(st));
         return SKT_OK;
     }
+    {
+        // page-locked source (cudaHostAlloc / cudaHostRegister / torch pin_memory): the DMA engine reads it in place --
+        // no staging copy, no host threads; N ranks of one node then share only the PCIe links, not the host cores
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, src_h) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+            SKT_CUDA(cudaMemcpyAsync(dst_d, src_h, nbytes, cudaMemcpyHostToDevice, st));
+            SKT_CUDA(cudaStreamSynchronize(st));
+            return SKT_OK;
+        }
+        cudaGetLastError();      // (pageable memory reports an error on older drivers: not ours)
+    }
     std::lock_guard<std::mutex> lock(g_mu);
     int device = 0;
     SKT_CUDA(cudaGetDevice(&device));

@@ -326,8 +326,11 @@ class CpAlsEngine(object):
 
         # ---- tensor to the device, ||X||^2
         if self.sparse:
-            self.Xd = be.upload_coo([np.asarray(s_) for s_ in local.subs], local.vals, self.lshape)
-            self.normX2 = be.coo_sumsq(self.Xd) if len(local.vals) else be.zeros((1,))
+            cached = getattr(local, '_coo', None)        # sptensor keeps its sorted device copies once built
+            self.Xd = cached if cached is not None else \
+                be.upload_coo([np.asarray(s_) for s_ in local.subs], local.vals, self.lshape)
+            nnz = getattr(self.Xd, 'nnz', len(local.vals))
+            self.normX2 = be.coo_sumsq(self.Xd) if nnz else be.zeros((1,))
         else:
             self.Xd = be.upload_dense(local)
             self.normX2 = be.sumsq(self.Xd)

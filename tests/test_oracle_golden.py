@@ -239,3 +239,16 @@ def test_golden_reproducible_from_reference(tmp_path, golden):
     for k in new.files:
         assert new[k].shape == golden.a[k].shape, k
         assert np.allclose(new[k], golden.a[k], rtol=1e-12, atol=1e-13, equal_nan=True), k
+
+
+def test_rescal_oracle_matches_reference(golden):
+    """RESCAL-ALS restatement (rescal.py:166-271) against the unmodified reference's factors and iteration counts."""
+    for name, c in golden.j['rescal_cases'].items():
+        X = [golden['rescal_%s_X%d' % (name, i)] for i in range(c['k'])]
+        np.random.seed(c['seed'])
+        A0 = np.random.rand(c['n'], c['rank'])
+        A, R, fval, itr = orc.rescal_als(X, c['rank'], A0, lambda_A=c['lambda_A'], lambda_R=c['lambda_R'])
+        assert itr == c['itr'], name
+        assert np.max(np.abs(A - golden['rescal_%s_A' % name])) < 1e-9
+        assert np.max(np.abs(np.array(R) - golden['rescal_%s_R' % name])) < 1e-8
+        assert c['f'] == 0                       # the reference returns its never-assigned f (rescal.py:170,208)
