@@ -230,6 +230,20 @@ SKT_API int skt_cp_update_finish_parts(const double *const *ex_parts_d, int worl
 SKT_API int skt_cp_update_cluster_slabs(const double *slabs_d, int nslabs, const double *P_d, int64_t rows, int rank,
                                 int ndim, int mode, int first_iter, double *G_d, double *U_d, double *lambda_d,
                                 double *ip_d, const double *normX2_d, double *fit_d, skt_stream stream);
+/* ---------------------------------------------------------------- the whole CP-ALS loop in one call
+ * cp.als for a dense tensor whose factors all fit the single-launch update kernel (sktensor/cp.py:132-171: per mode
+ * uttkrp -> Gram-Hadamard pinv solve -> normalise; per iteration fit + convergence test `itr > 0 and |fit - fitold| <
+ * conv`).  U_d: storage for all ndim factors (I_m x rank, row-major); bit m of init_mask set = U_d[m] holds an initial
+ * factor (cp._init leaves the first one out, cp.py:190-205; its storage is overwritten before it is read).
+ * fit_full = 0 reproduces fit_method=None (fit = iteration index, no early exit before max_iter unless conv > 1).
+ * On return: *fit_h, *itr_h (index of the last iteration), exectimes_h[0..*itr_h] wall seconds (may be NULL),
+ * lambda_d and the factors on the device.  SKT_ENONFINITE where scipy's pinv raises ValueError (cp.py:147).      */
+SKT_API int    skt_cp_als_run_fits(const int64_t *shape, int ndim, int rank);
+SKT_API size_t skt_cp_als_run_workspace(const int64_t *shape, int ndim, int rank);
+SKT_API int    skt_cp_als_run(const double *X_d, const int64_t *shape, int ndim, int rank, double *const *U_d,
+                      unsigned init_mask, int max_iter, double conv, int fit_full, double *lambda_d, void *ws_d,
+                      size_t ws_bytes, double *fit_h, int *itr_h, double *exectimes_h, skt_stream stream);
+
 /* ---------------------------------------------------------------- COO de-duplication (accumfun)
  * sptensor(subs, vals, accumfun=...) merges duplicate coordinates (sktensor/sptensor.py:80-84 -> utils.accum,
  * sktensor/utils.py:5-26: lexsort with the LAST mode most significant, `func` over every run).  Host arrays in, host

@@ -409,6 +409,25 @@ def unfold_gram(Xd, shape, mode):
     return G
 
 
+def cp_als_run_fits(shape, rank):
+    return bool(_lib.load().skt_cp_als_run_fits(_lib.shape_array(shape), len(shape), int(rank)))
+
+
+def cp_als_run(Xd, shape, rank, Ud, init_mask, max_iter, conv, fit_full):
+    """The whole loop of cp.als in one C call (``skt_cp_als_run``) -> (lambda device tensor, fit, itr, exectimes)."""
+    lib = _lib.load()
+    shp = _lib.shape_array(shape)
+    nd = len(shape)
+    lam = dev.empty((rank,))
+    ws, wsz = dev.workspace('run').get(lib.skt_cp_als_run_workspace(shp, nd, rank))
+    fit, itr = C.c_double(0.0), C.c_int(-1)
+    ex = np.zeros(max(int(max_iter), 1), dtype=np.float64)
+    _lib.check(lib.skt_cp_als_run(dev.ptr(Xd), shp, nd, int(rank), _factor_ptrs(Ud), int(init_mask), int(max_iter),
+                                  float(conv), 1 if fit_full else 0, dev.ptr(lam), ws, wsz, C.byref(fit), C.byref(itr),
+                                  C.c_void_p(ex.ctypes.data), dev.stream_ptr()))
+    return lam, fit.value, itr.value, ex[:itr.value + 1].copy()
+
+
 SYMEIG_MAX_N = 2048
 
 

@@ -97,6 +97,10 @@ PROTOTYPES = {
     'skt_coo_accumulate_host': (C.c_int, [c_voidpp, c_dp, C.c_int64, c_i64p, c_i64p, C.c_int, C.c_int, C.c_void_p, c_dp,
                                           C.POINTER(C.c_int64)]),
     'skt_compact_keys': (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_int64), c_stream]),
+    'skt_cp_als_run_fits': (C.c_int, [c_i64p, C.c_int, C.c_int]),
+    'skt_cp_als_run_workspace': (C.c_size_t, [c_i64p, C.c_int, C.c_int]),
+    'skt_cp_als_run': (C.c_int, [c_dp, c_i64p, C.c_int, C.c_int, c_voidpp, C.c_uint, C.c_int, C.c_double, C.c_int, c_dp,
+                                 C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p, c_stream]),
     'skt_symeig_workspace': (C.c_size_t, [C.c_int, C.c_int]),
     'skt_symeig_top': (C.c_int, [c_dp, C.c_int, C.c_int, C.c_int, c_dp, c_dp, C.c_void_p, C.c_void_p, C.c_size_t, c_stream]),
 }

@@ -61,6 +61,9 @@ def als(X, rank, **kwargs):
         X.cache_on_device()
     try:
         U = _init(ainit, X, N, rank, dtype)
+        small = _run_small(X, rank, U, maxiter, conv, fit_method)
+        if small is not None:
+            return small
         eng = _parallel.CpAlsEngine(X, rank, U)
     finally:
         if pinned_here:
@@ -90,6 +93,51 @@ def als(X, rank, **kwargs):
     lmbda = eng.download(U)               # fills the caller-visible list in place (cp.py:154,195-196)
     P = ktensor(U, lmbda)
     return P, fit, itr, np.array(exectimes)
+
+
+_RUN_LOOP_MAX_ELEMS = 1 << 21
+
+
+def _run_small(X, rank, U, maxiter, conv, fit_method):
+    """Small dense problems are launch-latency bound: the whole loop runs behind one C call (``skt_cp_als_run``: one
+    MTTKRP and one fused update launch per mode, one 24-byte read-back per iteration).  Returns None when the problem
+    does not qualify (large or sharded tensors, sparse tensors, tall factors) -- those take the sweep engine."""
+    import os
+    from .dtensor import dtensor
+    if not isinstance(X, dtensor) or os.environ.get('SKT_NO_RUN_LOOP', '0') == '1' or int(maxiter) < 1:
+        return None
+    if _parallel._Comm().active or X.size > _RUN_LOOP_MAX_ELEMS or X.size == 0:
+        return None
+    from . import _device as dev
+    from . import _kernels as K
+    dev.require_cuda()
+    shape = tuple(int(s) for s in X.shape)
+    R = int(rank)
+    if R < 1:
+        raise ValueError('rank must be a positive integer')
+    if R > 64 or not K.cp_als_run_fits(shape, R):
+        return None
+    Ud, mask = [], 0
+    for m in range(X.ndim):
+        if U[m] is None:
+            Ud.append(dev.empty((shape[m], R)))
+            continue
+        Um = np.asarray(U[m], dtype=np.float64)
+        if Um.ndim != 2 or Um.shape != (shape[m], R):
+            raise ValueError('Dimension mismatch of factor matrices')
+        Ud.append(dev.to_device(Um))
+        mask |= 1 << m
+    try:
+        lam, fit, itr, ex = K.cp_als_run(X._device_tensor(), shape, R, Ud, mask, int(maxiter), float(conv), fit_method == 'full')
+    except ValueError as e:
+        if 'infs or NaNs' in str(e):
+            raise ValueError('array must not contain infs or NaNs')
+        raise
+    for m in range(X.ndim):
+        U[m] = dev.to_host(Ud[m])
+    if fit_method != 'full':
+        fit = itr
+    return ktensor(U, dev.to_host(lam)), fit, itr, ex
 
 
 def opt(X, rank, **kwargs):

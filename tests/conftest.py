@@ -15,6 +15,18 @@ for p in (PKG, ROOT):
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    config.addinivalue_line('markers', 'runloop: let cp_als take the one-call loop (skt_cp_als_run) for small tensors')
+
+
+@pytest.fixture(autouse=True)
+def _engine_by_default(request, monkeypatch):
+    """Small dense cp_als calls normally run behind one C call (skt_cp_als_run).  The bulk of the suite is about the
+    sweep engine (dimension tree, cluster / exchange updates, sharding), so it is pinned to the engine here;
+    tests marked `runloop` (tests/test_gpu_runloop.py) exercise the one-call loop, against the same references."""
+    if request.node.get_closest_marker('runloop') is None:
+        monkeypatch.setenv('SKT_NO_RUN_LOOP', '1')
+    else:
+        monkeypatch.delenv('SKT_NO_RUN_LOOP', raising=False)
 
 
 class Golden(object):
