@@ -32,6 +32,8 @@ constexpr int ET = 512;          // threads per CTA
 constexpr int EW = ET / 32;
 constexpr int RB = 8;            // reflectors per chunk of the back-transformation ring
 constexpr int EIG_MAX_N = 2048;
+constexpr int LW = 32;            // largest group that takes the symmetric (Loewdin) orthonormalisation
+constexpr int DS = 8;             // threads per dot product in the back-transformation
 constexpr int ZCAP_MAX = 64;      // vectors per back-transformation pass (sizes the small WY scratch)
 
 struct EigParams {
@@ -45,13 +47,13 @@ struct EigParams {
     double *lamg;     // [k]
     double *Ag;       // [C][ncl * n] column blocks when they do not fit shared memory (else null)
     double *Fg;       // [C][kc * fslot] factor arrays when they do not fit shared memory (else null)
-    int C, ncl, kc, L, ldv, z_smem, iters, zcap;
+    int C, ncl, kc, L, ldv, z_smem, iters, zcap, cholqr;
     unsigned long long *prof;   // optional phase timestamps (globaltimer ns) written by CTA 0, SKT_EIG_PROF=1
 };
 
 // shared-memory layout in doubles (host and device agree through this function)
 struct EigLayout {
-    int vb, wb, pb, dd, ee, tt, lam, grp, red, nbs, wy, big;
+    int vb, wb, pb, dd, ee, tt, lam, grp, tgrp, red, nbs, wy, big;
     size_t big_doubles;      // capacity of the phase-overlaid region
     size_t total_bytes;
 };
@@ -67,9 +69,10 @@ __host__ __device__ inline EigLayout eig_layout(int n, int k, size_t big_doubles
     L.tt = o; o += n;
     L.lam = o; o += k;
     L.grp = o; o += (k + 1) / 2 + 1;        // ints
+    L.tgrp = o; o += (k + 1) / 2 + 1;       // ints
     L.red = o; o += 2 * EW + 2;
     L.nbs = o; o += (ET + 1) / 2 + 1;       // ints (one per multisection slot)
-    L.wy = o; o += 2 * RB * RB + 2 * RB * ZCAP_MAX;   // compact-WY scratch: G, T, V^T z, y
+    L.wy = o; o += 2 * RB * RB + 2 * RB * ZCAP_MAX + ET;   // compact-WY scratch: G, T, V^T z, y, partial dot products
     o = (o + 1) & ~1;                       // 16-byte alignment of the big region
     L.big = o;
     L.big_doubles = big_doubles;
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     double *vb = esm + Lo.vb, *wb = esm + Lo.wb, *pb = esm + Lo.pb, *dd = esm + Lo.dd, *ee = esm + Lo.ee, *tt = esm + Lo.tt;
     double *lam = esm + Lo.lam, *red = esm + Lo.red, *big = esm + Lo.big;
     int *grp = reinterpret_cast<int *>(esm + Lo.grp);
+    int *tgrp = reinterpret_cast<int *>(esm + Lo.tgrp);
     int *nbs = reinterpret_cast<int *>(esm + Lo.nbs);
     unsigned crank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
@@ -330,10 +334,12 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
     if (tid == 0) {
         const double ortol = 1e-3 * onenrm;
         grp[0] = 0;
+        tgrp[0] = 0;
         for (int j = 1; j < k; ++j) {
             const double sep = 10.0 * EPS * fabs(lam[j]);
             if (lam[j] - lam[j - 1] < sep) lam[j] = lam[j - 1] + sep;
             grp[j] = (lam[j] - lam[j - 1] < ortol) ? grp[j - 1] : j;
+            tgrp[j] = (lam[j] - lam[j - 1] < 1e-8 * onenrm) ? tgrp[j - 1] : j;     // numerically coincident
         }
     }
     __syncthreads();
@@ -453,47 +459,115 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
             double *zg = p.Zg + (size_t)q * n;
             for (int i = lane; i < n; i += 32) zg[i] = z[i] * sc;
         }
+        if (it + 1 == p.iters) stamp(10);
         __threadfence();
         cluster_sync();
+        if (it + 1 == p.iters) stamp(11);
         if (c == 0) {
-            // ---- right-looking modified Gram-Schmidt inside the groups, ascending; then unit 2-norm
-            // (without the shared copy the vectors are read where the peers wrote them: L2 loads, never a stale L1 line)
-            auto ldz = [&](const double *q_) -> double { return p.z_smem ? *q_ : __ldcg(q_); };
+            // ---- orthonormalisation inside groups of close eigenvalues (dstein's ortol on the last pass; between the
+            // solves only numerically coincident eigenvalues need it).  Vectors that come out of the solve nearly
+            // orthonormal -- the usual case -- get the symmetric third-order correction Z <- Z (I - E/2 + 3/8 E^2),
+            // E = Z^T Z - I: every dot product at once, no chain of dependent projections.  Anything else (tight
+            // clusters, large groups) goes through modified Gram-Schmidt in ascending order.
+            const bool last = (it + 1 == p.iters);
+            const int *gsel = last ? grp : tgrp;
             if (p.z_smem) {
                 for (size_t e = tid; e < (size_t)k * n; e += ET) Zs[e] = __ldcg(p.Zg + e);
                 __syncthreads();
             }
-            for (int i = 0; i + 1 < k; ++i) {
-                if (grp[i + 1] != grp[i]) continue;            // z_i is the last of its group: nothing to project
-                const double *zi = Zs + (size_t)i * n;
-                double nn = 0.0;
-                for (int r = lane; r < n; r += 32) { const double v = ldz(zi + r); nn += v * v; }
-                nn = warp_sum(nn);
-                for (int j = i + 1 + warp; j < k && grp[j] == grp[i]; j += EW) {
+            auto normalise = [&](int j0, int j1, bool store) {
+                for (int j = j0 + warp; j < j1; j += EW) {
                     double *zj = Zs + (size_t)j * n;
-                    double dot = 0.0;
-                    for (int r = lane; r < n; r += 32) dot += ldz(zi + r) * ldz(zj + r);
-                    dot = warp_sum(dot);
-                    const double f = nn > 0.0 ? dot / nn : 0.0;
-                    for (int r = lane; r < n; r += 32) zj[r] = ldz(zj + r) - f * ldz(zi + r);
+                    double nn = 0.0;
+                    for (int r = lane; r < n; r += 32) { const double v = p.z_smem ? zj[r] : __ldcg(zj + r); nn += v * v; }
+                    nn = warp_sum(nn);
+                    const double f = nn > 0.0 ? rsqrt(nn) : 0.0;
+                    for (int r = lane; r < n; r += 32) {
+                        const double v = (p.z_smem ? zj[r] : __ldcg(zj + r)) * f;
+                        zj[r] = v;
+                        if (store && p.z_smem) p.Zg[(size_t)j * n + r] = v;
+                    }
                 }
-                __syncthreads();
-            }
-            for (int j = warp; j < k; j += EW) {
-                double *zj = Zs + (size_t)j * n;
-                double nn = 0.0;
-                for (int r = lane; r < n; r += 32) { const double v = ldz(zj + r); nn += v * v; }
-                nn = warp_sum(nn);
-                const double f = nn > 0.0 ? rsqrt(nn) : 0.0;
-                for (int r = lane; r < n; r += 32) {
-                    const double v = ldz(zj + r) * f;
-                    zj[r] = v;
-                    if (p.z_smem) p.Zg[(size_t)j * n + r] = v;
+            };
+            normalise(0, k, false);
+            __syncthreads();
+            for (int g0 = 0, g1 = 0; g0 < k; g0 = g1) {
+                g1 = g0 + 1;
+                while (g1 < k && gsel[g1] == gsel[g0]) ++g1;
+                const int mg = g1 - g0;
+                if (mg == 1) continue;
+                bool done = false;
+                if (p.cholqr && last && mg <= LW) {
+                    double *Es = Freg, *Ms = Es + LW * LW;   // [LW][LW] each, over the LU factors (dead after the last solve)
+                    int *cflag = nbs;
+                    if (tid == 0) cflag[0] = 0;
+                    __syncthreads();
+                    for (int task = tid; task < mg * mg; task += ET) {
+                        const int a_ = task / mg, b_ = task - a_ * mg;
+                        if (a_ > b_) continue;
+                        const double *za = Zs + (size_t)(g0 + a_) * n, *zb = Zs + (size_t)(g0 + b_) * n;
+                        double d = 0.0;
+                        int r = lane % n;                    // staggered start: the threads of a warp hit different banks
+                        for (int cnt = 0; cnt < n; ++cnt) {
+                            d += za[r] * zb[r];
+                            r = (r + 1 == n) ? 0 : r + 1;
+                        }
+                        d -= (a_ == b_) ? 1.0 : 0.0;
+                        Es[a_ * LW + b_] = d;
+                        Es[b_ * LW + a_] = d;
+                        if (!(fabs(d) < 1e-4)) cflag[0] = 1;
+                    }
+                    __syncthreads();
+                    if (cflag[0] == 0) {
+                        for (int task = tid; task < mg * mg; task += ET) {
+                            const int a_ = task / mg, b_ = task - a_ * mg;
+                            double e2 = 0.0;
+                            for (int q_ = 0; q_ < mg; ++q_) e2 += Es[a_ * LW + q_] * Es[q_ * LW + b_];
+                            Ms[a_ * LW + b_] = (a_ == b_ ? 1.0 : 0.0) - 0.5 * Es[a_ * LW + b_] + 0.375 * e2;
+                        }
+                        __syncthreads();
+                        for (int r = tid; r < n; r += ET) {  // one row of Z_g per thread: z_row <- z_row M
+                            double zr[LW];
+#pragma unroll
+                            for (int i = 0; i < LW; ++i) zr[i] = i < mg ? Zs[(size_t)(g0 + i) * n + r] : 0.0;
+                            for (int j = 0; j < mg; ++j) {
+                                double v = 0.0;
+#pragma unroll
+                                for (int i = 0; i < LW; ++i) v += zr[i] * Ms[i * LW + j];
+                                Zs[(size_t)(g0 + j) * n + r] = v;
+                            }
+                        }
+                        done = true;
+                    }
+                    __syncthreads();
+                }
+                if (p.prof && tid == 0 && last) p.prof[done ? 14 : 15] += (unsigned long long)mg;
+                if (done) continue;
+                for (int i = g0; i + 1 < g1; ++i) {
+                    const double *zi = Zs + (size_t)i * n;
+                    double nn = 0.0;
+                    for (int r = lane; r < n; r += 32) { const double v = p.z_smem ? zi[r] : __ldcg(zi + r); nn += v * v; }
+                    nn = warp_sum(nn);
+                    for (int j = i + 1 + warp; j < g1; j += EW) {
+                        double *zj = Zs + (size_t)j * n;
+                        double dot = 0.0;
+                        for (int r = lane; r < n; r += 32)
+                            dot += p.z_smem ? zi[r] * zj[r] : __ldcg(zi + r) * __ldcg(zj + r);
+                        dot = warp_sum(dot);
+                        const double f = nn > 0.0 ? dot / nn : 0.0;
+                        for (int r = lane; r < n; r += 32)
+                            zj[r] = p.z_smem ? zj[r] - f * zi[r] : __ldcg(zj + r) - f * __ldcg(zi + r);
+                    }
+                    __syncthreads();
                 }
             }
+            __syncthreads();
+            normalise(0, k, true);
         }
+        if (it + 1 == p.iters) stamp(12);
         __threadfence();
         cluster_sync();
+        if (it + 1 == p.iters) stamp(13);
         if (it + 1 < p.iters) {
             for (int s = warp; s < myk; s += EW) {
                 const int q = c + C * s;
@@ -521,6 +595,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
         double *Ts = Gs + RB * RB;                       // [RB][RB]
         double *ws = Ts + RB * RB;                       // [zcap][RB] V^T z
         double *ys = ws + RB * ZCAP_MAX;                 // [zcap][nb] y = T V^T z
+        double *parts = ys + RB * ZCAP_MAX;              // [ET] partial dot products
         const int zcap = p.zcap;
         bool bad = false;
         for (int s0 = 0; s0 < myk; s0 += zcap) {
@@ -550,26 +625,42 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
                 // ---- A. dot products: pairs (a < b) of reflectors, and (reflector, vector); rows below a reflector's
                 // start hold stale memory and are never read (v_j lives on rows >= lo + j + 1, v_j[lo + j + 1] = 1)
                 const int npair = nb * (nb - 1) / 2, ntask = npair + nb * nz;
-                for (int task = warp; task < ntask; task += EW) {
-                    if (task < npair) {
-                        int a_ = 0, rem = task;
-                        while (rem >= nb - 1 - a_) { rem -= nb - 1 - a_; ++a_; }
-                        const int b_ = a_ + 1 + rem;
-                        const double *va = V + (size_t)a_ * ldv, *vb_ = V + (size_t)b_ * ldv;
-                        double d = 0.0;
-                        for (int i = lo + b_ + 1 + lane; i < n; i += 32) d += va[i] * vb_[i];
-                        d = warp_sum(d);
-                        if (lane == 0) Gs[a_ * RB + b_] = d;
-                    } else {
-                        const int t2 = task - npair, s = t2 / nb, j = t2 - s * nb;
-                        const double *vj = V + (size_t)j * ldv, *z = zv + (size_t)s * n;
-                        double d = 0.0;
-                        for (int i = lo + j + 1 + lane; i < n; i += 32) d += vj[i] * z[i];
-                        d = warp_sum(d);
-                        if (lane == 0) ws[s * RB + j] = d;
+                // every dot product is split over DS threads (a warp reduction costs ~220 ns on this part, a shared
+                // memory round trip a fraction of it); 512 / DS tasks per round, partial sums added in a fixed order
+                for (int t0_ = 0; t0_ < ntask; t0_ += ET / DS) {
+                    const int task = t0_ + tid / DS, sub = tid % DS;
+                    double d = 0.0;
+                    if (task < ntask) {
+                        if (task < npair) {
+                            int a_ = 0, rem = task;
+                            while (rem >= nb - 1 - a_) { rem -= nb - 1 - a_; ++a_; }
+                            const int b_ = a_ + 1 + rem;
+                            const double *va = V + (size_t)a_ * ldv, *vb_ = V + (size_t)b_ * ldv;
+                            for (int i = lo + b_ + 1 + sub; i < n; i += DS) d += va[i] * vb_[i];
+                        } else {
+                            const int t2 = task - npair, s = t2 / nb, j = t2 - s * nb;
+                            const double *vj = V + (size_t)j * ldv, *z = zv + (size_t)s * n;
+                            for (int i = lo + j + 1 + sub; i < n; i += DS) d += vj[i] * z[i];
+                        }
                     }
+                    parts[tid] = d;
+                    __syncthreads();
+                    if (tid < ET / DS && t0_ + tid < ntask) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int q_ = 0; q_ < DS; ++q_) sum += parts[tid * DS + q_];
+                        const int tk = t0_ + tid;
+                        if (tk < npair) {
+                            int a_ = 0, rem = tk;
+                            while (rem >= nb - 1 - a_) { rem -= nb - 1 - a_; ++a_; }
+                            Gs[a_ * RB + a_ + 1 + rem] = sum;
+                        } else {
+                            const int t2 = tk - npair, s = t2 / nb, j = t2 - s * nb;
+                            ws[s * RB + j] = sum;
+                        }
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 // ---- B. coefficients of the rank-nb update without forming T: applying H_hi first, then H_hi-1, ...,
                 // s_j = tau_j v_j^T (z - sum_{i > j} s_i v_i) = tau_j (w_j - sum_{i > j} s_i G[j][i]); one thread per vector
                 if (tid < nz) {
@@ -633,7 +724,7 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
 }
 
 struct EigPlan {
-    int C, ncl, kc, L, ldv, z_smem, zcap;
+    int C, ncl, kc, L, ldv, z_smem, zcap, cholqr;
     bool a_smem, f_smem;
     size_t smem_bytes, ws_bytes;
     size_t off_V, off_Z, off_lam, off_A, off_F;
@@ -694,6 +785,8 @@ int eig_plan(int n, int k, EigPlan &pl) {
     pl.a_smem = needA <= avail;
     pl.f_smem = needF <= avail;
     pl.z_smem = ((pl.f_smem ? needF : 0) + needZ <= avail) ? 1 : 0;
+    // the symmetric orthonormalisation of the last pass keeps its two LW x LW matrices where the LU factors were
+    pl.cholqr = (pl.z_smem && pl.f_smem && needF >= (size_t)2 * LW * LW) ? 1 : 0;
     size_t bigd = need4;
     if (pl.a_smem) bigd = std::max(bigd, needA);
     bigd = std::max(bigd, (pl.f_smem ? needF : 0) + (pl.z_smem ? needZ : 0));
@@ -737,7 +830,8 @@ extern "C" int skt_symeig_top(const double *A_d, int n, int k, int flipsign, dou
     p.lamg = (double *)(ws + pl.off_lam);
     p.Ag = pl.a_smem ? nullptr : (double *)(ws + pl.off_A);
     p.Fg = pl.f_smem ? nullptr : (double *)(ws + pl.off_F);
-    p.C = pl.C; p.ncl = pl.ncl; p.kc = pl.kc; p.L = pl.L; p.ldv = pl.ldv; p.z_smem = pl.z_smem; p.zcap = pl.zcap;
+    p.C = pl.C; p.ncl = pl.ncl; p.kc = pl.kc; p.L = pl.L; p.ldv = pl.ldv; p.z_smem = pl.z_smem; p.zcap = pl.zcap; p.cholqr = pl.cholqr;
+    if (const char *e = getenv("SKT_EIG_NO_LOEWDIN")) if (e[0] == '1') p.cholqr = 0;
     p.iters = 2;        // inverse iterations (tools/symeig_model.py: two reach the residual floor on every spectrum tried)
     if (const char *e = getenv("SKT_EIG_ITERS")) p.iters = std::max(1, atoi(e));
     p.prof = nullptr;
@@ -769,7 +863,10 @@ extern "C" int skt_symeig_top(const double *A_d, int n, int k, int flipsign, dou
         fprintf(stderr, "[symeig n=%d k=%d C=%d L=%d] tridiag %.1f us | eigenvalues %.1f | factor %.1f | iterations", n, k, pl.C,
                 pl.L, (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3);
         for (int i = 0; i < p.iters && i < 5; ++i) fprintf(stderr, " %.1f", (h[4 + i] - h[3 + i]) * 1e-3);
-        fprintf(stderr, " | back-transform %.1f us\n", (h[9] - h[3 + std::min(p.iters, 5)]) * 1e-3);
+        fprintf(stderr, " | back-transform %.1f us", (h[9] - h[3 + std::min(p.iters, 5)]) * 1e-3);
+        fprintf(stderr, " || last iteration: solve %.1f, barrier %.1f, orthonormalise (CTA 0) %.1f, barrier %.1f us\n",
+                (h[10] - h[2 + p.iters]) * 1e-3, (h[11] - h[10]) * 1e-3, (h[12] - h[11]) * 1e-3, (h[13] - h[12]) * 1e-3);
+        fprintf(stderr, "   vectors orthonormalised symmetrically / by Gram-Schmidt on the last pass: %llu / %llu\n", h[14], h[15]);
     }
     return SKT_OK;
 }

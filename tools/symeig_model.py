@@ -185,18 +185,39 @@ def tridiag_eigenvectors(d, e, lam, bnorm, iters=2):
         amax = np.maximum(amax, np.abs(fac[3]).max(axis=0))
     tol = np.where(amax == 0, EPS, np.maximum(amax * EPS, SAFMIN / EPS))     # dlagts: tol = eps * max|U|, eps if U = 0
     Z = lcg_uniform(n, k)
-    for _ in range(iters):
+    # sub-groups of numerically coincident eigenvalues: only these need orthogonalising BETWEEN the solves
+    tight = np.zeros(k, dtype=np.int64)
+    for j in range(1, k):
+        tight[j] = tight[j - 1] if (lam[j] - lam[j - 1]) < 1e-8 * onenrm else j
+    for it in range(iters):
+        last = it == iters - 1
         # scale the right-hand side like dstein so that the solve cannot overflow
         nrm1 = np.abs(Z).sum(axis=0)
         scl = n * onenrm * np.maximum(EPS, np.abs(fac[0][n - 1])) / np.where(nrm1 == 0, 1.0, nrm1)
         Z = lu_solve(fac, Z * scl[None, :], tol)
         zmax = np.abs(Z).max(axis=0)                 # keep the squares of the next norms inside the double range
         Z = Z / np.where(zmax > 0, zmax, 1.0)[None, :]
-        for j in range(k):                           # MGS, ascending inside each group
-            for i in range(group[j], j):
-                Z[:, j] -= np.dot(Z[:, i], Z[:, j]) * Z[:, i]
-            nz = np.linalg.norm(Z[:, j])
-            Z[:, j] /= nz if nz > 0 else 1.0
+        nz = np.linalg.norm(Z, axis=0)
+        Z = Z / np.where(nz > 0, nz, 1.0)[None, :]
+        grp = group if last else tight
+        j0 = 0
+        while j0 < k:
+            j1 = j0 + 1
+            while j1 < k and grp[j1] == grp[j0]:
+                j1 += 1
+            if j1 - j0 > 1:
+                Zg = Z[:, j0:j1]
+                E = Zg.T.dot(Zg) - np.eye(j1 - j0)
+                if np.abs(E).max() < 1e-4 and j1 - j0 <= 32:
+                    # nearly orthonormal already: symmetric (Loewdin) correction to third order, no sequential steps
+                    Z[:, j0:j1] = Zg.dot(np.eye(j1 - j0) - 0.5 * E + 0.375 * E.dot(E))
+                else:
+                    for j in range(j0, j1):          # modified Gram-Schmidt, ascending
+                        for i in range(j0, j):
+                            Z[:, j] -= np.dot(Z[:, i], Z[:, j]) * Z[:, i]
+                        nzj = np.linalg.norm(Z[:, j])
+                        Z[:, j] /= nzj if nzj > 0 else 1.0
+            j0 = j1
     return Z
 
 
