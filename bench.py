@@ -573,6 +573,18 @@ def timed_sweeps(torch, dist, world, eng, steps, warm):
     if world > 1:
         dist.barrier()
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if os.environ.get('SKT_SWEEP_TRACE', '0') == '1' and hasattr(eng, 'trace_begin'):
+        eng.trace_begin()
+        for _ in range(5):
+            eng.sweep(first_iter=False)
+            eng.begin_read()
+            eng.prefetch_next_sweep()
+            eng.read_fit()
+        torch.cuda.synchronize()
+        rep = eng.trace_report()
+        if int(os.environ.get('RANK', '0')) == 0:
+            sys.stderr.write('[sweep trace, ms per iteration on rank 0] ' +
+                             ', '.join('%s %.3f' % (k, v / 5.0) for k, v in rep.items()) + '\n')
     return float(ms.item()) / steps, fit
 
 
@@ -595,9 +607,24 @@ def device_shard_cfg3(torch, K, _parallel, sptensor, world, rank, nnz):
     """This rank's equal-nnz row range of the sparse configs[2] tensor, generated and sorted on the device."""
     gshape = SPARSE_SHAPE
     I0 = gshape[0]
-    offsets = np.array([int(np.ceil(I0 * (r / float(world)) ** 3.0)) for r in range(world)] + [I0], dtype=np.int64)
-    nloc = nnz // world
-    subs, vals = device_powerlaw_coo(torch, gshape, nloc, seed=3000 + rank, lo_hi=(rank / float(world), (rank + 1) / float(world)))
+    # the engine's cuts (_parallel.split_nnz) balance nnz + w * rows; with the generator's CDF F(x) = (x / I0)^(1/3) the
+    # same cuts follow in closed form: solve nnz F(x) + w x = r / world * (nnz + w I0) for x
+    w = float(os.environ.get('SKT_SHARD_ROW_WEIGHT', '2'))
+    offsets = [0]
+    for r in range(1, world):
+        target = r / float(world) * (nnz + w * I0)
+        lo_, hi_ = 0.0, float(I0)
+        for _ in range(80):
+            mid = 0.5 * (lo_ + hi_)
+            if nnz * (mid / I0) ** (1.0 / 3.0) + w * mid < target:
+                lo_ = mid
+            else:
+                hi_ = mid
+        offsets.append(int(np.ceil(hi_)))
+    offsets = np.array(offsets + [I0], dtype=np.int64)
+    q_lo, q_hi = (offsets[rank] / float(I0)) ** (1.0 / 3.0), (offsets[rank + 1] / float(I0)) ** (1.0 / 3.0)
+    nloc = int(round(nnz * (q_hi - q_lo)))
+    subs, vals = device_powerlaw_coo(torch, gshape, nloc, seed=3000 + rank, lo_hi=(q_lo, q_hi))
     subs[0] = torch.clamp(subs[0], min=int(offsets[rank]), max=int(offsets[rank + 1]) - 1) - int(offsets[rank])
     lshape = (int(offsets[rank + 1] - offsets[rank]),) + tuple(gshape[1:])
     coo = K.CooHandle.from_device(subs, vals, lshape)
@@ -605,7 +632,11 @@ def device_shard_cfg3(torch, K, _parallel, sptensor, world, rank, nnz):
     torch.cuda.empty_cache()
     S = sptensor(tuple(np.zeros(0, dtype=np.int64) for _ in gshape), np.zeros(0), shape=lshape)
     S._coo = coo                                               # the engine uses the sorted device copies as they are
-    return _parallel.LocalShard(S, 0, gshape, offsets), gshape, nloc * world
+    tot = torch.tensor([nloc], dtype=torch.int64, device='cuda')
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tot)
+    return _parallel.LocalShard(S, 0, gshape, offsets), gshape, int(tot.item())
 
 
 def secondary_configs(torch, dist, world, rank, steps):

@@ -35,16 +35,20 @@ def split_rows(n, world):
     return np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
 
 
-def split_nnz(idx, dim, world):
-    """Offsets on ``range(dim)`` such that each range holds about ``nnz / world`` entries of ``idx``.
+def split_nnz(idx, dim, world, row_weight=None):
+    """Offsets on ``range(dim)`` that balance ``nnz + row_weight * rows`` over the ranks.
 
-    Power-law tensors put most non-zeros on few rows: equal-row cuts would leave one rank
-    with nearly all the work, so the cuts follow the cumulative non-zero count instead.
-    Cuts never split a row (a row's non-zeros stay on one rank).
+    Power-law tensors put most non-zeros on few rows: equal-row cuts would leave one rank with nearly all the
+    MTTKRP work, so the cuts follow the cumulative non-zero count.  Equal-nnz cuts alone leave the last rank with
+    most of the ROWS, i.e. most of the factor update of the sharded mode (measured on config 3 at 8 GPUs: 3.3 M of
+    10 M rows, 0.71 ms of a 4.3 ms iteration waiting for it), hence the row term: one row of the update costs about
+    as much as two non-zeros of the three MTTKRPs (``SKT_SHARD_ROW_WEIGHT``, default 2).  Cuts never split a row.
     """
+    if row_weight is None:
+        row_weight = float(os.environ.get('SKT_SHARD_ROW_WEIGHT', '2'))
     counts = np.bincount(np.asarray(idx, dtype=np.int64), minlength=int(dim))
-    cum = np.cumsum(counts)
-    total = int(cum[-1]) if len(cum) else 0
+    cum = np.cumsum(counts).astype(np.float64) + row_weight * np.arange(1, int(dim) + 1, dtype=np.float64)
+    total = float(cum[-1]) if len(cum) else 0.0
     offs = [0]
     for r in range(1, world):
         target = total * r / float(world)
@@ -490,9 +494,30 @@ class CpAlsEngine(object):
             self.comm.allreduce_sum(self.M[n])          # (modes with a symmetric-memory M are summed inside the update kernel)
         return self.M[n]
 
+    def _mark(self, label):
+        """SKT_SWEEP_TRACE=1: CUDA events at the phase boundaries of a sweep (see trace_report)."""
+        tr = getattr(self, '_trace', None)
+        if tr is None:
+            return
+        ev = self.be.dev.torch().cuda.Event(enable_timing=True)
+        ev.record()
+        tr.append((label, ev))
+
+    def trace_begin(self):
+        self._trace = []
+
+    def trace_report(self):
+        """ms per phase since trace_begin(), summed over the sweeps traced (call after a synchronise)."""
+        tr, self._trace = self._trace, None
+        out = {}
+        for (l0, e0), (l1, e1) in zip(tr[:-1], tr[1:]):
+            out[l1] = out.get(l1, 0.0) + e0.elapsed_time(e1)
+        return out
+
     def sweep(self, first_iter, want_fit=True):
         be, comm, N = self.be, self.comm, self.N
         fit_done = False
+        self._mark('start')
 
         def start_pinv(m):
             # pinv(Y_m) only needs the Grams of the other modes: run it on the side stream beside the MTTKRP of mode m
@@ -505,6 +530,7 @@ class CpAlsEngine(object):
                 M, self._m0_ready = self.M[0], False
             else:
                 M = self.mttkrp(n)
+            self._mark('mttkrp%d' % n)
             last = (n == N - 1) and want_fit
             fit_args = (self.ip if last else None, self.normX2 if last else None, self.fitout if last else None)
             if self.apinv[n]:
@@ -555,6 +581,7 @@ class CpAlsEngine(object):
                     comm.allreduce_sum(self.G[n])
                     if last:
                         comm.allreduce_sum(self.ip)
+            self._mark('update%d' % n)
             start_pinv((n + 1) % N)                         # the Grams it needs are final now
         if want_fit and not fit_done:
             be.cp_fit(self.G, self.lam, self.ip, self.normX2, self.fitout)
@@ -567,7 +594,9 @@ class CpAlsEngine(object):
     def prefetch_next_sweep(self):
         """Enqueue the next sweep's mode-0 MTTKRP now (it reads the current factors and writes only
         M[0]), so the GPU has work while the host waits for the fit; harmless if no sweep follows."""
+        self._mark('start')
         self.mttkrp(0)
+        self._mark('mttkrp0(prefetched)')
         self._m0_ready = True
 
     def _results(self):
