@@ -29,25 +29,45 @@ int sm_count_total();
 
 int sm_count() { return std::max(1, sm_count_total() - g_reserved_sms); }
 
+// device properties are cached per device (a process may switch devices between calls)
+static int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (dev >= 0 && dev < 64) ? dev : -1;
+}
+
+bool first_use_on_device(unsigned long long &mask) {
+    const int slot = current_device_slot();
+    if (slot < 0) return true;
+    const unsigned long long bit = 1ULL << slot;
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 int sm_count_total() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;  // B200; only reached when no device is visible (workspace queries on a CPU box)
+    static int cache[64] = {0};
+    const int slot = current_device_slot();
+    if (slot >= 0 && cache[slot] > 0) return cache[slot];
+    int n = 0;
+    if (slot < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, slot) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 148;  // B200; only reached when no device is visible (workspace queries on a CPU box)
     }
+    cache[slot] = n;
     return n;
 }
 
 size_t smem_optin_bytes() {
-    static int v = 0;
-    if (v == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0)
-            v = 232448;
+    static int cache[64] = {0};
+    const int slot = current_device_slot();
+    if (slot >= 0 && cache[slot] > 0) return (size_t)cache[slot];
+    int v = 0;
+    if (slot < 0 || cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, slot) != cudaSuccess || v <= 0) {
+        cudaGetLastError();
+        return 232448;
     }
+    cache[slot] = v;
     return (size_t)v;
 }
 

@@ -38,6 +38,9 @@ extern unsigned long long g_launches;
         SKT_CUDA(cudaGetLastError()); \
     } while (0)
 
+// true the first time it is called with this mask on the current device (per-kernel cudaFuncSetAttribute guards:
+// the attribute is a per-device property of the function)
+bool first_use_on_device(unsigned long long &mask);
 int sm_count();            // SMs of the current device (cached)
 size_t smem_optin_bytes(); // max opt-in dynamic shared memory per block (cached)
 
@@ -132,6 +135,9 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const void *tmap, uint64_
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(tmap) : "memory");
 }
+
+// max that propagates NaN like numpy.max (fmax would drop it): the signed column maximum of cp.py:152
+__device__ __forceinline__ double nanmax(double a, double b) { return (b > a || b != b) ? b : a; }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NT) solve_stats_kernel(const double *__restric
                     if (c < R) {
                         Unew[(r0 + i) * R + c] = acc[a][b];
                         if (first_iter) stat[b] += acc[a][b] * acc[a][b];
-                        else stat[b] = fmax(stat[b], acc[a][b]);
+                        else stat[b] = nanmax(stat[b], acc[a][b]);
                     }
                 }
             }
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(NT) solve_stats_kernel(const double *__restric
         double s = first_iter ? 0.0 : -DBL_MAX;
         for (int y = 0; y < 16; ++y) {
             const double v = cs[y * 16 * TT + tid];
-            s = first_iter ? s + v : fmax(s, v);
+            s = first_iter ? s + v : nanmax(s, v);
         }
         mine[tid] = s;
     }
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(NT) solve_stats_kernel(const double *__restric
             double s = first_iter ? 0.0 : -DBL_MAX;
             for (int b = 0; b < nblk; ++b) {
                 const double v = partials[(size_t)b * MAXR + tid];
-                s = first_iter ? s + v : fmax(s, v);
+                s = first_iter ? s + v : nanmax(s, v);
             }
             colstat[tid] = s;
         }
@@ -400,10 +400,9 @@ extern "C" int skt_solve_stats(const double *M_d, const double *P_d, int64_t row
     const size_t smem = (size_t)(MAXR * (16 * tt + 1) + ROWS * (MAXR + 1) + 16 * 16 * tt) * sizeof(double);
 #define SS(TT_)                                                                                                   \
     do {                                                                                                          \
-        static bool cfg = false;                                                                                  \
-        if (!cfg) {                                                                                               \
+        static unsigned long long cfg = 0;   /* bit d: configured on device d */                                                                                  \
+        if (skt::first_use_on_device(cfg)) {                                                                                               \
             SKT_CUDA(cudaFuncSetAttribute(solve_stats_kernel<TT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            cfg = true;                                                                                           \
         }                                                                                                         \
         solve_stats_kernel<TT_><<<nb, NT, smem, st>>>(M_d, P_d, rows, rank, first_iter, Unew_d, colstat_d, partials, counter); \
     } while (0)
@@ -429,11 +428,10 @@ extern "C" int skt_hadamard_pinv(const double *G_d, int ndim, int rank, int mode
     int rc = check_rank(rank);
     if (rc) return rc;
     const size_t smem = pinv_smem_doubles(rank) * sizeof(double);
-    static bool cfg = false;
-    if (!cfg) {
+    static unsigned long long cfg = 0;   /* bit d: configured on device d */
+    if (skt::first_use_on_device(cfg)) {
         SKT_CUDA(cudaFuncSetAttribute(hadamard_pinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(pinv_smem_doubles(MAXR) * sizeof(double))));
-        cfg = true;
     }
     hadamard_pinv_kernel<<<1, 1024, smem, (cudaStream_t)stream>>>(G_d, ndim, rank, mode, P_d, info_d);
     SKT_LAUNCH_CHECK();

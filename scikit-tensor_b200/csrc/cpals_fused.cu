@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
             const int i1 = min(rows, (ch + 1) * per);
             for (int i = ch * per; i < i1; ++i) {
                 const double v = Ms[i * LD + c];
-                st = p.first_iter ? st + v * v : fmax(st, v);
+                st = p.first_iter ? st + v * v : nanmax(st, v);
             }
         }
         cs[ch * RP + c] = st;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(FT, 1) cp_update_fused_kernel(const __grid_con
             double sacc = p.first_iter ? 0.0 : -DBL_MAX;
             for (int k = 0; k < nchunk; ++k) {
                 const double v = cs[k * RP + tid];
-                sacc = p.first_iter ? sacc + v : fmax(sacc, v);
+                sacc = p.first_iter ? sacc + v : nanmax(sacc, v);
             }
             const double l = p.first_iter ? sqrt(sacc) : (sacc < 1.0 ? 1.0 : sacc);   // cp.py:150 / cp.py:152-153
             lam[tid] = l;
@@ -389,7 +389,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
             const int i1 = min(nr, (ch + 1) * perc);
             for (int i = ch * perc; i < i1; ++i) {
                 const double v = Us[i * LD + c];
-                st = p.first_iter ? st + v * v : fmax(st, v);
+                st = p.first_iter ? st + v * v : nanmax(st, v);
             }
         }
         double *scr = gp;                                   // [nchunk][RP] scratch (the Gram comes later)
@@ -399,7 +399,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
             double sacc = p.first_iter ? 0.0 : -DBL_MAX;
             for (int k = 0; k < nchunk; ++k) {
                 const double v = scr[k * RP + tid];
-                sacc = p.first_iter ? sacc + v : fmax(sacc, v);
+                sacc = p.first_iter ? sacc + v : nanmax(sacc, v);
             }
             cst[tid] = sacc;
         }
@@ -414,7 +414,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(CTH, 1)
         double sacc = p.first_iter ? 0.0 : -DBL_MAX;
         for (unsigned k = 0; k < CL; ++k) {
             const double v = remote(cst, k)[tid];
-            sacc = p.first_iter ? sacc + v : fmax(sacc, v);
+            sacc = p.first_iter ? sacc + v : nanmax(sacc, v);
         }
         double l = p.first_iter ? sqrt(sacc) : (sacc < 1.0 ? 1.0 : sacc);   // cp.py:150 / cp.py:152-153
         if (p.ex) {                      // phase A of a sharded update: the statistic still has to meet the other ranks'
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(SXT) solve_exchange_kernel(const double *__res
                     Unew[(r0 + i) * R + c] = v;
                     ip += v * Ms[i * ML + c];
                     if (first_iter) stat[b] += v * v;
-                    else stat[b] = fmax(stat[b], v);
+                    else stat[b] = nanmax(stat[b], v);
                 }
             }
         }
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(SXT) solve_exchange_kernel(const double *__res
         double sacc = first_iter ? 0.0 : -DBL_MAX;
         for (int y = 0; y < 16; ++y) {
             const double v = cs[y * 16 * TT + tid];
-            sacc = first_iter ? sacc + v : fmax(sacc, v);
+            sacc = first_iter ? sacc + v : nanmax(sacc, v);
         }
         mine[tid] = sacc;
     }
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(SXT) solve_exchange_kernel(const double *__res
             double sacc = (is_stat && !first_iter) ? -DBL_MAX : 0.0;
             for (int b = 0; b < nblk; ++b) {
                 const double v = partials[(size_t)b * REC + e];
-                sacc = (is_stat && !first_iter) ? fmax(sacc, v) : sacc + v;
+                sacc = (is_stat && !first_iter) ? nanmax(sacc, v) : sacc + v;
             }
             ex[e] = sacc;
         }
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(256) cp_finish_kernel(const double *__restrict
         double sacc = first_iter ? 0.0 : -DBL_MAX;
         for (int w = 0; w < world; ++w) {
             const double v = finish_record(ex_all, ex_parts, w, REC)[tid];
-            sacc = first_iter ? sacc + v : fmax(sacc, v);
+            sacc = first_iter ? sacc + v : nanmax(sacc, v);
         }
         const double l = first_iter ? sqrt(sacc) : (sacc < 1.0 ? 1.0 : sacc);   // cp.py:150 / cp.py:152-153
         lam[tid] = l;
@@ -725,10 +725,9 @@ extern "C" int skt_cp_update_fused(const double *M_d, int64_t rows, int rank, in
                 "factor of %lld x %d does not fit the fused update kernel", (long long)rows, rank);
     const FusedLayout L = fused_layout(rows, rank);
     const size_t smem = L.total * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
+    static unsigned long long configured = 0;   /* bit d: configured on device d */
+    if (skt::first_use_on_device(configured)) {
         SKT_CUDA(cudaFuncSetAttribute(cp_update_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin_bytes()));
-        configured = smem_optin_bytes();
     }
     FusedParams p;
     p.M = M_d; p.G = G_d; p.U = U_d; p.lambda = lambda_d; p.info = info_d; p.ip = ip_d; p.normX2 = normX2_d; p.fit = fit_d;
@@ -755,10 +754,9 @@ static int update_cluster_impl(const double *M_d, int nslabs, const double *cons
                 "factor of %lld x %d does not fit the cluster update kernel", (long long)rows, rank);
     const ClusterLayout L = cluster_layout(rows, rank);
     const size_t smem = L.total * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   /* bit d: configured on device d */
+    if (skt::first_use_on_device(configured)) {
         SKT_CUDA(cudaFuncSetAttribute(cp_update_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin_bytes()));
-        configured = true;
     }
     ClusterParams p;
     p.M = M_d; p.P = P_d; p.G = G_d; p.U = U_d; p.lambda = lambda_d; p.ip = ip_d; p.normX2 = normX2_d; p.fit = fit_d;
@@ -784,10 +782,9 @@ extern "C" int skt_cp_update_exchange(const double *M_d, const double *P_d, int6
     if (rows > 0 && skt_cp_update_cluster_fits(rows, rank)) {      // small slab: the cluster kernel in phase-A mode
         const ClusterLayout L = cluster_layout(rows, rank);
         const size_t smem = L.total * sizeof(double);
-        static bool configured = false;
-        if (!configured) {
+        static unsigned long long configured = 0;   /* bit d: configured on device d */
+        if (skt::first_use_on_device(configured)) {
             SKT_CUDA(cudaFuncSetAttribute(cp_update_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin_bytes()));
-            configured = true;
         }
         ClusterParams p;
         p.M = M_d; p.P = P_d; p.G = nullptr; p.U = Unew_d; p.lambda = nullptr; p.ip = nullptr; p.normX2 = nullptr; p.fit = nullptr;
@@ -807,10 +804,9 @@ extern "C" int skt_cp_update_exchange(const double *M_d, const double *P_d, int6
     const size_t smem = (size_t)(SKT_MAX_RANK * (16 * tt + 1) + SXROWS * (SKT_MAX_RANK + 1) + SXROWS * (16 * tt + 1) + 16 * 16 * tt) * sizeof(double);
 #define SX(TT_)                                                                                                      \
     do {                                                                                                             \
-        static bool cfg = false;                                                                                     \
-        if (!cfg) {                                                                                                  \
+        static unsigned long long cfg = 0;   /* bit d: configured on device d */                                                                                     \
+        if (skt::first_use_on_device(cfg)) {                                                                                                  \
             SKT_CUDA(cudaFuncSetAttribute(solve_exchange_kernel<TT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            cfg = true;                                                                                              \
         }                                                                                                            \
         solve_exchange_kernel<TT_><<<nb, SXT, smem, st>>>(M_d, P_d, rows, rank, first_iter, Unew_d, ex_d, partials, counter); \
     } while (0)

@@ -177,12 +177,12 @@ int gram_dmma(const double *X_d, long long L, long long In, long long T, double 
     const size_t smem = (size_t)GSTAGES * 2 * (mmajor ? GK * LDM : GB * LDK) * sizeof(double);
     dim3 grid((unsigned)npairs, (unsigned)nsplit);
     if (mmajor) {
-        static bool cfg = false;
-        if (!cfg) { SKT_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+        static unsigned long long cfg = 0;   /* bit d: configured on device d */
+        if (skt::first_use_on_device(cfg)) { SKT_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
         gram_dmma_kernel<true><<<grid, GTH, smem, st>>>(p);
     } else {
-        static bool cfg = false;
-        if (!cfg) { SKT_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = true; }
+        static unsigned long long cfg = 0;   /* bit d: configured on device d */
+        if (skt::first_use_on_device(cfg)) { SKT_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
         gram_dmma_kernel<false><<<grid, GTH, smem, st>>>(p);
     }
     SKT_LAUNCH_CHECK();

@@ -914,10 +914,9 @@ int launch_dense(const DenseParams &p, int grid, cudaStream_t st) {
     constexpr int XSTAGE = MMAJOR ? BK * XS_M : BM * XS_K;
     constexpr int STAGE = XSTAGE + BK * RS;
     const size_t smem = (size_t)(STAGES * STAGE + BM * ZS) * sizeof(double);
-    static bool configured = false;  // per template instance
-    if (!configured) {
+    static unsigned long long configured = 0;   /* bit d: configured on device d */  // per template instance
+    if (skt::first_use_on_device(configured)) {
         SKT_CUDA(cudaFuncSetAttribute(mttkrp_dense_kernel<NB, MMAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     mttkrp_dense_kernel<NB, MMAJOR><<<grid, NTHREADS, smem, st>>>(p);
     SKT_LAUNCH_CHECK();
@@ -980,10 +979,9 @@ int make_tensor_map(const double *X, const DensePlan &pl, CUtensorMap &tm) {
 template <int NB, bool MMAJOR>
 int launch_dense_tma(const CUtensorMap &tm, const DenseParams &p, int grid, cudaStream_t st) {
     const size_t smem = TmaCfg<NB>::SMEM;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;   /* bit d: configured on device d */
+    if (skt::first_use_on_device(configured)) {
         SKT_CUDA(cudaFuncSetAttribute(mttkrp_dense_tma_kernel<NB, MMAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     mttkrp_dense_tma_kernel<NB, MMAJOR><<<grid, TTHREADS, smem, st>>>(tm, p);
     SKT_LAUNCH_CHECK();

@@ -204,17 +204,25 @@ class CudaBackend(object):
             return None
         key = (self.dev.torch().cuda.current_device(), tuple(int(d) for d in shape), tag)
         if key in CudaBackend._SYMM:
-            return CudaBackend._SYMM[key]
+            return CudaBackend._SYMM[key]      # (the outcome, None included, was agreed on by all ranks below)
+        t = self.dev.torch()
+        got = None
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            t = symm_mem.empty(key[1], dtype=self.dev.torch().float64, device=self.dev.device())
-            t.zero_()
-            hdl = symm_mem.rendezvous(t, dist.group.WORLD)
-            CudaBackend._SYMM[key] = (t, hdl)
-            return t, hdl
+            buf = symm_mem.empty(key[1], dtype=t.float64, device=self.dev.device())
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            got = (buf, hdl)
         except Exception:
-            CudaBackend._SYMM[key] = None
-            return None
+            got = None
+        # a rank that failed alone would take the NCCL path while the others wait in the peer-memory barrier:
+        # every rank uses the peer-memory path only if every rank got its buffer
+        ok = t.tensor([1 if got is not None else 0], dtype=t.int32, device=self.dev.device())
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            got = None
+        CudaBackend._SYMM[key] = got
+        return got
 
     def symm_barrier(self, hdl, channel=0):
         hdl.barrier(channel=channel)            # cross-rank barrier on the current stream
@@ -618,11 +626,15 @@ class CpAlsEngine(object):
         self.check_status(info)
         return float(fitout[0])
 
-    def download(self, U):
-        """Write the factors into the caller's list (in place) and return lambda."""
+    def release(self):
+        """Give back what the engine holds process-wide (the SM reserved for the side-stream pinv)."""
         if hasattr(self.be, 'release_side'):
             self.be.release_side()          # a speculative pinv of the next sweep may still be running
         self._pinv_pending = [None] * self.N
+
+    def download(self, U):
+        """Write the factors into the caller's list (in place) and return lambda."""
+        self.release()
         for m in range(self.N):
             if self.comm.active and m == self.s:
                 U[m] = self.comm.allgather_rows(self.Ud[m], self.offsets, self.be)

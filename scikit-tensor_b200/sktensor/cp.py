@@ -54,6 +54,9 @@ def als(X, rank, **kwargs):
     if not len(kwargs) == 0:
         raise ValueError('Unknown keywords (%s)' % (kwargs.keys()))
 
+    if int(maxiter) < 1:
+        # the reference leaves its loop without ever assigning the model and fails on an unbound name (cp.py:138,163-171)
+        raise ValueError('max_iter must be at least 1 (got %s)' % str(maxiter))
     N = X.ndim
     # one upload per call: the 'nvecs' initialisation and the sweep engine share the device copy
     pinned_here = hasattr(X, 'cache_on_device') and getattr(X, '_dev', None) is None and ainit == 'nvecs'
@@ -69,6 +72,13 @@ def als(X, rank, **kwargs):
         if pinned_here:
             X.drop_device_cache()
 
+    try:
+        return _sweeps(eng, U, maxiter, fit_method, conv)
+    finally:
+        eng.release()                     # gives the reserved SM back even when a sweep raises
+
+
+def _sweeps(eng, U, maxiter, fit_method, conv):
     fit = 0
     exectimes = []
     itr = -1
