@@ -91,24 +91,34 @@ def _hooi_dense_device(X, rank, U, maxIter, conv):
         tic = time.perf_counter()
         fitold = fit
         for n in range(N):
-            # Utilde = X x_{m != n} U_m^T (tucker.py:103, core.py:99-102).  The first -- by far the largest --
-            # contraction runs on the TMA / FP64 tensor-core kernel: the last mode for n < N-1, the first mode
-            # (result stored with the new mode last) for n = N-1.  `layout` lists which original mode sits at
-            # each position; the later, 12x smaller contractions and the Gram work on any position.
-            if n < N - 1:
-                Yd, yshape = K.ttm_dense(Xd, shape, Ud[N - 1], N - 1, True)
-                layout = list(range(N))
-            else:
-                Yd, yshape = K.ttm_dense_first_rot(Xd, shape, Ud[0])
-                layout = list(range(1, N)) + [0]
-            done = layout[-1]
-            for m in range(N):
-                if m != n and m != done:
+            # Utilde = X x_{m != n} U_m^T (tucker.py:103, core.py:99-102).  Only a contraction over the LAST mode
+            # (K-major GEMM, mode order kept) or over the FIRST mode (M-major GEMM, result stored with the new mode last)
+            # runs on the TMA / FP64 tensor-core kernel, so the chain is ordered greedily to hit those two positions:
+            # `layout` lists which original mode sits at each position; a mode stuck in the middle (one contraction of
+            # the n = 0 chain of a 3-way tensor) takes the tiled GEMM; the Gram works on any position.
+            Yd, yshape, layout = Xd, shape, list(range(N))
+            todo = [m for m in range(N) if m != n]
+            while todo:
+                if layout[-1] in todo:
+                    m = layout[-1]
+                    Yd, yshape = K.ttm_dense(Yd, yshape, Ud[m], len(layout) - 1, True)
+                elif layout[0] in todo:
+                    m = layout[0]
+                    Yd, yshape = K.ttm_dense_first_rot(Yd, yshape, Ud[m])
+                    layout = layout[1:] + [m]
+                else:
+                    m = todo[0]
                     Yd, yshape = K.ttm_dense(Yd, yshape, Ud[m], layout.index(m), True)
+                todo.remove(m)
             # U_n = leading eigenvectors of Utilde_(n) Utilde_(n)^T, descending, sign-fixed (core.py:275-306)
             G = K.unfold_gram(Yd, yshape, layout.index(n))
             Ud[n] = device_nvecs(G, rank[n])
-        core_d, core_shape = K.ttm_dense(Yd, yshape, Ud[N - 1], layout.index(N - 1), True)
+        # core = Utilde x_{N-1} U_{N-1}^T (tucker.py:105); the last mode sits first after its own chain
+        if layout[0] == N - 1:
+            core_d, core_shape = K.ttm_dense_first_rot(Yd, yshape, Ud[N - 1])
+            layout = layout[1:] + [N - 1]
+        else:
+            core_d, core_shape = K.ttm_dense(Yd, yshape, Ud[N - 1], layout.index(N - 1), True)
         normcore2 = float(dev.to_host(K.sumsq(core_d))[0])
         fit = 1 - (np.sqrt(max(normX2 - normcore2, 0.0)) / normX)
         fitchange = abs(fitold - fit)
