@@ -1,7 +1,7 @@
 // De-duplication of COO coordinates on the device -- the `accumfun` path of sptensor.__init__
 // (reference: sktensor/sptensor.py:80-84 -> sktensor/utils.py:5-26 `accum`: lexsort of the subscripts (last mode most
 // significant), boundaries where any subscript changes, `func` over each run of values).  Here: one 64-bit key per
-// non-zero (the column-major linear index), one stable radix sort (CUB, library, ingest only), run heads by comparison
+// non-zero (the column-major linear index), one stable radix sort (own kernels, radix_sort.cuh), run heads by comparison
 // with the predecessor, an inclusive scan for the output slots, and one thread per run reducing its values in storage
 // order (sum, max or min -- the reducers that can run on the device; other callables stay on the host).
 // The same machinery numbers the distinct keys of an array (skt_compact_keys): the sparse unfolding X_(n) only has as
@@ -9,9 +9,8 @@
 #include <algorithm>
 #include <cstring>
 
-#include <cub/cub.cuh>
-
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 namespace skt {
 namespace {
@@ -26,13 +25,14 @@ __global__ void accum_key_kernel(const long long *const *__restrict__ subs, cons
         perm[i] = (unsigned int)i;
     }
 }
-__global__ void head_flag_kernel(const unsigned long long *__restrict__ key, long long n, int *flag) {
+// slot[i] = 1 where a run of equal keys starts (exclusive-scanned in place afterwards: slot[i] = runs before i)
+__global__ void head_flag_kernel(const unsigned long long *__restrict__ key, long long n, unsigned int *slot) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+        slot[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
 }
 // one thread per run head: reduce the run's values in storage order
 __global__ void run_reduce_kernel(const unsigned long long *__restrict__ key, const unsigned int *__restrict__ perm,
-                                  const int *__restrict__ slot, const double *__restrict__ vals, long long n, int op,
+                                  const unsigned int *__restrict__ slot, const double *__restrict__ vals, long long n, int op,
                                   unsigned long long *out_key, double *out_val) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         if (i > 0 && key[i] == key[i - 1]) continue;
@@ -42,14 +42,17 @@ __global__ void run_reduce_kernel(const unsigned long long *__restrict__ key, co
             const double v = vals[perm[j]];
             acc = (op == 0) ? acc + v : (op == 1 ? (v > acc || v != v ? v : acc) : (v < acc || v != v ? v : acc));
         }
-        out_key[slot[i] - 1] = k;
-        out_val[slot[i] - 1] = acc;
+        out_key[slot[i]] = k;          // exclusive count of run heads before i = this run's output slot
+        out_val[slot[i]] = acc;
     }
 }
 // id of every element's key among the sorted distinct keys, scattered back to the original order
-__global__ void scatter_ids_kernel(const unsigned int *__restrict__ perm, const int *__restrict__ slot, long long n, int *ids) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        ids[perm[i]] = slot[i] - 1;
+__global__ void scatter_ids_kernel(const unsigned long long *__restrict__ key, const unsigned int *__restrict__ perm,
+                                   const unsigned int *__restrict__ slot, long long n, int *ids) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const bool head = (i == 0 || key[i] != key[i - 1]);
+        ids[perm[i]] = (int)slot[i] - (head ? 0 : 1);       // runs started up to and including i, minus one
+    }
 }
 
 __global__ void iota_u32_kernel(unsigned int *p, long long n) {
@@ -60,41 +63,39 @@ __global__ void iota_u32_kernel(unsigned int *p, long long n) {
 int blocks_for(long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 8LL * sm_count())); }
 
 struct SortedKeys {
-    unsigned long long *key = nullptr, *key_sorted = nullptr;
-    unsigned int *perm = nullptr, *perm_sorted = nullptr;
-    int *flag = nullptr, *slot = nullptr;
+    unsigned long long *key = nullptr, *key_b = nullptr, *key_sorted = nullptr;
+    unsigned int *perm = nullptr, *perm_b = nullptr, *perm_sorted = nullptr;
+    unsigned int *slot = nullptr;
     void *tmp = nullptr;
-    void release() {
-        cudaFree(key); cudaFree(key_sorted); cudaFree(perm); cudaFree(perm_sorted); cudaFree(flag); cudaFree(slot); cudaFree(tmp);
-    }
+    void release() { cudaFree(key); cudaFree(key_b); cudaFree(perm); cudaFree(perm_b); cudaFree(slot); cudaFree(tmp); }
 };
 
-// sort `key` (already filled, with perm = iota), flag run heads, scan -> slot; returns the number of distinct keys
+// sort `key` (already filled, with perm = iota), flag run heads, exclusive scan -> slot; returns the number of distinct keys
 int sort_and_number(SortedKeys &S, long long n, int bits, cudaStream_t st, long long *ndistinct) {
-    size_t tb1 = 0, tb2 = 0;
-    SKT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb1, S.key, S.key_sorted, S.perm, S.perm_sorted, (int)n, 0, bits, st));
-    SKT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb2, S.flag, S.slot, (int)n, st));
-    SKT_CUDA(cudaMalloc(&S.tmp, std::max(tb1, tb2) + 256));
-    size_t tb = std::max(tb1, tb2) + 256;
-    SKT_CUDA(cub::DeviceRadixSort::SortPairs(S.tmp, tb, S.key, S.key_sorted, S.perm, S.perm_sorted, (int)n, 0, bits, st));
-    head_flag_kernel<<<blocks_for(n), 256, 0, st>>>(S.key_sorted, n, S.flag);
+    SKT_CUDA(cudaMalloc(&S.tmp, rsort::scratch_bytes(n)));
+    int where = 0;
+    const int rc = rsort::sort_pairs<unsigned long long>(S.key, S.perm, S.key_b, S.perm_b, n, bits, S.tmp, st, &where);
+    if (rc != SKT_OK) return rc;
+    S.key_sorted = where ? S.key_b : S.key;
+    S.perm_sorted = where ? S.perm_b : S.perm;
+    head_flag_kernel<<<blocks_for(n), 256, 0, st>>>(S.key_sorted, n, S.slot);
     SKT_LAUNCH_CHECK();
-    tb = std::max(tb1, tb2) + 256;
-    SKT_CUDA(cub::DeviceScan::InclusiveSum(S.tmp, tb, S.flag, S.slot, (int)n, st));
-    int last = 0;
-    SKT_CUDA(cudaMemcpyAsync(&last, S.slot + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned int last_flag = 0, last_excl = 0;
+    SKT_CUDA(cudaMemcpyAsync(&last_flag, S.slot + (n - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    const int rc2 = rsort::inclusive_scan_u32(S.slot, n, S.tmp, st);       // (exclusive, in place)
+    if (rc2 != SKT_OK) return rc2;
+    SKT_CUDA(cudaMemcpyAsync(&last_excl, S.slot + (n - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     SKT_CUDA(cudaStreamSynchronize(st));
-    *ndistinct = last;
+    *ndistinct = (long long)last_excl + last_flag;
     return SKT_OK;
 }
 
 int alloc_sorted(SortedKeys &S, long long n) {
     SKT_CUDA(cudaMalloc(&S.key, n * sizeof(unsigned long long)));
-    SKT_CUDA(cudaMalloc(&S.key_sorted, n * sizeof(unsigned long long)));
+    SKT_CUDA(cudaMalloc(&S.key_b, n * sizeof(unsigned long long)));
     SKT_CUDA(cudaMalloc(&S.perm, n * sizeof(unsigned int)));
-    SKT_CUDA(cudaMalloc(&S.perm_sorted, n * sizeof(unsigned int)));
-    SKT_CUDA(cudaMalloc(&S.flag, n * sizeof(int)));
-    SKT_CUDA(cudaMalloc(&S.slot, n * sizeof(int)));
+    SKT_CUDA(cudaMalloc(&S.perm_b, n * sizeof(unsigned int)));
+    SKT_CUDA(cudaMalloc(&S.slot, n * sizeof(unsigned int)));
     return SKT_OK;
 }
 
@@ -193,7 +194,7 @@ extern "C" int skt_compact_keys(const uint64_t *keys_d, int64_t n, int key_bits,
         long long nd = 0;
         rc = sort_and_number(S, n, key_bits, st, &nd);
         if (rc == SKT_OK) {
-            scatter_ids_kernel<<<blocks_for(n), 256, 0, st>>>(S.perm_sorted, S.slot, n, ids_d);
+            scatter_ids_kernel<<<blocks_for(n), 256, 0, st>>>(S.key_sorted, S.perm_sorted, S.slot, n, ids_d);
             ++g_launches;
             if (cudaStreamSynchronize(st) != cudaSuccess) rc = SKT_ECUDA;
             *ndistinct = nd;

@@ -3,7 +3,7 @@
 // sptensor.py:153-177: gather-multiply, unique, searchsorted, bincount).
 //
 // Device format (built once per tensor by skt_coo_build): for every output mode n a copy of the
-// non-zeros stably radix-sorted by i_n -- int32 subscripts for all N modes plus the FP64 values,
+// non-zeros stably radix-sorted by i_n (own LSD radix sort, radix_sort.cuh) -- int32 subscripts for all N modes plus the FP64 values,
 // 4N+8 bytes per non-zero, which is exactly the compulsory index/value traffic of one MTTKRP.
 //
 // Kernel: all R rank columns in ONE pass.  A group of GS lanes (GS = next power of two >= R,
@@ -19,9 +19,8 @@
 #include <type_traits>
 #include <cstring>
 
-#include <cub/cub.cuh>
-
 #include "common.cuh"
+#include "radix_sort.cuh"
 
 struct skt_coo {
     int ndim;
@@ -669,9 +668,8 @@ extern "C" int skt_coo_build(const int64_t *const *subs_d, const double *vals_d,
     BUILD_TRY(cudaMalloc(&keys_out, n * sizeof(int)));
     BUILD_TRY(cudaMalloc(&perm_in, n * sizeof(unsigned int)));
     BUILD_TRY(cudaMalloc(&perm_out, n * sizeof(unsigned int)));
-    if (nnz > 0) iota_kernel<<<stream_blocks(nnz), 256, 0, st>>>(perm_in, nnz);
-    BUILD_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const int *)base[0], keys_out, (const unsigned int *)perm_in,
-                                              perm_out, (int)std::min<int64_t>(nnz, INT32_MAX), 0, 32, st));
+    BUILD_TRY(cudaMalloc(&pkey, n * sizeof(int)));
+    tmp_bytes = rsort::scratch_bytes((long long)n);
     BUILD_TRY(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 256));
 
     // Index-panel blocking.  A gathered factor much larger than L2 (config 3: the 10 M x 16 factor of mode 0, 1.28 GB) is
@@ -701,29 +699,35 @@ extern "C" int skt_coo_build(const int64_t *const *subs_d, const double *vals_d,
         t->panel_rows[nmode] = prow;
         int bits = 1;
         while ((1LL << bits) < shape[nmode] * P) ++bits;
+        const int *sorted_keys = keys_out;
+        const unsigned int *sorted_perm = perm_out;
         if (nnz > 0) {
-            const int *keys_in = base[nmode];
+            // sort key -> pkey (the sort ping-pongs between (pkey, perm_in) and (keys_out, perm_out))
             if (P > 1) {
-                if (!pkey) BUILD_TRY(cudaMalloc(&pkey, n * sizeof(int)));
                 panel_key_kernel<<<stream_blocks(nnz), 256, 0, st>>>(base[nmode], base[g], nnz, (int)shape[nmode], (int)prow, pkey);
-                keys_in = pkey;
+            } else {
+                BUILD_TRY(cudaMemcpyAsync(pkey, base[nmode], (size_t)nnz * sizeof(int), cudaMemcpyDeviceToDevice, st));
             }
-            BUILD_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out,
-                                                      (const unsigned int *)perm_in, perm_out, (int)nnz, 0, bits, st));
+            iota_kernel<<<stream_blocks(nnz), 256, 0, st>>>(perm_in, nnz);
+            int where = 0;
+            rc = rsort::sort_pairs<unsigned int>((unsigned int *)pkey, perm_in, (unsigned int *)keys_out, perm_out, nnz, bits,
+                                                 tmp, st, &where);
+            if (rc != SKT_OK) { cleanup(); skt_coo_destroy(t); return rc; }
+            if (where == 0) { sorted_keys = pkey; sorted_perm = perm_in; }
         }
         for (int m = 0; m < ndim; ++m) {
             BUILD_TRY(cudaMalloc(&t->idx[nmode][m], n * sizeof(int)));
             t->bytes += n * sizeof(int);
             if (nnz > 0) {
-                if (m == nmode && P > 1)      // the sorted keys ARE the virtual rows
-                    BUILD_TRY(cudaMemcpyAsync(t->idx[nmode][m], keys_out, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToDevice, st));
+                if (m == nmode)               // the sorted keys ARE the (virtual) rows
+                    BUILD_TRY(cudaMemcpyAsync(t->idx[nmode][m], sorted_keys, (size_t)nnz * sizeof(int), cudaMemcpyDeviceToDevice, st));
                 else
-                    gather_kernel<int><<<stream_blocks(nnz), 256, 0, st>>>(base[m], perm_out, nnz, t->idx[nmode][m]);
+                    gather_kernel<int><<<stream_blocks(nnz), 256, 0, st>>>(base[m], sorted_perm, nnz, t->idx[nmode][m]);
             }
         }
         BUILD_TRY(cudaMalloc(&t->vals[nmode], n * sizeof(double)));
         t->bytes += n * sizeof(double);
-        if (nnz > 0) gather_kernel<double><<<stream_blocks(nnz), 256, 0, st>>>(vals_d, perm_out, nnz, t->vals[nmode]);
+        if (nnz > 0) gather_kernel<double><<<stream_blocks(nnz), 256, 0, st>>>(vals_d, sorted_perm, nnz, t->vals[nmode]);
         t->built_mask |= (1u << nmode);
     }
     BUILD_TRY(cudaGetLastError());
