@@ -220,9 +220,17 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
                 if (j >= n) break;
                 double *col = Ablk + (size_t)t * n;
                 const double vj = vo[j], wj = po[j] + alo * vo[j];
-                for (int i = kk + 1 + lane; i < n; i += 32) {
-                    const double voi = vo[i];
-                    col[i] -= voi * wj + (po[i] + alo * voi) * vj;
+                if (p.Ag) {                                         // columns in L2: keep four loads in flight per lane
+#pragma unroll 4
+                    for (int i = kk + 1 + lane; i < n; i += 32) {
+                        const double voi = vo[i];
+                        col[i] -= voi * wj + (po[i] + alo * voi) * vj;
+                    }
+                } else {
+                    for (int i = kk + 1 + lane; i < n; i += 32) {
+                        const double voi = vo[i];
+                        col[i] -= voi * wj + (po[i] + alo * voi) * vj;
+                    }
                 }
             }
         }
@@ -235,7 +243,20 @@ __global__ void __launch_bounds__(ET, 1) symeig_cluster_kernel(const __grid_cons
             if (j >= n) break;
             const double *col = Ablk + (size_t)t * n;
             double acc = 0.0;
-            for (int i = kk + 1 + lane; i < n; i += 32) acc += col[i] * vc[i];
+            if (p.Ag) {                                             // columns in L2: four loads in flight per lane
+                double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+                int i = kk + 1 + lane;
+                for (; i + 96 < n; i += 128) {
+                    acc += col[i] * vc[i];
+                    acc1 += col[i + 32] * vc[i + 32];
+                    acc2 += col[i + 64] * vc[i + 64];
+                    acc3 += col[i + 96] * vc[i + 96];
+                }
+                for (; i < n; i += 32) acc += col[i] * vc[i];
+                acc = (acc + acc1) + (acc2 + acc3);
+            } else {
+                for (int i = kk + 1 + lane; i < n; i += 32) acc += col[i] * vc[i];
+            }
             acc = warp_sum(acc) * tau;
             if (lane < C) remote(pc, lane)[j] = acc;
         }
