@@ -284,6 +284,23 @@ class _Comm(object):
             parts = [out[w] for w in range(self.world)]
             self.dist.all_gather(parts, rec)
 
+    def reduce_scatter_rows(self, full, out):
+        """``out`` (chunk x R) = this rank's chunk of the sum over ranks of ``full`` (world * chunk x R)."""
+        try:
+            self.dist.reduce_scatter_tensor(out, full, op=self.dist.ReduceOp.SUM)
+        except Exception:           # backends without reduce-scatter (gloo): all-reduce, keep the own chunk
+            self.dist.all_reduce(full, op=self.dist.ReduceOp.SUM)
+            c = out.shape[0]
+            out.copy_(full[self.rank * c:(self.rank + 1) * c])
+
+    def allgather_chunks(self, chunk, full):
+        """``full`` (world * chunk x R) = the ranks' ``chunk`` buffers, in rank order."""
+        try:
+            self.dist.all_gather_into_tensor(full, chunk)
+        except Exception:
+            c = chunk.shape[0]
+            self.dist.all_gather([full[w * c:(w + 1) * c] for w in range(self.world)], chunk)
+
     def allgather_rows(self, local, offsets, backend):
         """Concatenate the ranks' row blocks (sizes from ``offsets``) into one host array."""
         if not self.active:
@@ -416,6 +433,33 @@ class CpAlsEngine(object):
                 if got is not None:
                     self.ex, self.exh = got
 
+        # ---- multi-GPU, tall replicated factor (sparse configs: 10^5 .. 10^6 rows): instead of all-reducing the full-height
+        # partial M_n and repeating the update of every row on every rank, reduce-scatter M_n, update the scattered rows in
+        # exchange form (one record per rank), all-gather the updated rows.  Same bytes on the wire as the
+        # all-reduce; the update work and its HBM traffic drop by the world size.
+        self.rs = [False] * N
+        self.rs_chunk = [0] * N
+        self.Mpad = [None] * N
+        self.Mloc = [None] * N
+        self.Upad = [None] * N
+        self.Uloc = [None] * N
+        if comm.active and self.exchange and os.environ.get('SKT_NO_SCATTERED_UPDATE', '0') != '1':
+            for m in range(N):
+                if m == self.s or self.cluster[m] or self.fused[m] or self.Mh[m] is not None:
+                    continue
+                rows = self.lshape[m]
+                if rows < int(os.environ.get('SKT_SCATTER_MIN_ROWS', '32768')):
+                    continue
+                chunk = (rows + comm.world - 1) // comm.world
+                self.rs[m], self.rs_chunk[m] = True, chunk
+                self.Mpad[m] = be.zeros((chunk * comm.world, R))
+                self.M[m] = self.Mpad[m][:rows]                 # the MTTKRP writes (and clears) the first `rows` rows only
+                self.Mloc[m] = be.zeros((chunk, R))
+                self.Upad[m] = be.zeros((chunk * comm.world, R))
+                self.Upad[m][:rows].copy_(self.Ud[m])
+                self.Ud[m] = self.Upad[m][:rows]
+                self.Uloc[m] = be.zeros((chunk, R))
+
         # modes whose pinv runs on the side stream: every mode that consumes a ready-made P
         has_async = hasattr(be, 'pinv_async') and os.environ.get('SKT_NO_CLUSTER_UPDATE', '0') != '1'
         self.apinv = [bool(has_async and (self.cluster[m] or (self.exchange and not self.fused[m]))) for m in range(N)]
@@ -498,8 +542,9 @@ class CpAlsEngine(object):
                     be.kr_reduce(self.TB, self.lshape[s:], self.Ud[s:], self.R, n - s, self.M[n])
         else:
             be.mttkrp_dense(self.Xd, self.lshape, self.Ud, self.R, n, self.M[n])
-        if self.comm.active and n != self.s and self.Mh[n] is None:
-            self.comm.allreduce_sum(self.M[n])          # (modes with a symmetric-memory M are summed inside the update kernel)
+        if self.comm.active and n != self.s and self.Mh[n] is None and not self.rs[n]:
+            self.comm.allreduce_sum(self.M[n])          # (modes with a symmetric-memory M are summed inside the update kernel;
+                                                        #  tall modes are reduce-scattered in sweep())
         return self.M[n]
 
     def _mark(self, label):
@@ -562,6 +607,16 @@ class CpAlsEngine(object):
             elif self.fused[n]:
                 # the same in one CTA, pinv included (no side stream)
                 be.update_fused(M, self.G, n, first_iter, self.Ud[n], self.lam, self.info[n:n + 1], *fit_args)
+                fit_done = fit_done or last
+            elif self.exchange and self.rs[n]:
+                # tall replicated factor on several GPUs: scattered update (see __init__)
+                chunk, rows = self.rs_chunk[n], self.lshape[n]
+                nloc = max(0, min(chunk, rows - comm.rank * chunk))
+                comm.reduce_scatter_rows(self.Mpad[n], self.Mloc[n])
+                be.update_exchange(self.Mloc[n][:nloc], P, first_iter, self.Uloc[n][:nloc], self.ex)
+                comm.allgather_records(self.ex, self.ex_all)
+                be.update_finish(self.ex_all, comm.world, first_iter, self.Uloc[n][:nloc], self.lam, self.G, n, *fit_args)
+                comm.allgather_chunks(self.Uloc[n], self.Upad[n])
                 fit_done = fit_done or last
             elif self.exchange:
                 # sharded mode / tall factor: one record per rank, one all-gather, one finishing kernel

@@ -44,6 +44,15 @@ def main():
     run('cp_d4_s3', dtensor(g['cp4_X']), 4, 3, init='random', max_iter=30)      # 4-way, sharded on the last mode
     subs = tuple(g['cpsp_sub%d' % m] for m in range(3))
     run('cp_sp_s1', sptensor(subs, g['cpsp_vals'], shape=(60, 50, 40)), 5, 1, init='random', max_iter=25)
+    # tall replicated factors take the scattered update (reduce-scatter, exchange-form update of the own rows,
+    # all-gather): forced here on a small tensor, same golden run
+    os.environ['SKT_SCATTER_MIN_ROWS'] = '1'
+    os.environ['SKT_NO_CLUSTER_UPDATE'] = '1'
+    os.environ['SKT_NO_FUSED_UPDATE'] = '1'
+    run('cp_sp_s1_scatter', sptensor(subs, g['cpsp_vals'], shape=(60, 50, 40)), 5, 1, init='random', max_iter=25)
+    run('cp_d4_s3_scatter', dtensor(g['cp4_X']), 4, 3, init='random', max_iter=30)
+    for k_ in ('SKT_SCATTER_MIN_ROWS', 'SKT_NO_CLUSTER_UPDATE', 'SKT_NO_FUSED_UPDATE'):
+        os.environ.pop(k_)
     # lopsided cuts: rank 0 owns every row of the sharded mode, all other ranks own EMPTY slabs (what happens for real
     # when a mode is shorter than the world size, or with power-law non-zero cuts); results must not change
     world = dist.get_world_size()

@@ -30,10 +30,10 @@ def test_sharded_cp_als_nccl(tmp_path, golden, world):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     results = [json.load(open('%s.%d' % (out, k))) for k in range(world)]
-    for key in ('cp_cfg1_s42', 'cp_cfg1_s42_it5', 'cp_kat3_s42', 'cp_d4_s3', 'cp_sp_s1', 'cp_cfg1_s42_lopsided',
+    for key in ('cp_cfg1_s42', 'cp_cfg1_s42_it5', 'cp_kat3_s42', 'cp_d4_s3', 'cp_sp_s1', 'cp_sp_s1_scatter', 'cp_d4_s3_scatter', 'cp_cfg1_s42_lopsided',
                 'cp_kat3_s42_lopsided', 'cp_cfg1_s42_othersymm', 'cp_d4_s3_othersymm'):
         # lopsided: empty slabs on all ranks but one; othersymm: NVLink peer-memory reductions toggled -- same golden run
-        gkey = key.replace('_lopsided', '').replace('_othersymm', '')
+        gkey = key.replace('_lopsided', '').replace('_scatter', '').replace('_othersymm', '')
         for res in results:
             got = res[key]
             assert got['itr'] == golden.j[gkey]['itr'], key
