@@ -94,9 +94,8 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
     d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
     return d;
 }
-__host__ __device__ constexpr uint32_t instr_desc(bool a_signed, bool b_signed) {
-    return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(TM >> 4) << 24);
+__host__ __device__ constexpr uint32_t instr_desc(int n) {     // S32 accumulate, signed x signed, both K-major, M = 128
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
 struct Params {
@@ -112,9 +111,12 @@ __device__ __forceinline__ void slice4(const double x[4], double scale, int S, u
     uint32_t lo[4], hi[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const double t = fma(x[e], scale, 6755399441055744.0);       // 1.5 * 2^52
-        lo[e] = (uint32_t)__double2loint(t);
-        hi[e] = (uint32_t)__double2hiint(t);
+        // 1.5 * 2^52 puts rint(x * scale) into the low mantissa bits (two's complement); the added 0x80 per lower byte and
+        // the XOR below turn its bytes into BALANCED digits (every byte signed, -128..127), so that all slice products are
+        // signed x signed and the B slices of one A slice can be stacked along N in a single MMA
+        const double t = fma(x[e], scale, 6755399441055744.0 + (S == 6 ? 551911719040.0 : 2155905152.0));
+        lo[e] = (uint32_t)__double2loint(t) ^ 0x80808080u;
+        hi[e] = (uint32_t)__double2hiint(t) ^ (S == 6 ? 0x80u : 0u);
     }
     const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
     const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
@@ -224,25 +226,31 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (lt >= 2) mbar_wait(&tempty[ab], ((lt >> 1) - 1) & 1u);
                 tc_fence_after();
                 const uint32_t tacc = tmem + ab * (uint32_t)(MAXS * N);
-                uint32_t started = 0;                            // accumulators that already hold a product of this tile
                 for (int c = 0; c < NCHUNK; ++c)
                     for (int i = S - 1; i >= 0; --i, ++u) {
                         const int st = u % NS;
                         mbar_wait(&full[st], (u / NS) & 1u);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(sA + st * STAGE_BYTES);
+                        // every B slice j >= j0 pairs with this A slice; they lie one after the other in shared memory
+                        // (32 rows each) and their products belong to the consecutive accumulators i + j: ONE MMA of
+                        // N = 32 (S - j0) columns per 32 bytes of K
                         const int j0 = p.smin - i > 0 ? p.smin - i : 0;
-                        for (int j = j0; j < S; ++j) {
-                            const uint32_t b_addr = smem_u32(sB + (c * MAXS + j) * BTILE_BYTES);
-                            const uint32_t idesc = instr_desc(i == S - 1, j == S - 1);
-                            const int a = i + j - p.smin;
-                            const uint32_t d = tacc + (uint32_t)(a * N);
-                            const uint32_t acc0 = (started >> a) & 1u;
-                            started |= 1u << a;
+                        const uint32_t b_addr = smem_u32(sB + (c * MAXS + j0) * BTILE_BYTES);
+                        const uint32_t idesc = instr_desc(N * (S - j0));
+                        const uint32_t d = tacc + (uint32_t)((i + j0 - p.smin) * N);
 #pragma unroll
-                            for (int ks = 0; ks < KC / 32; ++ks)
-                                umma_i8(d, smem_desc_sw128(a_addr + ks * 32), smem_desc_sw128(b_addr + ks * 32), idesc,
-                                        ks == 0 ? acc0 : 1u);
+                        for (int ks = 0; ks < KC / 32; ++ks) {
+                            const uint64_t da = smem_desc_sw128(a_addr + ks * 32), db = smem_desc_sw128(b_addr + ks * 32);
+                            if (c == 0 && ks == 0 && i == S - 1) {
+                                umma_i8(d, da, db, idesc, 0u);                  // first product of the tile: overwrite
+                            } else if (c == 0 && ks == 0 && i >= p.smin) {
+                                // this slice opens one more accumulator (its first 32 columns); the others already hold data
+                                umma_i8(d, da, db, instr_desc(N), 0u);
+                                umma_i8(d + N, da, smem_desc_sw128(b_addr + BTILE_BYTES + ks * 32), instr_desc(N * (S - 1)), 1u);
+                            } else {
+                                umma_i8(d, da, db, idesc, 1u);
+                            }
                         }
                         umma_commit(&empty[st]);
                     }
@@ -329,7 +337,7 @@ static double pow2_scale(double amax, int S) {          // largest 2^e with amax
     int ex;
     frexp(amax, &ex);                                   // amax = f * 2^ex, f in [0.5, 1)
     double sc = ldexp(1.0, 8 * S - 1 - ex);             // amax * sc in [2^(8S-2), 2^(8S-1))
-    if (rint(amax * sc) > ldexp(1.0, 8 * S - 1) - 1.0) sc *= 0.5;
+    if (rint(amax * sc) > ldexp(127.0, 8 * S - 8)) sc *= 0.5;       // balanced digits reach 127.5 * 256^(S-1)
     return sc;
 }
 
