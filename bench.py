@@ -306,6 +306,16 @@ def run_gpu(args):
             self.events.append((n, e0, e1))
             return r
 
+        def planes_ttm(self, planes, mode, U, R_, out):
+            if not self.record:
+                return _parallel.CudaBackend.planes_ttm(self, planes, mode, U, R_, out)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = _parallel.CudaBackend.planes_ttm(self, planes, mode, U, R_, out)
+            e1.record()
+            self.events.append((mode, e0, e1))
+            return r
+
     be = TimedBackend()
     eng = _parallel.CpAlsEngine(make_input(), R, init_factors(), backend=be)
     W = max(args.warmup, 3)
@@ -422,12 +432,71 @@ def run_gpu(args):
                        'fit read-back, final factor download; bytes are per iteration (upload amortised over '
                        '%d iterations)' % K2}
 
+    # ---- opt-in arm (not the headline): the same workload with both tree passes as sliced contractions on the INT8
+    # tensor cores (SKT_DENSE_I8=6: 48-bit fixed point per operand, csrc/slice_gemm.cu)
+    sliced = None
+    if not args.no_extras:
+        os.environ['SKT_DENSE_I8'] = '6'
+        try:
+            be2 = TimedBackend()
+            eng2 = _parallel.CpAlsEngine(make_input(), R, init_factors(), backend=be2)
+            if eng2.i8 is not None:
+                plane_bytes = eng2.i8.device_bytes()
+                be2.record = True
+                ms2, fit2_ = timed_sweeps(torch, dist, world, eng2, args.steps, W)
+                be2.record = False
+                ev = be2.events[-2 * args.steps:]
+                pass_ms = {}
+                for mode, e0, e1 in ev:
+                    pass_ms.setdefault(mode, []).append(e0.elapsed_time(e1))
+                eng2.release()
+                del eng2
+                torch.cuda.empty_cache()
+                runs = []
+                for rep in range(3):
+                    if world > 1:
+                        dist.barrier()
+                    np.random.seed(1)
+                    tic = time.perf_counter()
+                    cp_als(make_input(), R, init='random', max_iter=K2, conv=0)
+                    torch.cuda.synchronize()
+                    runs.append(time.perf_counter() - tic)
+                e2 = torch.tensor([float(np.median(runs))], dtype=torch.float64, device='cuda')
+                if world > 1:
+                    dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+                avg_pass = float(np.mean([d for v in pass_ms.values() for d in v]))
+                nelem = float(np.prod([float(d) for d in lshape]))
+                sliced = {
+                    'how': 'SKT_DENSE_I8=6 (opt-in; the headline above is the default FP64 DMMA path)',
+                    'ms_per_step': ms2, 'als_iters_per_sec': 1e3 / ms2, 'value_GBps': iter_bytes / (ms2 * 1e-3) / 1e9,
+                    'speedup_vs_default': ms_step / ms2, 'final_fit': fit2_, 'fit_delta_vs_default': abs(fit2_ - fit),
+                    'per_pass_ms': {('last-mode contraction (serves modes 0,1)' if m == 2 else
+                                     'first-mode contraction (+ second-stage reduction -> mode 2)'): float(np.mean(v))
+                                    for m, v in sorted(pass_ms.items())},
+                    'plane_bytes_per_gpu': plane_bytes,
+                    'e2e_als_iters_per_sec': K2 / float(e2.item()),
+                    'roofline': {'kernel': 'slice_gemm_kernel (tcgen05.mma.kind::i8, INT32 accumulators in tensor memory, TMA-fed; '
+                                           'streams 6 byte planes per element instead of 8 bytes of FP64)',
+                                 'bound': 'hbm', 'achieved': 6.0 * nelem / (avg_pass * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                                 'frac': 6.0 * nelem / (avg_pass * 1e-3) / 1e9 / hbm_peak, 'avg_launch_ms': avg_pass,
+                                 'note': 'per launch: the factor slicing kernel + the contraction; bytes = 6 per tensor element'},
+                    'accuracy': 'max|dT|/max|T| 4e-15 against the FP64 kernel on this tensor (tools/slices_perf.py); tests/test_gpu_slices.py',
+                }
+        except Exception as e:
+            sliced = {'error': '%s: %s' % (type(e).__name__, e)}
+            if world > 1:
+                raise
+        finally:
+            os.environ.pop('SKT_DENSE_I8', None)
+
     extras = {}
+    if sliced is not None:
+        extras['opt_in_int8_slices'] = sliced
     if not args.no_extras:
         try:
-            extras = secondary_configs(torch, dist, world, rank, args.steps)
+            extras.update(secondary_configs(torch, dist, world, rank, args.steps))
         except Exception as e:                      # the headline line must survive a failure of a secondary run
-            extras = {'extras_error': '%s: %s' % (type(e).__name__, e)}
+            extras['extras_error'] = '%s: %s' % (type(e).__name__, e)
             if world > 1:
                 raise
     if rank == 0:

@@ -244,6 +244,26 @@ SKT_API int    skt_cp_als_run(const double *X_d, const int64_t *shape, int ndim,
                       unsigned init_mask, int max_iter, double conv, int fit_full, double *lambda_d, void *ws_d,
                       size_t ws_bytes, double *fit_h, int *itr_h, double *exectimes_h, skt_stream stream);
 
+/* ---------------------------------------------------------------- opt-in: sliced contraction on the INT8 tensor cores
+ * The two partial contractions of the dense 3-way dimension tree (the unfolded product of dtensor.uttkrp,
+ * sktensor/dtensor.py:117-137, on the 2-way views  T[row, r] = sum_c X[.., c, ..] U[c, r]) computed FP64-accurately
+ * by error-free slicing: X is cut ONCE into `nslices` (6: 48-bit, 5: 40-bit) planes of balanced byte digits under one
+ * power-of-two scale; every pass streams those planes through tcgen05.mma.kind::i8 with INT32 accumulators in tensor
+ * memory and recombines them in FP64 (csrc/slice_gemm.cu).  The default path (skt_mttkrp_dense) stays FP64 DMMA.
+ * skt_planes_supported: 1 when skt_planes_ttm accepts (shape, mode, rank): mode first or last, rank <= 32, contracted
+ * mode <= 512, 16-byte aligned plane rows.  skt_planes_ttm: T_d (rows x rank, rows = the other modes in memory order).
+ * Error bound |dT| <= 2^-(8 nslices - 1) (max|X| sum_c |U[c,r]| + max_c |U[c,r]| sum_c |X|); non-finite input -> NaN. */
+typedef struct skt_planes skt_planes;
+SKT_API int    skt_planes_supported(const int64_t *shape, int ndim, int mode, int rank);
+SKT_API int    skt_planes_create(const double *X_d, const int64_t *shape, int ndim, int nslices, skt_planes **out,
+                         skt_stream stream);
+SKT_API int    skt_planes_destroy(skt_planes *p);
+SKT_API size_t skt_planes_device_bytes(const skt_planes *p);
+SKT_API int    skt_planes_nslices(const skt_planes *p);
+SKT_API size_t skt_planes_ttm_workspace(const skt_planes *p, int mode, int rank);
+SKT_API int    skt_planes_ttm(const skt_planes *p, int mode, const double *U_d, int rank, double *T_d, void *ws_d,
+                      size_t ws_bytes, skt_stream stream);
+
 /* ---------------------------------------------------------------- COO de-duplication (accumfun)
  * sptensor(subs, vals, accumfun=...) merges duplicate coordinates (sktensor/sptensor.py:80-84 -> utils.accum,
  * sktensor/utils.py:5-26: lexsort with the LAST mode most significant, `func` over every run).  Host arrays in, host

@@ -1,0 +1,572 @@
+// Opt-in: the two partial contractions of the 3-way dimension tree on the INT8 tensor cores (tcgen05.mma.kind::i8, TMEM
+// accumulators, TMA), FP64-accurate by error-free slicing.  The default dense path stays the FP64 DMMA kernel of
+// mttkrp_dense.cu; this one exists because at rank <= 32 that kernel is bound by the 37 TFLOP/s of the FP64 tensor pipe
+// (0.28 ms per 512^3 pass) while HBM would allow 0.16 ms.  Prototype and measurements: tools/slice_gemm_probe.cu.
+//
+//   T[row, r] = sum_c X[.., c, ..] U[c, r]     c = the LAST mode (rows = the other modes in memory order; K-major A operand)
+//                                              or the FIRST mode (MN-major A operand)
+//   replaces skt_mttkrp_dense on the 2-way views of sktensor/_parallel.py (`_tree_pass`), i.e. the unfolded product the
+//   reference forms with khatrirao + dot (sktensor/dtensor.py:117-137).
+//
+// Numbers.  v = rint(x * 2^e) is an S-byte two's-complement integer (S = 6: 48 bits, or 5: 40 bits; 2^e is one scale for
+// the whole tensor, one per column for the factor).  With 0x80 added to every lower byte its bytes, XOR 0x80, are BALANCED
+// digits d_s in [-128, 127], v = sum_s d_s 256^s: one DFMA with the constant 1.5 * 2^52 + 0x80..80 puts them in the low
+// mantissa bits, byte permutes move them into S planes.  X is sliced ONCE (it does not change during an ALS run), so a
+// pass streams S bytes per element instead of 8.  A slice product sum_c a_i[row, c] b_j[c, r] is an exact INT32 dot
+// product (128 * 128 * K * 6 pairs < 2^31 for K <= 512); all B slices j >= smin - i that pair with one A slice lie one after
+// the other in shared memory and feed the consecutive accumulators i + j, so ONE MMA of N = 32 (S - j0) columns covers
+// them.  Pairs with i + j < smin (S = 6: 4, S = 5: 2; at most 2^-52 of full scale) are skipped.  The epilogue recombines
+// the accumulators in FP64 (Horner in powers of 256) and applies the exact power-of-two scales.
+// Error: |dT| <= 2^-(8S-1) max|X| sum_c |U[c, r]| + the same with the roles swapped (normwise 1e-14 .. 1e-13 for S = 6 on
+// uniform / normal data, see tests/test_gpu_slices.py); non-finite input poisons the output with NaN.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+
+#include "common.cuh"
+
+struct skt_planes {
+    int ndim;
+    int64_t shape[SKT_MAX_NDIM];
+    int64_t total;
+    int S;
+    unsigned char *planes;      // S planes of `total` bytes, each in X's memory order
+    double *scale;              // device: [0] = 2^e, [1] = 2^-e (NaN when max|X| is not finite)
+    unsigned long long *amax;   // device: bits of max|X|
+    int device;
+};
+
+namespace skt {
+namespace {
+
+constexpr int NB = 32;                  // columns per slice (rank padded with zero digits)
+constexpr int TM = 128;                 // rows per tile = TMEM lanes
+constexpr int KC = 128;                 // contraction bytes per stage
+constexpr int MAXS = 6;
+constexpr int MAXK = 512;
+constexpr int STAGE_BYTES = TM * KC;
+constexpr int BTILE_BYTES = NB * KC;
+constexpr int GEMM_THREADS = 192;
+
+constexpr int MAXACC = 7;               // accumulators (pair sums smin .. 2(S-1)) per set; two sets of 224 columns
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]: 128 x n x 32 bytes of K, signed 8-bit operands, INT32 accumulators (SASS: UTCIMMA)
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor, SWIZZLE_128B, 128-byte rows, 8-row groups 1024 bytes apart (both majors of this file)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset: one swizzle atom wide, never stepped
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+    d |= (uint64_t)1 << 46;                 // descriptor version of sm_100
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: S32 accumulate, signed x signed, B K-major, A K-major or MN-major, M = 128, N = n
+__device__ __forceinline__ uint32_t instr_desc(int n, bool a_mn) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+// ---- slicing ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void slice4(const double x[4], double scale, int S, uint32_t w[MAXS]) {
+    uint32_t lo[4], hi[4];
+    const double magic = 6755399441055744.0 + (S == 6 ? 551911719040.0 : 2155905152.0);     // 1.5 * 2^52 + 0x80..80
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const double t = fma(x[e], scale, magic);
+        lo[e] = (uint32_t)__double2loint(t) ^ 0x80808080u;
+        hi[e] = (uint32_t)__double2hiint(t) ^ (S == 6 ? 0x80u : 0u);
+    }
+    const uint32_t t0 = __byte_perm(lo[0], lo[1], 0x5140), t1 = __byte_perm(lo[2], lo[3], 0x5140);
+    const uint32_t t2 = __byte_perm(lo[0], lo[1], 0x7362), t3 = __byte_perm(lo[2], lo[3], 0x7362);
+    const uint32_t t4 = __byte_perm(hi[0], hi[1], 0x5140), t5 = __byte_perm(hi[2], hi[3], 0x5140);
+    w[0] = __byte_perm(t0, t1, 0x5410);
+    w[1] = __byte_perm(t0, t1, 0x7632);
+    w[2] = __byte_perm(t2, t3, 0x5410);
+    w[3] = __byte_perm(t2, t3, 0x7632);
+    w[4] = __byte_perm(t4, t5, 0x5410);
+    w[5] = __byte_perm(t4, t5, 0x7632);
+}
+
+// largest 2^e with rint(amax 2^e) representable by S balanced digits (<= 127 * 256^(S-1)); 1 for amax = 0
+__device__ double pow2_scale(double amax, int S) {
+    if (!(amax > 0.0)) return 1.0;
+    const int ex = ilogb(amax) + 1;                     // amax = f 2^ex, f in [0.5, 1)
+    double sc = ldexp(1.0, max(-1000, min(1000, 8 * S - 1 - ex)));
+    if (rint(amax * sc) > ldexp(127.0, 8 * S - 8)) sc *= 0.5;
+    return sc;
+}
+
+__global__ void planes_absmax_kernel(const double *__restrict__ X, long long n, unsigned long long *out) {
+    double m = 0.0;
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double a = fabs(X[i]);
+        bad |= !(a <= DBL_MAX);
+        m = fmax(m, a);
+    }
+    if (bad) m = __longlong_as_double(0x7ff0000000000000ll);
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void planes_scale_kernel(const unsigned long long *amax_bits, int S, double *scale) {
+    const double amax = __longlong_as_double((long long)amax_bits[0]);
+    if (!(amax <= DBL_MAX)) {
+        scale[0] = 0.0;
+        scale[1] = nan("");
+    } else {
+        const double sc = pow2_scale(amax, S);
+        scale[0] = sc;
+        scale[1] = 1.0 / sc;
+    }
+}
+
+__global__ void planes_slice_kernel(const double *__restrict__ X, long long total4, long long plane4, const double *scale_d, int S,
+                                    uint32_t *__restrict__ P) {
+    const double scale = scale_d[0];
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
+        const double2 a = reinterpret_cast<const double2 *>(X)[2 * q], b = reinterpret_cast<const double2 *>(X)[2 * q + 1];
+        const double x[4] = {a.x, a.y, b.x, b.y};
+        uint32_t w[MAXS];
+        slice4(x, scale, S, w);
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s)
+            if (s < S) P[s * plane4 + q] = w[s];
+    }
+}
+
+// factor U [Kc x R] row-major -> planes Bp[s][n][kpad] (K-major rows of U^T, zero beyond Kc and R), one block per column;
+// inv[n] = 256^smin / (scale_X * scale_n)
+__global__ void __launch_bounds__(128) factor_slice_kernel(const double *__restrict__ U, int Kc, int R, int kpad, int S,
+                                                           int smin, const double *__restrict__ xscale,
+                                                           uint32_t *__restrict__ Bp, double *__restrict__ inv) {
+    __shared__ double red[4];
+    __shared__ double sc_s;
+    const int n = blockIdx.x;
+    double m = 0.0;
+    bool bad = false;
+    if (n < R)
+        for (int k = threadIdx.x; k < Kc; k += 128) {
+            const double a = fabs(U[(size_t)k * R + n]);
+            bad |= !(a <= DBL_MAX);
+            m = fmax(m, a);
+        }
+    if (bad) m = __longlong_as_double(0x7ff0000000000000ll);
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double amax = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+        const bool finite = amax <= DBL_MAX;
+        const double sc = finite ? pow2_scale(amax, S) : 0.0;
+        sc_s = sc;
+        inv[n] = finite ? ldexp(1.0, 8 * smin) * xscale[1] / sc : nan("");
+    }
+    __syncthreads();
+    const double sc = sc_s;
+    for (int k4 = threadIdx.x; k4 < kpad / 4; k4 += 128) {
+        double x[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = 4 * k4 + e;
+            x[e] = (n < R && k < Kc) ? U[(size_t)k * R + n] : 0.0;
+        }
+        uint32_t w[MAXS];
+        slice4(x, sc, S, w);
+        const bool pad = n >= R || sc == 0.0;
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s)
+            if (s < S) Bp[((size_t)s * NB + n) * (kpad / 4) + k4] = pad ? 0u : w[s];
+    }
+}
+
+// ---- the contraction --------------------------------------------------------------------------------------------------
+struct GemmParams {
+    long long rows;      // output rows (GEMM M)
+    int tiles;           // ceil(rows / 128)
+    int nchunk;          // ceil(Kc / 128)
+    int S, R, NS, smin;
+    double *T;           // rows x R
+    const double *inv;   // per column
+};
+
+// warp 0: TMA producer, warp 1: MMA issuer (owns the tensor memory), warps 2..5: epilogue (one TMEM lane quarter each)
+template <bool A_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int S = p.S, NS = p.NS, smin = p.smin;
+    unsigned char *sB = smem;                                      // [chunk][slice] tiles of 32 rows x 128 bytes
+    unsigned char *sA = smem + (size_t)p.nchunk * S * BTILE_BYTES;  // NS stages of 128 x 128 bytes
+    uint64_t *bars = (uint64_t *)(sA + (size_t)NS * STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + NS, *bfull = bars + 2 * NS, *tfull = bars + 2 * NS + 1, *tempty = bars + 2 * NS + 3;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NS + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(bfull, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    constexpr int ACC_COLS = MAXACC * NB;                          // columns of one accumulator set (two sets: 448 of 512)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bfull, (uint32_t)(p.nchunk * S * BTILE_BYTES));
+            for (int c = 0; c < p.nchunk; ++c)
+                for (int j = 0; j < S; ++j) tma_load_3d(sB + (size_t)(c * S + j) * BTILE_BYTES, &tmB, bfull, c * KC, 0, j);
+            int st = 0;
+            uint32_t ph = 0;
+            bool wrapped = false;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
+                for (int c = 0; c < p.nchunk; ++c)
+                    for (int i = S - 1; i >= 0; --i) {
+                        if (wrapped) mbar_wait(&empty[st], ph ^ 1u);
+                        mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+                        if (A_MN)
+                            tma_load_3d(sA + (size_t)st * STAGE_BYTES, &tmA, &full[st], tile * TM, c * KC, i);
+                        else
+                            tma_load_3d(sA + (size_t)st * STAGE_BYTES, &tmA, &full[st], c * KC, tile * TM, i);
+                        if (++st == NS) {
+                            st = 0;
+                            ph ^= 1u;
+                            wrapped = true;
+                        }
+                    }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(bfull, 0);
+            int st = 0;
+            uint32_t ph = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+                const uint32_t ab = lt & 1u;
+                if (lt >= 2) mbar_wait(&tempty[ab], ((lt >> 1) - 1) & 1u);
+                tc_fence_after();
+                const uint32_t tacc = tmem + ab * (uint32_t)ACC_COLS;
+                for (int c = 0; c < p.nchunk; ++c)
+                    for (int i = S - 1; i >= 0; --i) {
+                        mbar_wait(&full[st], ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(sA + (size_t)st * STAGE_BYTES);
+                        const int j0 = smin - i > 0 ? smin - i : 0;
+                        const uint32_t b_addr = smem_u32(sB + (size_t)(c * S + j0) * BTILE_BYTES);
+                        const uint32_t idesc = instr_desc(NB * (S - j0), A_MN);
+                        const uint32_t d = tacc + (uint32_t)((i + j0 - smin) * NB);
+                        // K-major A: 32 bytes further along the 128-byte rows; MN-major A: 32 rows (4 groups of 8) further
+                        constexpr uint32_t A_STEP = A_MN ? 32 * 128 : 32;
+#pragma unroll
+                        for (int ks = 0; ks < KC / 32; ++ks) {
+                            const uint64_t da = smem_desc_sw128(a_addr + ks * A_STEP), db = smem_desc_sw128(b_addr + ks * 32);
+                            if (c == 0 && ks == 0 && i == S - 1) {
+                                umma_i8(d, da, db, idesc, 0u);           // first product of the tile: overwrite
+                            } else if (c == 0 && ks == 0 && i >= smin) {
+                                // this slice opens one more accumulator (its first 32 columns); the others hold data already
+                                umma_i8(d, da, db, instr_desc(NB, A_MN), 0u);
+                                umma_i8(d + NB, da, smem_desc_sw128(b_addr + BTILE_BYTES + ks * 32), instr_desc(NB * (S - 1), A_MN),
+                                        1u);
+                            } else {
+                                umma_i8(d, da, db, idesc, 1u);
+                            }
+                        }
+                        umma_commit(&empty[st]);
+                        if (++st == NS) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                umma_commit(&tfull[ab]);
+            }
+        }
+    } else {
+        const int q = warp & 3;                                    // the TMEM lane quarter this warp may read
+        const int nacc = 2 * (S - 1) - smin + 1;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+            const uint32_t ab = lt & 1u;
+            mbar_wait(&tfull[ab], (lt >> 1) & 1u);
+            tc_fence_after();
+            double r[NB];
+#pragma unroll
+            for (int n = 0; n < NB; ++n) r[n] = 0.0;
+            for (int a = nacc - 1; a >= 0; --a) {
+                uint32_t v[NB];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)ACC_COLS + (uint32_t)(a * NB);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                    "tcgen05.wait::ld.sync.aligned;\n"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+#pragma unroll
+                for (int n = 0; n < NB; ++n) r[n] = fma(r[n], 256.0, (double)(int)v[n]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[ab]);
+            const long long row = (long long)tile * TM + q * 32 + lane;
+            if (row < p.rows) {
+                double *out = p.T + row * p.R;
+                if (p.R == NB) {
+#pragma unroll
+                    for (int n = 0; n < NB; n += 2) {
+                        double2 o;
+                        o.x = r[n] * p.inv[n];
+                        o.y = r[n + 1] * p.inv[n + 1];
+                        *reinterpret_cast<double2 *>(out + n) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int n = 0; n < NB; ++n)
+                        if (n < p.R) out[n] = r[n] * p.inv[n];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// byte tensor (inner, outer, slice) with a box of 128 x box_outer x 1, 128-byte swizzle, zero fill outside
+int byte_map3(const void *base, uint64_t inner, uint64_t outer, uint64_t slices, uint64_t outer_stride, uint64_t slice_stride,
+              uint32_t box_outer, CUtensorMap &tm) {
+    EncodeTiledFn enc = encode_fn();
+    SKT_REQUIRE(enc != nullptr, SKT_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[3] = {inner, outer, slices}, strides[2] = {outer_stride, slice_stride};
+    cuuint32_t box[3] = {KC, box_outer, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SKT_REQUIRE(r == CUDA_SUCCESS, SKT_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SKT_OK;
+}
+
+struct TtmPlan {
+    bool a_mn;
+    long long rows;
+    int Kc, nchunk, kpad;
+};
+
+int plan_ttm(const skt_planes *P, int mode, int R, TtmPlan &pl) {
+    SKT_REQUIRE(P != nullptr, SKT_EINVAL, "null planes handle");
+    SKT_REQUIRE(P->ndim >= 2 && (mode == 0 || mode == P->ndim - 1), SKT_EUNSUPPORTED,
+                "the sliced contraction runs over the first or the last mode (got mode %d of %d)", mode, P->ndim);
+    SKT_REQUIRE(R >= 1 && R <= NB, SKT_EUNSUPPORTED, "the sliced contraction supports rank 1..%d (got %d)", NB, R);
+    pl.a_mn = (mode == 0);
+    pl.Kc = (int)P->shape[mode];
+    SKT_REQUIRE(pl.Kc >= 1 && pl.Kc <= MAXK, SKT_EUNSUPPORTED, "the sliced contraction supports a contracted mode of 1..%d (got %d)",
+                MAXK, pl.Kc);
+    pl.rows = P->total / pl.Kc;
+    SKT_REQUIRE(P->total % 16 == 0 && (pl.a_mn ? pl.rows % 16 == 0 : pl.Kc % 16 == 0), SKT_EUNSUPPORTED,
+                "the sliced contraction needs 16-byte aligned rows of the byte planes");
+    SKT_REQUIRE(pl.rows < (1ll << 31) * 1ll, SKT_EUNSUPPORTED, "too many rows");
+    pl.nchunk = (pl.Kc + KC - 1) / KC;
+    pl.kpad = pl.nchunk * KC;
+    return SKT_OK;
+}
+
+size_t ttm_ws(const TtmPlan &pl, int S) { return align_up((size_t)S * NB * pl.kpad, 256) + align_up(NB * sizeof(double), 256); }
+
+}  // namespace
+}  // namespace skt
+
+using namespace skt;
+
+extern "C" {
+
+int skt_planes_supported(const int64_t *shape, int ndim, int mode, int rank) {
+    if (!shape || ndim < 2 || ndim > SKT_MAX_NDIM || (mode != 0 && mode != ndim - 1) || rank < 1 || rank > NB) return 0;
+    long long total = 1;
+    for (int m = 0; m < ndim; ++m) {
+        if (shape[m] < 1) return 0;
+        total *= shape[m];
+    }
+    const long long Kc = shape[mode], rows = total / Kc;
+    if (Kc > MAXK || total % 16 != 0 || rows >= (1ll << 31)) return 0;
+    return (mode == 0 ? rows % 16 == 0 : Kc % 16 == 0) ? 1 : 0;
+}
+
+int skt_planes_create(const double *X_d, const int64_t *shape, int ndim, int nslices, skt_planes **out, skt_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SKT_REQUIRE(X_d && shape && out, SKT_EINVAL, "null argument");
+    SKT_REQUIRE(ndim >= 2 && ndim <= SKT_MAX_NDIM, SKT_EINVAL, "ndim %d outside [2, %d]", ndim, SKT_MAX_NDIM);
+    SKT_REQUIRE(nslices == 5 || nslices == 6, SKT_EINVAL, "nslices must be 5 (40-bit) or 6 (48-bit), got %d", nslices);
+    int cc_major = 0, dev = 0;
+    SKT_CUDA(cudaGetDevice(&dev));
+    SKT_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    SKT_REQUIRE(cc_major == 10, SKT_EUNSUPPORTED, "the sliced contraction needs the tcgen05 tensor cores of sm_100a");
+    long long total = 1;
+    for (int m = 0; m < ndim; ++m) {
+        SKT_REQUIRE(shape[m] >= 1, SKT_EINVAL, "empty mode %d", m);
+        total *= shape[m];
+    }
+    SKT_REQUIRE(total % 4 == 0 && (((uintptr_t)X_d) & 15) == 0, SKT_EUNSUPPORTED, "the byte planes need a 16-byte aligned tensor");
+    skt_planes *P = new skt_planes();
+    P->ndim = ndim;
+    for (int m = 0; m < ndim; ++m) P->shape[m] = shape[m];
+    P->total = total;
+    P->S = nslices;
+    P->device = dev;
+    P->planes = nullptr;
+    P->scale = nullptr;
+    P->amax = nullptr;
+    cudaError_t e = cudaMalloc((void **)&P->planes, (size_t)nslices * total);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&P->scale, 256);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&P->amax, 256);
+    if (e == cudaSuccess) e = cudaMemsetAsync(P->amax, 0, 8, st);
+    if (e != cudaSuccess) {
+        skt_planes_destroy(P);
+        return cuda_fail(e, "allocating the byte planes", __FILE__, __LINE__);
+    }
+    const int grid = 8 * sm_count();
+    planes_absmax_kernel<<<grid, 256, 0, st>>>(X_d, total, P->amax);
+    ++g_launches;
+    planes_scale_kernel<<<1, 1, 0, st>>>(P->amax, nslices, P->scale);
+    ++g_launches;
+    planes_slice_kernel<<<2 * grid, 256, 0, st>>>(X_d, total / 4, total / 4, P->scale, nslices, (uint32_t *)P->planes);
+    ++g_launches;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        skt_planes_destroy(P);
+        return cuda_fail(e, "slicing kernels", __FILE__, __LINE__);
+    }
+    *out = P;
+    return SKT_OK;
+}
+
+int skt_planes_destroy(skt_planes *P) {
+    if (!P) return SKT_OK;
+    if (P->planes) cudaFree(P->planes);
+    if (P->scale) cudaFree(P->scale);
+    if (P->amax) cudaFree(P->amax);
+    delete P;
+    return SKT_OK;
+}
+
+size_t skt_planes_device_bytes(const skt_planes *P) { return P ? (size_t)P->S * P->total + 512 : 0; }
+int skt_planes_nslices(const skt_planes *P) { return P ? P->S : 0; }
+
+size_t skt_planes_ttm_workspace(const skt_planes *P, int mode, int rank) {
+    TtmPlan pl;
+    if (plan_ttm(P, mode, rank, pl) != SKT_OK) return 0;
+    return ttm_ws(pl, P->S);
+}
+
+int skt_planes_ttm(const skt_planes *P, int mode, const double *U_d, int rank, double *T_d, void *ws_d, size_t ws_bytes,
+                   skt_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    TtmPlan pl;
+    const int rc = plan_ttm(P, mode, rank, pl);
+    if (rc) return rc;
+    SKT_REQUIRE(U_d && T_d, SKT_EINVAL, "null argument");
+    const int S = P->S;
+    int smin = S == 6 ? 4 : 2;                          // pairs below it: < 2^-52 of full scale
+    if (const char *e = getenv("SKT_I8_SMIN")) smin = std::max(2 * (S - 1) + 1 - MAXACC, std::min(S - 1, atoi(e)));
+    const size_t need = ttm_ws(pl, S);
+    SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    SKT_REQUIRE((((uintptr_t)ws_d) & 255) == 0 && (((uintptr_t)T_d) & 15) == 0, SKT_EINVAL, "misaligned workspace or output");
+    unsigned char *Bp = (unsigned char *)ws_d;
+    double *inv = (double *)(Bp + align_up((size_t)S * NB * pl.kpad, 256));
+
+    factor_slice_kernel<<<NB, 128, 0, st>>>(U_d, pl.Kc, rank, pl.kpad, S, smin, P->scale, (uint32_t *)Bp, inv);
+    SKT_LAUNCH_CHECK();
+
+    CUtensorMap tmA, tmB;
+    int e;
+    if (pl.a_mn)
+        e = byte_map3(P->planes, (uint64_t)pl.rows, (uint64_t)pl.Kc, (uint64_t)S, (uint64_t)pl.rows, (uint64_t)P->total, KC, tmA);
+    else
+        e = byte_map3(P->planes, (uint64_t)pl.Kc, (uint64_t)pl.rows, (uint64_t)S, (uint64_t)pl.Kc, (uint64_t)P->total, TM, tmA);
+    if (e) return e;
+    e = byte_map3(Bp, (uint64_t)pl.kpad, NB, (uint64_t)S, (uint64_t)pl.kpad, (uint64_t)NB * pl.kpad, NB, tmB);
+    if (e) return e;
+
+    GemmParams gp;
+    gp.rows = pl.rows;
+    gp.tiles = (int)((pl.rows + TM - 1) / TM);
+    gp.nchunk = pl.nchunk;
+    gp.S = S;
+    gp.R = rank;
+    gp.smin = smin;
+    gp.T = T_d;
+    gp.inv = inv;
+    const size_t fixed = 1024 + (size_t)pl.nchunk * S * BTILE_BYTES + 256;
+    const size_t cap = smem_optin_bytes();
+    SKT_REQUIRE(cap >= fixed + 2 * STAGE_BYTES, SKT_EUNSUPPORTED, "not enough shared memory for the sliced contraction");
+    gp.NS = (int)std::min<size_t>(12, (cap - fixed) / STAGE_BYTES);
+    const size_t smem = fixed + (size_t)gp.NS * STAGE_BYTES;
+    const int grid = std::min(gp.tiles, sm_count());
+    static unsigned long long attr_mask[2] = {0, 0};
+    if (pl.a_mn) {
+        if (first_use_on_device(attr_mask[1]))
+            SKT_CUDA(cudaFuncSetAttribute(slice_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        slice_gemm_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, gp);
+    } else {
+        if (first_use_on_device(attr_mask[0]))
+            SKT_CUDA(cudaFuncSetAttribute(slice_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        slice_gemm_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, gp);
+    }
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+}  // extern "C"

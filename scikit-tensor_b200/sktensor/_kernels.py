@@ -142,6 +142,54 @@ class CooHandle(object):
             pass
 
 
+class PlanesHandle(object):
+    """Owner of the byte-digit planes of a dense device tensor (``skt_planes*``): the opt-in sliced contraction on the
+    INT8 tensor cores (csrc/slice_gemm.cu).  ``nslices`` 6 = 48-bit, 5 = 40-bit fixed point under one scale."""
+
+    def __init__(self, X_d, shape, nslices=6):
+        lib = _lib.load()
+        dev.require_cuda()
+        self.shape = tuple(int(s) for s in shape)
+        self.ndim = len(self.shape)
+        self.nslices = int(nslices)
+        h = C.c_void_p()
+        _lib.check(lib.skt_planes_create(dev.ptr(X_d), _lib.shape_array(self.shape), self.ndim, self.nslices, C.byref(h),
+                                         dev.stream_ptr()))
+        self.h = h
+
+    @staticmethod
+    def supported(shape, mode, rank):
+        shape = tuple(int(s) for s in shape)
+        return bool(_lib.load().skt_planes_supported(_lib.shape_array(shape), len(shape), int(mode), int(rank)))
+
+    def device_bytes(self):
+        return int(_lib.load().skt_planes_device_bytes(self.h))
+
+    def ttm(self, mode, U, rank, out=None):
+        """``T[row, r] = sum_c X[.., c, ..] U[c, r]`` over the first or the last mode; rows in memory order."""
+        lib = _lib.load()
+        rows = 1
+        for m, d in enumerate(self.shape):
+            if m != mode:
+                rows *= d
+        if out is None:
+            out = dev.empty((rows, rank))
+        ws, wsz = dev.workspace('mttkrp').get(lib.skt_planes_ttm_workspace(self.h, mode, rank))
+        _lib.check(lib.skt_planes_ttm(self.h, mode, dev.ptr(U), rank, dev.ptr(out), ws, wsz, dev.stream_ptr()))
+        return out
+
+    def close(self):
+        if getattr(self, 'h', None):
+            _lib.load().skt_planes_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 _ACCUM_OPS = {'sum': 0, 'max': 1, 'min': 2}
 
 

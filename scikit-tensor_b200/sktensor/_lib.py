@@ -94,6 +94,13 @@ PROTOTYPES = {
     'skt_unfold_gram_workspace': (C.c_size_t, [c_i64p, C.c_int, C.c_int]),
     'skt_unfold_gram': (C.c_int, [c_dp, c_i64p, C.c_int, C.c_int, c_dp, C.c_void_p, C.c_size_t, c_stream]),
     'skt_probe_fp64_peaks': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    'skt_planes_supported': (C.c_int, [c_i64p, C.c_int, C.c_int, C.c_int]),
+    'skt_planes_create': (C.c_int, [c_dp, c_i64p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_stream]),
+    'skt_planes_destroy': (C.c_int, [C.c_void_p]),
+    'skt_planes_device_bytes': (C.c_size_t, [C.c_void_p]),
+    'skt_planes_nslices': (C.c_int, [C.c_void_p]),
+    'skt_planes_ttm_workspace': (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    'skt_planes_ttm': (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, c_dp, C.c_void_p, C.c_size_t, c_stream]),
     'skt_coo_accumulate_host': (C.c_int, [c_voidpp, c_dp, C.c_int64, c_i64p, c_i64p, C.c_int, C.c_int, C.c_void_p, c_dp,
                                           C.POINTER(C.c_int64)]),
     'skt_compact_keys': (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_int64), c_stream]),

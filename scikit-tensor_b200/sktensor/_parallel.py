@@ -144,6 +144,9 @@ class CudaBackend(object):
     def mttkrp_dense(self, Xd, shape, U, R, n, out): return self.K.mttkrp_dense(Xd, shape, U, R, n, out=out)
     def mttkrp_coo(self, coo, U, R, n, out): return self.K.mttkrp_coo(coo, U, R, n, out=out)
     def kr_reduce(self, T, dims, W, R, n, out): return self.K.kr_reduce(T, dims, W, R, n, out=out)
+    def planes_supported(self, shape, mode, R): return self.K.PlanesHandle.supported(shape, mode, R)
+    def planes_create(self, Xd, shape, nslices): return self.K.PlanesHandle(Xd, shape, nslices)
+    def planes_ttm(self, planes, mode, U, R, out): return planes.ttm(mode, U, R, out=out)
     def kr_reduce_slab_buffer(self, dims, R, n): return self.empty((max(1, self.K.kr_reduce_workspace(dims, R, n) // 8),))
     def kr_reduce_slabs(self, T, dims, W, R, n, slabs): return self.K.kr_reduce_slabs(T, dims, W, R, n, slabs)
     def update_cluster_slabs(self, slabs, nslabs, P, G, n, first, U, lam, ip, normX2, fit):
@@ -469,6 +472,7 @@ class CpAlsEngine(object):
         # served by T_A = X contracted with U_s..U_{N-1}; modes [s, N) by T_B = X contracted with
         # U_0..U_{s-1}.  A one-mode group needs no second stage: its partial tensor IS the MTTKRP.
         self.slabbuf = [None] * N        # per mode: buffer for un-summed second-stage slabs (see below)
+        self.i8 = None                   # byte planes of X for the opt-in sliced passes
         self.nslabs = [0] * N
         self.tree = (not self.sparse) and N >= 3 and hasattr(be, 'kr_reduce') and \
             os.environ.get('SKT_NO_DIMTREE', '0') != '1'
@@ -480,6 +484,15 @@ class CpAlsEngine(object):
             self.shapeB = tuple(self.lshape[:s]) + (nB,)
             self.TA = self.M[0] if s == 1 else be.empty((nA, R))
             self.TB = self.M[N - 1] if s == N - 1 else be.empty((nB, R))
+            # opt-in (SKT_DENSE_I8=6 | 5 | 1): both passes of a 3-way tree as sliced contractions on the INT8 tensor cores
+            # (csrc/slice_gemm.cu).  X is cut into byte planes once; a pass whose group holds two modes becomes the GEMM
+            # over the outer mode followed by the second-stage reduction the tree already has.
+            want = os.environ.get('SKT_DENSE_I8', '0')
+            if want not in ('', '0') and N == 3 and hasattr(be, 'planes_create') and \
+                    be.planes_supported(self.lshape, 0, R) and be.planes_supported(self.lshape, N - 1, R):
+                self.i8 = be.planes_create(self.Xd, self.lshape, 5 if want == '5' else 6)
+                keep = self.lshape[1:] if s == N - 1 else self.lshape[:N - 1]
+                self.T2 = be.empty((int(np.prod(keep)), R))
             # single process: the second stage leaves its per-split slabs for the cluster update to add while it stages
             # M (same arithmetic, one launch less on the critical path)
             if not comm.active and hasattr(be, 'kr_reduce_slabs') and os.environ.get('SKT_NO_KR_SLABS', '0') != '1':
@@ -513,6 +526,19 @@ class CpAlsEngine(object):
         """One pass over X: the partial contraction that serves every mode of ``group`` (0: modes
         ``[0, s)``, 1: modes ``[s, N)``), by the dense MTTKRP kernel on a reshaped view of X."""
         be, s, N = self.be, self.ts, self.N
+        if self.i8 is not None:
+            R, Ud, ls = self.R, self.Ud, self.lshape
+            if group == 0 and s == N - 1:
+                be.planes_ttm(self.i8, N - 1, Ud[N - 1], R, self.TA)
+            elif group == 0:                                    # s == 1: T_A = M_0
+                be.planes_ttm(self.i8, N - 1, Ud[N - 1], R, self.T2)
+                be.kr_reduce(self.T2, ls[:N - 1], Ud[:N - 1], R, 0, self.TA)
+            elif s == 1:
+                be.planes_ttm(self.i8, 0, Ud[0], R, self.TB)
+            else:                                               # s == N - 1: T_B = M_{N-1}
+                be.planes_ttm(self.i8, 0, Ud[0], R, self.T2)
+                be.kr_reduce(self.T2, ls[1:], Ud[1:], R, N - 2, self.TB)
+            return
         if group == 0:
             be.mttkrp_dense(self.Xd, self.shapeA, [None] + list(self.Ud[s:]), self.R, 0, self.TA)
         else:
@@ -686,6 +712,9 @@ class CpAlsEngine(object):
         if hasattr(self.be, 'release_side'):
             self.be.release_side()          # a speculative pinv of the next sweep may still be running
         self._pinv_pending = [None] * self.N
+        if getattr(self, 'i8', None) is not None:
+            self.i8.close()
+            self.i8 = None
 
     def download(self, U):
         """Write the factors into the caller's list (in place) and return lambda."""

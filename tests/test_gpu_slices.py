@@ -1,0 +1,196 @@
+"""Opt-in sliced contraction on the INT8 tensor cores (csrc/slice_gemm.cu, `skt_planes_*`): the two partial contractions
+of the 3-way dimension tree, FP64-accurate by error-free slicing.  The kernel is checked against NumPy's FP64 product of
+the same unfolding (the reference's khatrirao + dot on a 2-way view, sktensor/dtensor.py:117-137) with the MTTKRP parity
+measure and tolerance of SURVEY 8(d): max|a - b| / max|b| < 1e-10."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def K():
+    from sktensor import _device as dev, _kernels as K
+    dev.require_cuda()
+    return K
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from sktensor import _device as dev
+    return dev
+
+
+def _draw(rng, shape, dist):
+    if dist == 'uniform':
+        return rng.rand(*shape)
+    if dist == 'normal':
+        return rng.randn(*shape)
+    if dist == 'wide':                                  # six decades of dynamic range, both signs
+        return rng.randn(*shape) * 10.0 ** rng.uniform(-3, 3, size=shape)
+    raise ValueError(dist)
+
+
+def _ref(X, mode, U):
+    if mode == 0:
+        return X.reshape(X.shape[0], -1).T.dot(U)
+    return X.reshape(-1, X.shape[-1]).dot(U)
+
+
+SHAPES = [((16, 16, 16), 4), ((48, 20, 64), 7), ((130, 36, 208), 32), ((512, 8, 512), 32), ((96, 100, 48), 1),
+          ((33, 16, 400), 20), ((400, 16), 32), ((8, 6, 10, 32), 5)]
+
+
+@pytest.mark.parametrize('shape,R', SHAPES)
+@pytest.mark.parametrize('dist', ['uniform', 'normal'])
+@pytest.mark.parametrize('S', [6, 5])
+def test_planes_ttm_matches_numpy(K, dev, shape, R, dist, S):
+    rng = np.random.RandomState(sum(shape) + R + S)
+    X = _draw(rng, shape, dist)
+    Xd = dev.to_device(X)
+    P = K.PlanesHandle(Xd, shape, S)
+    try:
+        assert P.device_bytes() >= S * X.size
+        for mode in (0, len(shape) - 1):
+            U = _draw(rng, (shape[mode], R), dist)
+            if not K.PlanesHandle.supported(shape, mode, R):
+                with pytest.raises(Exception):
+                    P.ttm(mode, dev.to_device(U), R)
+                continue
+            T = dev.to_host(P.ttm(mode, dev.to_device(U), R))
+            ref = _ref(X, mode, U)
+            assert T.shape == ref.shape
+            # bound of the header: 2^-(8S-1) (max|X| sum|U| + max|U| sum|X|) per entry, far below the parity tolerance
+            bound = 2.0 ** -(8 * S - 1) * (np.abs(X).max() * np.abs(U).sum(axis=0).max() +
+                                            np.abs(U).max() * np.abs(X).sum(axis=mode).max())
+            assert np.abs(T - ref).max() <= 4 * bound + 1e-15 * np.abs(ref).max()
+            assert relerr(T, ref) < (1e-12 if S == 6 else 1e-10)
+    finally:
+        P.close()
+
+
+def test_planes_wide_dynamic_range_stays_within_the_bound(K, dev):
+    rng = np.random.RandomState(5)
+    shape = (64, 48, 128)
+    X = _draw(rng, shape, 'wide')
+    P = K.PlanesHandle(dev.to_device(X), shape, 6)
+    try:
+        for mode in (0, 2):
+            U = _draw(rng, (shape[mode], 16), 'wide')
+            T = dev.to_host(P.ttm(mode, dev.to_device(U), 16))
+            ref = _ref(X, mode, U)
+            bound = 2.0 ** -47 * (np.abs(X).max() * np.abs(U).sum(axis=0) + np.abs(U).max(axis=0) * np.abs(X).sum(axis=mode).max())
+            assert (np.abs(T - ref) <= 4 * bound[None, :] + 1e-15 * np.abs(ref).max()).all()
+    finally:
+        P.close()
+
+
+def test_planes_exact_on_integers_and_zero(K, dev):
+    rng = np.random.RandomState(11)
+    shape = (32, 16, 64)
+    X = rng.randint(-1000, 1000, size=shape).astype(float)
+    X[3] = 0.0
+    P = K.PlanesHandle(dev.to_device(X), shape, 6)
+    Z = K.PlanesHandle(dev.to_device(np.zeros(shape)), shape, 6)
+    try:
+        for mode in (0, 2):
+            U = rng.randint(-50, 50, size=(shape[mode], 8)).astype(float)
+            U[:, 2] = 0.0                                # a zero column keeps scale 1 and gives exact zeros
+            T = dev.to_host(P.ttm(mode, dev.to_device(U), 8))
+            assert np.array_equal(T, _ref(X, mode, U))   # small integers: every digit product is exact
+            assert not dev.to_host(Z.ttm(mode, dev.to_device(U), 8)).any()
+    finally:
+        P.close()
+        Z.close()
+
+
+def test_planes_non_finite_input_poisons_the_output(K, dev):
+    shape = (16, 16, 32)
+    X = np.random.RandomState(2).rand(*shape)
+    U = np.random.RandomState(3).rand(32, 4)
+    Xbad = X.copy()
+    Xbad[1, 2, 3] = np.inf
+    P = K.PlanesHandle(dev.to_device(Xbad), shape, 6)
+    try:
+        assert np.isnan(dev.to_host(P.ttm(2, dev.to_device(U), 4))).all()
+    finally:
+        P.close()
+    P = K.PlanesHandle(dev.to_device(X), shape, 6)
+    try:
+        Ubad = U.copy()
+        Ubad[5, 1] = np.nan
+        T = dev.to_host(P.ttm(2, dev.to_device(Ubad), 4))
+        assert np.isnan(T[:, 1]).all() and np.isfinite(T[:, [0, 2, 3]]).all()
+    finally:
+        P.close()
+
+
+def test_planes_rejects_what_it_does_not_support(K, dev):
+    shape = (24, 16, 32)
+    Xd = dev.to_device(np.ones(shape))
+    with pytest.raises(Exception):
+        K.PlanesHandle(Xd, shape, 4)
+    P = K.PlanesHandle(Xd, shape, 6)
+    try:
+        assert not K.PlanesHandle.supported(shape, 1, 8)          # a middle mode
+        assert not K.PlanesHandle.supported(shape, 2, 33)         # rank beyond one slice block
+        assert not K.PlanesHandle.supported((24, 16, 600), 2, 8)  # contraction longer than the resident factor planes
+        assert not K.PlanesHandle.supported((24, 16, 30), 2, 8)   # rows of the planes not 16-byte aligned
+        with pytest.raises(Exception):
+            P.ttm(1, dev.to_device(np.ones((16, 8))), 8)
+    finally:
+        P.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cp_als with the sliced passes switched on (SKT_DENSE_I8): same iterates as the FP64 engine and as the oracle
+@pytest.fixture
+def sliced(monkeypatch):
+    monkeypatch.setenv('SKT_DENSE_I8', '6')
+
+
+def _cp(X, R, U0, **kw):
+    from sktensor import cp_als, dtensor
+    return cp_als(dtensor(X), R, init=[u.copy() for u in U0], **kw)
+
+
+@pytest.mark.parametrize('shape,R', [((64, 48, 32), 8), ((32, 80, 64), 32), ((208, 16, 16), 5), ((16, 16, 304), 12)])
+def test_cp_als_sliced_matches_fp64_engine_and_oracle(monkeypatch, shape, R):
+    from oracle import sktensor_oracle as orc
+    rng = np.random.RandomState(sum(shape))
+    X = rng.rand(*shape)
+    U0 = [rng.rand(d, R) for d in shape]
+    P0, fit0, itr0, _ = _cp(X, R, U0, max_iter=12, conv=0)
+    monkeypatch.setenv('SKT_DENSE_I8', '6')
+    P1, fit1, itr1, _ = _cp(X, R, U0, max_iter=12, conv=0)
+    assert itr1 == itr0
+    assert abs(fit1 - fit0) < 1e-9
+    for a, b in zip(P1.U, P0.U):
+        assert relerr(a, b) < 1e-8
+    assert relerr(P1.lmbda, P0.lmbda) < 1e-8
+    Uo, lamo, fito, itro = orc.cp_als(X, R, init=[u.copy() for u in U0], max_iter=12, conv=0)[:4]
+    assert abs(fit1 - fito) < 1e-6
+
+
+def test_cp_als_sliced_engine_really_takes_the_sliced_passes(sliced):
+    from sktensor import _kernels as K, _parallel as par, dtensor
+    rng = np.random.RandomState(1)
+    X = rng.rand(32, 32, 32)
+    U = [rng.rand(32, 4) for _ in range(3)]
+    eng = par.CpAlsEngine(dtensor(X), 4, U)
+    try:
+        assert eng.i8 is not None and eng.i8.nslices == 6
+        eng.mttkrp(0)
+    finally:
+        eng.release()
+    assert eng.i8 is None
+
+
+def test_cp_als_sliced_falls_back_to_fp64_when_the_shape_is_not_supported(sliced):
+    rng = np.random.RandomState(2)
+    X = rng.rand(20, 18, 30)                               # plane rows not 16-byte aligned
+    U0 = [rng.rand(d, 3) for d in X.shape]
+    P, fit, itr, _ = _cp(X, 3, U0, max_iter=5, conv=0)
+    assert np.isfinite(fit)
