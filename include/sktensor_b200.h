@@ -263,6 +263,16 @@ SKT_API int    skt_planes_nslices(const skt_planes *p);
 SKT_API size_t skt_planes_ttm_workspace(const skt_planes *p, int mode, int rank);
 SKT_API int    skt_planes_ttm(const skt_planes *p, int mode, const double *U_d, int rank, double *T_d, void *ws_d,
                       size_t ws_bytes, skt_stream stream);
+/* General tree pass on the same planes: X seen as the matrix [P x Q], P = prod(shape[:split]), Q = prod(shape[split:]).
+ * group 0: T_d[P x rank] = X KR(U_split .. U_{ndim-1});  group 1: T_d[Q x rank] = X^T KR(U_0 .. U_{split-1}), KR = the
+ * Khatri-Rao product of the group's factors in X's memory order (the khatrirao + dot of dtensor.uttkrp, dtensor.py:117-137
+ * with core.py:333-378, restricted to one group of modes; its rows are formed on the fly, never stored in FP64).  U_d holds
+ * ndim factor pointers (only the group's are read).  rank <= 64, Q a multiple of 16; contractions of any length (the
+ * factor planes stream through shared memory, INT32 accumulators are flushed every 16384 products).                 */
+SKT_API int    skt_planes_pass_supported(const int64_t *shape, int ndim, int split, int rank);
+SKT_API size_t skt_planes_pass_workspace(const skt_planes *p, int split, int group, int rank);
+SKT_API int    skt_planes_pass(const skt_planes *p, int split, int group, const double *const *U_d, int rank, double *T_d,
+                       void *ws_d, size_t ws_bytes, skt_stream stream);
 
 /* ---------------------------------------------------------------- COO de-duplication (accumfun)
  * sptensor(subs, vals, accumfun=...) merges duplicate coordinates (sktensor/sptensor.py:80-84 -> utils.accum,

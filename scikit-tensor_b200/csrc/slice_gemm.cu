@@ -367,6 +367,283 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
 }
 
+
+// ---- general tree pass: long contractions, rank up to 64 --------------------------------------------------------------
+// X seen as the matrix [P x Q] (P = product of the modes before the split, Q = of the others):
+//   group 0:  T[P x R] = X   KR(U_s .. U_{N-1})      (A operand K-major:  rows p, contraction q)
+//   group 1:  T[Q x R] = X^T KR(U_0 .. U_{s-1})      (A operand MN-major: rows q, contraction p)
+// KR = the Khatri-Rao product of the group's factors in X's memory order; its rows are formed on the fly by the slicing
+// kernel (never stored in FP64).  The factor planes no longer fit shared memory: one k-chunk of them (S tiles of NB x 128
+// bytes) travels through a two-slot ring beside the A ring.  A unit of work is (row tile, K segment); a segment is at most
+// 128 chunks (16384 products per INT32 accumulator) and segments of one tile are summed in order from FP64 slabs.
+struct KrDesc {
+    int nfac, R;
+    int dims[SKT_MAX_NDIM];
+    const double *U[SKT_MAX_NDIM];
+};
+
+__device__ __forceinline__ double kr_value(const KrDesc &d, long long k, int n) {
+    double v = 1.0;
+    for (int m = d.nfac - 1; m >= 0; --m) {
+        const int idx = (int)(k % d.dims[m]);
+        k /= d.dims[m];
+        v *= d.U[m][(size_t)idx * d.R + n];
+    }
+    return v;
+}
+
+// column abs-max of KR (bits of a non-negative double order like unsigned integers); 256 threads = 4 rows x 64 columns
+__global__ void __launch_bounds__(256) kr_absmax_kernel(const KrDesc d, long long K, unsigned long long *colmax) {
+    const int n = threadIdx.x & 63, sub = threadIdx.x >> 6;
+    double m = 0.0;
+    bool bad = false;
+    if (n < d.R)
+        for (long long k = (long long)blockIdx.x * 4 + sub; k < K; k += (long long)gridDim.x * 4) {
+            const double a = fabs(kr_value(d, k, n));
+            bad |= !(a <= DBL_MAX);
+            m = fmax(m, a);
+        }
+    if (bad) m = __longlong_as_double(0x7ff0000000000000ll);
+    if (n < d.R && m > 0.0) atomicMax(&colmax[n], (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void kr_scale_kernel(const unsigned long long *colmax, int S, int smin, const double *__restrict__ xscale, double *sc,
+                                double *inv) {
+    const int n = threadIdx.x;
+    const double amax = __longlong_as_double((long long)colmax[n]);
+    const bool finite = amax <= DBL_MAX;
+    const double s = finite ? pow2_scale(amax, S) : 0.0;
+    sc[n] = s;
+    inv[n] = finite ? ldexp(1.0, 8 * smin) * xscale[1] / s : nan("");
+}
+
+// planes Bp[s][n][kpad] of KR^T; thread = (column n, four consecutive k)
+__global__ void __launch_bounds__(256) kr_slice_kernel(const KrDesc d, long long K, long long kpad4, int nb, int S,
+                                                       const double *__restrict__ sc, uint32_t *__restrict__ Bp) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= kpad4 * nb) return;
+    const int n = (int)(q / kpad4);
+    const long long k4 = q % kpad4;
+    const double scale = sc[n];
+    double x[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const long long k = 4 * k4 + e;
+        x[e] = (n < d.R && k < K) ? kr_value(d, k, n) : 0.0;
+    }
+    uint32_t w[MAXS];
+    slice4(x, scale, S, w);
+    const bool pad = n >= d.R || scale == 0.0;
+#pragma unroll
+    for (int s = 0; s < MAXS; ++s)
+        if (s < S) Bp[((size_t)s * nb + n) * kpad4 + k4] = pad ? 0u : w[s];
+}
+
+struct StreamParams {
+    long long rows;
+    int tiles, nchunk, nseg, cps;      // row tiles, k-chunks, K segments, chunks per segment
+    int Kc;
+    int S, R, NS, smin;
+    double *T;                         // rows x R (nseg == 1) ...
+    double *slabs;                     // ... or nseg slabs of rows x R
+    const double *inv;
+};
+
+template <int NBW>
+__device__ __forceinline__ void issue_blocks(uint32_t d, uint64_t da, uint32_t b_addr, int ks, int nblk, bool a_mn, uint32_t acc_first,
+                                             uint32_t acc_rest) {
+    // nblk stacked B slices of NBW columns each, at most 256 columns per instruction; the first block may carry its own
+    // accumulate flag (it opens a new accumulator)
+    constexpr int GMAX = 256 / NBW;
+    constexpr uint32_t BT = NBW * KC;
+    int b = 0;
+    if (acc_first != acc_rest) {
+        umma_i8(d, da, smem_desc_sw128(b_addr + ks * 32), instr_desc(NBW, a_mn), acc_first);
+        b = 1;
+    }
+    while (b < nblk) {
+        const int g = min(GMAX, nblk - b);
+        umma_i8(d + (uint32_t)(b * NBW), da, smem_desc_sw128(b_addr + b * BT + ks * 32), instr_desc(NBW * g, a_mn), b == 0 ? acc_first : acc_rest);
+        b += g;
+    }
+}
+
+template <bool A_MN, int NBW>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+slice_gemm_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StreamParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr uint32_t BT = NBW * KC;                              // one B slice tile
+    constexpr int NSETS = NBW == 32 ? 2 : 1;                       // accumulator sets in the 512 columns of tensor memory
+    constexpr int ACC_COLS = MAXACC * NBW;
+    const int S = p.S, NS = p.NS, smin = p.smin;
+    unsigned char *sB = smem;                                      // 2 slots of S tiles
+    unsigned char *sA = smem + 2 * (size_t)S * BT;
+    uint64_t *bars = (uint64_t *)(sA + (size_t)NS * STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + NS, *bfull = bars + 2 * NS, *bempty = bars + 2 * NS + 2, *tfull = bars + 2 * NS + 4,
+             *tempty = bars + 2 * NS + 6;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NS + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bfull[b], 1);
+            mbar_init(&bempty[b], 1);
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int nunits = p.tiles * p.nseg;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int st = 0, bs = 0;
+            uint32_t ph = 0, bph = 0;
+            bool wrapped = false, bwrapped = false;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const int tile = u / p.nseg, g = u % p.nseg;
+                const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
+                for (int c = c0; c < c1; ++c) {
+                    if (bwrapped) mbar_wait(&bempty[bs], bph ^ 1u);
+                    mbar_arrive_expect_tx(&bfull[bs], (uint32_t)(S * BT));
+                    for (int j = 0; j < S; ++j) tma_load_3d(sB + ((size_t)bs * S + j) * BT, &tmB, &bfull[bs], c * KC, 0, j);
+                    if (++bs == 2) {
+                        bs = 0;
+                        bph ^= 1u;
+                        bwrapped = true;
+                    }
+                    for (int i = S - 1; i >= 0; --i) {
+                        if (wrapped) mbar_wait(&empty[st], ph ^ 1u);
+                        mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
+                        if (A_MN)
+                            tma_load_3d(sA + (size_t)st * STAGE_BYTES, &tmA, &full[st], tile * TM, c * KC, i);
+                        else
+                            tma_load_3d(sA + (size_t)st * STAGE_BYTES, &tmA, &full[st], c * KC, tile * TM, i);
+                        if (++st == NS) {
+                            st = 0;
+                            ph ^= 1u;
+                            wrapped = true;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int st = 0, bs = 0;
+            uint32_t ph = 0, bph = 0, lu = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++lu) {
+                const int g = u % p.nseg;
+                const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
+                const uint32_t set = lu % NSETS, use = lu / NSETS;
+                if (use >= 1) mbar_wait(&tempty[set], (use - 1) & 1u);
+                tc_fence_after();
+                const uint32_t tacc = tmem + set * (uint32_t)ACC_COLS;
+                for (int c = c0; c < c1; ++c) {
+                    mbar_wait(&bfull[bs], bph);
+                    const int valid = min(KC, p.Kc - c * KC);
+                    const int nks = (valid + 31) / 32;                 // the zero-filled tail of the last chunk is skipped
+                    for (int i = S - 1; i >= 0; --i) {
+                        mbar_wait(&full[st], ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(sA + (size_t)st * STAGE_BYTES);
+                        const int j0 = smin - i > 0 ? smin - i : 0;
+                        const uint32_t b_addr = smem_u32(sB + ((size_t)bs * S + j0) * BT);
+                        const uint32_t d = tacc + (uint32_t)((i + j0 - smin) * NBW);
+                        constexpr uint32_t A_STEP = A_MN ? 32 * 128 : 32;
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint64_t da = smem_desc_sw128(a_addr + ks * A_STEP);
+                            const bool head = (c == c0 && ks == 0);
+                            const uint32_t acc_first = (head && (i == S - 1 || i >= smin)) ? 0u : 1u;
+                            const uint32_t acc_rest = (head && i == S - 1) ? 0u : 1u;
+                            issue_blocks<NBW>(d, da, b_addr, ks, S - j0, A_MN, acc_first, acc_rest);
+                        }
+                        umma_commit(&empty[st]);
+                        if (++st == NS) {
+                            st = 0;
+                            ph ^= 1u;
+                        }
+                    }
+                    umma_commit(&bempty[bs]);
+                    if (++bs == 2) {
+                        bs = 0;
+                        bph ^= 1u;
+                    }
+                }
+                umma_commit(&tfull[set]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int nacc = 2 * (S - 1) - smin + 1;
+        uint32_t lu = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++lu) {
+            const int tile = u / p.nseg, g = u % p.nseg;
+            const uint32_t set = lu % NSETS, use = lu / NSETS;
+            mbar_wait(&tfull[set], use & 1u);
+            tc_fence_after();
+            const long long row = (long long)tile * TM + q * 32 + lane;
+            double *out = (p.nseg == 1 ? p.T : p.slabs + (size_t)g * p.rows * p.R) + row * p.R;
+#pragma unroll 1
+            for (int h = 0; h < NBW / 32; ++h) {
+                double r[32];
+#pragma unroll
+                for (int n = 0; n < 32; ++n) r[n] = 0.0;
+                for (int a = nacc - 1; a >= 0; --a) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + set * (uint32_t)ACC_COLS + (uint32_t)(a * NBW + h * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                        "tcgen05.wait::ld.sync.aligned;\n"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr)
+                        : "memory");
+#pragma unroll
+                    for (int n = 0; n < 32; ++n) r[n] = fma(r[n], 256.0, (double)(int)v[n]);
+                }
+                if (row < p.rows) {
+#pragma unroll
+                    for (int n = 0; n < 32; ++n)
+                        if (h * 32 + n < p.R) out[h * 32 + n] = r[n] * p.inv[h * 32 + n];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[set]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
+// T[e] = sum_g slab[g][e], g ascending (fixed order)
+__global__ void slab_sum_kernel(const double *__restrict__ slabs, int nseg, long long n, double *__restrict__ T) {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        double s = slabs[e];
+        for (int g = 1; g < nseg; ++g) s += slabs[(size_t)g * n + e];
+        T[e] = s;
+    }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -425,6 +702,90 @@ int plan_ttm(const skt_planes *P, int mode, int R, TtmPlan &pl) {
 }
 
 size_t ttm_ws(const TtmPlan &pl, int S) { return align_up((size_t)S * NB * pl.kpad, 256) + align_up(NB * sizeof(double), 256); }
+
+
+struct PassPlan {
+    bool a_mn;
+    long long P, Q, rows, Kc;
+    int nfac, fac0;            // the group's factors: modes fac0 .. fac0 + nfac - 1
+    int nb;                    // 32 or 64 columns per slice
+    int nchunk, nseg, cps;
+    long long kpad;
+    int tiles;
+};
+
+int plan_pass(const skt_planes *P, int split, int group, int R, PassPlan &pl) {
+    SKT_REQUIRE(P != nullptr, SKT_EINVAL, "null planes handle");
+    SKT_REQUIRE(split >= 1 && split < P->ndim && (group == 0 || group == 1), SKT_EINVAL, "bad split %d / group %d", split, group);
+    SKT_REQUIRE(R >= 1 && R <= 64, SKT_EUNSUPPORTED, "the sliced tree pass supports rank 1..64 (got %d)", R);
+    pl.P = 1;
+    pl.Q = 1;
+    for (int m = 0; m < P->ndim; ++m) (m < split ? pl.P : pl.Q) *= P->shape[m];
+    SKT_REQUIRE(pl.Q % 16 == 0, SKT_EUNSUPPORTED, "the sliced tree pass needs 16-byte aligned rows of the byte planes");
+    pl.a_mn = (group == 1);
+    pl.rows = pl.a_mn ? pl.Q : pl.P;
+    pl.Kc = pl.a_mn ? pl.P : pl.Q;
+    pl.fac0 = pl.a_mn ? 0 : split;
+    pl.nfac = pl.a_mn ? split : P->ndim - split;
+    pl.nb = R <= 32 ? 32 : 64;
+    SKT_REQUIRE(pl.rows < (1ll << 31) && pl.Kc < (1ll << 31), SKT_EUNSUPPORTED, "view too large");
+    pl.nchunk = (int)((pl.Kc + KC - 1) / KC);
+    pl.kpad = (long long)pl.nchunk * KC;
+    pl.tiles = (int)((pl.rows + TM - 1) / TM);
+    // K segments: at most 128 chunks each (INT32 range), as many as balance the persistent grid best
+    const int sms = sm_count();
+    const int min_seg = (pl.nchunk + 127) / 128;
+    long long best = -1;
+    pl.nseg = min_seg;
+    for (int ns = min_seg; ns <= std::max(min_seg, std::min(pl.nchunk, 64)); ++ns) {
+        const int cps = (pl.nchunk + ns - 1) / ns;
+        const long long waves = ((long long)pl.tiles * ns + sms - 1) / sms;
+        const long long cost = waves * (cps + 1);                    // one chunk-time per unit for the epilogue / fill
+        if (best < 0 || cost < best) {
+            best = cost;
+            pl.nseg = ns;
+        }
+    }
+    pl.cps = (pl.nchunk + pl.nseg - 1) / pl.nseg;
+    pl.nseg = (pl.nchunk + pl.cps - 1) / pl.cps;
+    return SKT_OK;
+}
+
+struct PassWs {
+    size_t bp, colmax, sc, inv, slabs, total;
+};
+PassWs pass_ws(const PassPlan &pl, int S, int R) {
+    PassWs w;
+    size_t off = 0;
+    w.bp = off;
+    off += align_up((size_t)S * pl.nb * pl.kpad, 256);
+    w.colmax = off;
+    off += align_up(64 * sizeof(unsigned long long), 256);
+    w.sc = off;
+    off += align_up(64 * sizeof(double), 256);
+    w.inv = off;
+    off += align_up(64 * sizeof(double), 256);
+    w.slabs = off;
+    if (pl.nseg > 1) off += align_up((size_t)pl.nseg * pl.rows * R * sizeof(double), 256);
+    w.total = off;
+    return w;
+}
+
+template <bool A_MN, int NBW>
+int launch_stream(const CUtensorMap &tmA, const CUtensorMap &tmB, StreamParams &sp, cudaStream_t st) {
+    const size_t fixed = 1024 + 2 * (size_t)sp.S * NBW * KC + 512;         // alignment slack, two B slots, barriers
+    const size_t cap = smem_optin_bytes();
+    SKT_REQUIRE(cap >= fixed + 3 * STAGE_BYTES, SKT_EUNSUPPORTED, "not enough shared memory for the sliced tree pass");
+    sp.NS = (int)std::min<size_t>(12, (cap - fixed) / STAGE_BYTES);
+    const size_t smem = fixed + (size_t)sp.NS * STAGE_BYTES;
+    static unsigned long long mask = 0;
+    if (first_use_on_device(mask))
+        SKT_CUDA(cudaFuncSetAttribute(slice_gemm_stream_kernel<A_MN, NBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    const int grid = std::min(sp.tiles * sp.nseg, sm_count());
+    slice_gemm_stream_kernel<A_MN, NBW><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, sp);
+    SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
 
 }  // namespace
 }  // namespace skt
@@ -566,6 +927,91 @@ int skt_planes_ttm(const skt_planes *P, int mode, const double *U_d, int rank, d
         slice_gemm_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, gp);
     }
     SKT_LAUNCH_CHECK();
+    return SKT_OK;
+}
+
+
+int skt_planes_pass_supported(const int64_t *shape, int ndim, int split, int rank) {
+    if (!shape || ndim < 2 || ndim > SKT_MAX_NDIM || split < 1 || split >= ndim || rank < 1 || rank > 64) return 0;
+    long long P = 1, Q = 1;
+    for (int m = 0; m < ndim; ++m) {
+        if (shape[m] < 1) return 0;
+        (m < split ? P : Q) *= shape[m];
+    }
+    return (Q % 16 == 0 && P < (1ll << 31) && Q < (1ll << 31)) ? 1 : 0;
+}
+
+size_t skt_planes_pass_workspace(const skt_planes *P, int split, int group, int rank) {
+    PassPlan pl;
+    if (plan_pass(P, split, group, rank, pl) != SKT_OK) return 0;
+    return pass_ws(pl, P->S, rank).total;
+}
+
+int skt_planes_pass(const skt_planes *P, int split, int group, const double *const *U_d, int rank, double *T_d, void *ws_d,
+                    size_t ws_bytes, skt_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PassPlan pl;
+    const int rc = plan_pass(P, split, group, rank, pl);
+    if (rc) return rc;
+    SKT_REQUIRE(U_d && T_d, SKT_EINVAL, "null argument");
+    const int S = P->S;
+    int smin = S == 6 ? 4 : 2;
+    if (const char *e = getenv("SKT_I8_SMIN")) smin = std::max(2 * (S - 1) + 1 - MAXACC, std::min(S - 1, atoi(e)));
+    const PassWs w = pass_ws(pl, S, rank);
+    SKT_REQUIRE(ws_d && ws_bytes >= w.total, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total, ws_bytes);
+    SKT_REQUIRE((((uintptr_t)ws_d) & 255) == 0, SKT_EINVAL, "misaligned workspace");
+    char *base = (char *)ws_d;
+    uint32_t *Bp = (uint32_t *)(base + w.bp);
+    unsigned long long *colmax = (unsigned long long *)(base + w.colmax);
+    double *sc = (double *)(base + w.sc), *inv = (double *)(base + w.inv), *slabs = (double *)(base + w.slabs);
+
+    KrDesc kd;
+    kd.nfac = pl.nfac;
+    kd.R = rank;
+    for (int f = 0; f < pl.nfac; ++f) {
+        kd.dims[f] = (int)P->shape[pl.fac0 + f];
+        kd.U[f] = U_d[pl.fac0 + f];
+        SKT_REQUIRE(kd.U[f] != nullptr, SKT_EINVAL, "factor %d of the group is null", pl.fac0 + f);
+    }
+    SKT_CUDA(cudaMemsetAsync(colmax, 0, 64 * sizeof(unsigned long long), st));
+    const int kblocks = (int)std::min<long long>((pl.Kc + 3) / 4, 4LL * sm_count());
+    kr_absmax_kernel<<<kblocks, 256, 0, st>>>(kd, pl.Kc, colmax);
+    SKT_LAUNCH_CHECK();
+    kr_scale_kernel<<<1, 64, 0, st>>>(colmax, S, smin, P->scale, sc, inv);
+    SKT_LAUNCH_CHECK();
+    const long long kpad4 = pl.kpad / 4, nthreads = kpad4 * pl.nb;
+    kr_slice_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(kd, pl.Kc, kpad4, pl.nb, S, sc, Bp);
+    SKT_LAUNCH_CHECK();
+
+    CUtensorMap tmA, tmB;
+    int e = byte_map3(P->planes, (uint64_t)pl.Q, (uint64_t)pl.P, (uint64_t)S, (uint64_t)pl.Q, (uint64_t)P->total, 128, tmA);
+    if (e) return e;
+    e = byte_map3(Bp, (uint64_t)pl.kpad, (uint64_t)pl.nb, (uint64_t)S, (uint64_t)pl.kpad, (uint64_t)pl.nb * pl.kpad, (uint32_t)pl.nb, tmB);
+    if (e) return e;
+
+    StreamParams sp;
+    sp.rows = pl.rows;
+    sp.tiles = pl.tiles;
+    sp.nchunk = pl.nchunk;
+    sp.nseg = pl.nseg;
+    sp.cps = pl.cps;
+    sp.Kc = (int)pl.Kc;
+    sp.S = S;
+    sp.R = rank;
+    sp.smin = smin;
+    sp.T = T_d;
+    sp.slabs = slabs;
+    sp.inv = inv;
+    if (pl.a_mn)
+        e = pl.nb == 32 ? launch_stream<true, 32>(tmA, tmB, sp, st) : launch_stream<true, 64>(tmA, tmB, sp, st);
+    else
+        e = pl.nb == 32 ? launch_stream<false, 32>(tmA, tmB, sp, st) : launch_stream<false, 64>(tmA, tmB, sp, st);
+    if (e) return e;
+    if (pl.nseg > 1) {
+        const long long n = pl.rows * rank;
+        slab_sum_kernel<<<(int)std::min<long long>((n + 255) / 256, 8LL * sm_count()), 256, 0, st>>>(slabs, pl.nseg, n, T_d);
+        SKT_LAUNCH_CHECK();
+    }
     return SKT_OK;
 }
 

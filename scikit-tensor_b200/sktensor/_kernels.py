@@ -178,6 +178,27 @@ class PlanesHandle(object):
         _lib.check(lib.skt_planes_ttm(self.h, mode, dev.ptr(U), rank, dev.ptr(out), ws, wsz, dev.stream_ptr()))
         return out
 
+    @staticmethod
+    def pass_supported(shape, split, rank):
+        shape = tuple(int(s) for s in shape)
+        return bool(_lib.load().skt_planes_pass_supported(_lib.shape_array(shape), len(shape), int(split), int(rank)))
+
+    def tree_pass(self, split, group, U, rank, out=None):
+        """X as the matrix ``[prod(shape[:split]) x prod(shape[split:])]``: group 0 -> ``X KR(U[split:])``, group 1 ->
+        ``X^T KR(U[:split])`` (Khatri-Rao product of the group's factors in memory order); rank <= 64, any length."""
+        lib = _lib.load()
+        P = 1
+        for d in self.shape[:split]:
+            P *= d
+        Q = 1
+        for d in self.shape[split:]:
+            Q *= d
+        if out is None:
+            out = dev.empty((Q if group else P, rank))
+        ws, wsz = dev.workspace('mttkrp').get(lib.skt_planes_pass_workspace(self.h, split, group, rank))
+        _lib.check(lib.skt_planes_pass(self.h, split, group, _factor_ptrs(U), rank, dev.ptr(out), ws, wsz, dev.stream_ptr()))
+        return out
+
     def close(self):
         if getattr(self, 'h', None):
             _lib.load().skt_planes_destroy(self.h)

@@ -147,6 +147,8 @@ class CudaBackend(object):
     def planes_supported(self, shape, mode, R): return self.K.PlanesHandle.supported(shape, mode, R)
     def planes_create(self, Xd, shape, nslices): return self.K.PlanesHandle(Xd, shape, nslices)
     def planes_ttm(self, planes, mode, U, R, out): return planes.ttm(mode, U, R, out=out)
+    def planes_pass_supported(self, shape, split, R): return self.K.PlanesHandle.pass_supported(shape, split, R)
+    def planes_pass(self, planes, split, group, U, R, out): return planes.tree_pass(split, group, U, R, out=out)
     def kr_reduce_slab_buffer(self, dims, R, n): return self.empty((max(1, self.K.kr_reduce_workspace(dims, R, n) // 8),))
     def kr_reduce_slabs(self, T, dims, W, R, n, slabs): return self.K.kr_reduce_slabs(T, dims, W, R, n, slabs)
     def update_cluster_slabs(self, slabs, nslabs, P, G, n, first, U, lam, ip, normX2, fit):
@@ -473,6 +475,7 @@ class CpAlsEngine(object):
         # U_0..U_{s-1}.  A one-mode group needs no second stage: its partial tensor IS the MTTKRP.
         self.slabbuf = [None] * N        # per mode: buffer for un-summed second-stage slabs (see below)
         self.i8 = None                   # byte planes of X for the opt-in sliced passes
+        self.i8_general = False
         self.nslabs = [0] * N
         self.tree = (not self.sparse) and N >= 3 and hasattr(be, 'kr_reduce') and \
             os.environ.get('SKT_NO_DIMTREE', '0') != '1'
@@ -487,12 +490,18 @@ class CpAlsEngine(object):
             # opt-in (SKT_DENSE_I8=6 | 5 | 1): both passes of a 3-way tree as sliced contractions on the INT8 tensor cores
             # (csrc/slice_gemm.cu).  X is cut into byte planes once; a pass whose group holds two modes becomes the GEMM
             # over the outer mode followed by the second-stage reduction the tree already has.
+            # Other shapes (4-way and up, rank 33..64, long modes): X as the matrix [prod(shape[:s]) x prod(shape[s:])], each
+            # pass one long GEMM against the Khatri-Rao product of the group's factors (skt_planes_pass).
             want = os.environ.get('SKT_DENSE_I8', '0')
-            if want not in ('', '0') and N == 3 and hasattr(be, 'planes_create') and \
-                    be.planes_supported(self.lshape, 0, R) and be.planes_supported(self.lshape, N - 1, R):
-                self.i8 = be.planes_create(self.Xd, self.lshape, 5 if want == '5' else 6)
-                keep = self.lshape[1:] if s == N - 1 else self.lshape[:N - 1]
-                self.T2 = be.empty((int(np.prod(keep)), R))
+            self.i8_general = False
+            if want not in ('', '0') and hasattr(be, 'planes_create'):
+                if N == 3 and be.planes_supported(self.lshape, 0, R) and be.planes_supported(self.lshape, N - 1, R):
+                    self.i8 = be.planes_create(self.Xd, self.lshape, 5 if want == '5' else 6)
+                    keep = self.lshape[1:] if s == N - 1 else self.lshape[:N - 1]
+                    self.T2 = be.empty((int(np.prod(keep)), R))
+                elif be.planes_pass_supported(self.lshape, s, R):
+                    self.i8 = be.planes_create(self.Xd, self.lshape, 5 if want == '5' else 6)
+                    self.i8_general = True
             # single process: the second stage leaves its per-split slabs for the cluster update to add while it stages
             # M (same arithmetic, one launch less on the critical path)
             if not comm.active and hasattr(be, 'kr_reduce_slabs') and os.environ.get('SKT_NO_KR_SLABS', '0') != '1':
@@ -526,6 +535,9 @@ class CpAlsEngine(object):
         """One pass over X: the partial contraction that serves every mode of ``group`` (0: modes
         ``[0, s)``, 1: modes ``[s, N)``), by the dense MTTKRP kernel on a reshaped view of X."""
         be, s, N = self.be, self.ts, self.N
+        if self.i8 is not None and self.i8_general:
+            be.planes_pass(self.i8, s, group, self.Ud, self.R, self.TA if group == 0 else self.TB)
+            return
         if self.i8 is not None:
             R, Ud, ls = self.R, self.Ud, self.lshape
             if group == 0 and s == N - 1:

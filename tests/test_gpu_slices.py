@@ -194,3 +194,74 @@ def test_cp_als_sliced_falls_back_to_fp64_when_the_shape_is_not_supported(sliced
     U0 = [rng.rand(d, 3) for d in X.shape]
     P, fit, itr, _ = _cp(X, 3, U0, max_iter=5, conv=0)
     assert np.isfinite(fit)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the general tree pass (skt_planes_pass): X as [P x Q], one long GEMM against the Khatri-Rao product of a group's factors
+def _kr(mats):
+    out = mats[0]
+    for M in mats[1:]:
+        out = (out[:, None, :] * M[None, :, :]).reshape(-1, M.shape[1])
+    return out
+
+
+PASS_CASES = [((16, 16, 16), 1, 4), ((16, 16, 16), 2, 4), ((12, 20, 8, 16), 2, 64), ((40, 6, 10, 32), 2, 33),
+              ((160, 20, 160), 2, 64), ((9, 64, 80), 1, 17), ((24, 40, 608), 2, 32), ((6, 5, 4, 8, 16), 3, 48),
+              ((2100, 16), 1, 8), ((130, 20, 34, 32), 2, 20)]
+
+
+@pytest.mark.parametrize('shape,split,R', PASS_CASES)
+@pytest.mark.parametrize('S', [6, 5])
+def test_planes_tree_pass_matches_numpy(K, dev, shape, split, R, S):
+    rng = np.random.RandomState(sum(shape) + R + S + split)
+    X = rng.rand(*shape) - 0.25
+    U = [rng.rand(d, R) - 0.4 for d in shape]
+    Ud = [dev.to_device(u) for u in U]
+    assert K.PlanesHandle.pass_supported(shape, split, R)
+    P = K.PlanesHandle(dev.to_device(X), shape, S)
+    try:
+        Pn = int(np.prod(shape[:split]))
+        X2 = X.reshape(Pn, -1)
+        TA = dev.to_host(P.tree_pass(split, 0, Ud, R))
+        refA = X2.dot(_kr(U[split:]))
+        TB = dev.to_host(P.tree_pass(split, 1, Ud, R))
+        refB = X2.T.dot(_kr(U[:split]))
+        tol = 1e-12 if S == 6 else 1e-10
+        assert TA.shape == refA.shape and TB.shape == refB.shape
+        assert relerr(TA, refA) < tol
+        assert relerr(TB, refB) < tol
+    finally:
+        P.close()
+
+
+def test_planes_tree_pass_long_contraction_crosses_the_int32_flush(K, dev):
+    # 20480 products per output: two K segments at least (an INT32 accumulator holds 16384 of them safely); worst-case digits
+    shape, R = (20480, 16), 8
+    X = np.full(shape, -1.0)
+    X[::3] = 0.999
+    U = [np.full((shape[0], R), -1.0), np.full((shape[1], R), 1.0)]
+    P = K.PlanesHandle(dev.to_device(X), shape, 6)
+    try:
+        T = dev.to_host(P.tree_pass(1, 1, [dev.to_device(u) for u in U], R))
+        assert relerr(T, X.T.dot(U[0])) < 1e-12
+    finally:
+        P.close()
+
+
+@pytest.mark.parametrize('shape,R', [((12, 16, 10, 16), 6), ((20, 12, 16, 16), 40), ((48, 16, 640), 16), ((64, 32, 32), 50)])
+def test_cp_als_sliced_general_passes_match_fp64_engine(monkeypatch, shape, R):
+    rng = np.random.RandomState(sum(shape) + R)
+    X = rng.rand(*shape)
+    U0 = [rng.rand(d, R) for d in shape]
+    P0, fit0, itr0, _ = _cp(X, R, U0, max_iter=8, conv=0)
+    monkeypatch.setenv('SKT_DENSE_I8', '6')
+    from sktensor import _parallel as par, dtensor
+    eng = par.CpAlsEngine(dtensor(X), R, [u.copy() for u in U0])
+    try:
+        assert eng.i8 is not None and eng.i8_general
+    finally:
+        eng.release()
+    P1, fit1, itr1, _ = _cp(X, R, U0, max_iter=8, conv=0)
+    assert abs(fit1 - fit0) < 1e-9
+    for a, b in zip(P1.U, P0.U):
+        assert relerr(a, b) < 1e-7
