@@ -69,21 +69,6 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// shared-memory matrix descriptor, SWIZZLE_128B, 128-byte rows, 8-row groups 1024 bytes apart (both majors of this file)
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                 // leading byte offset: one swizzle atom wide, never stepped
-    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
-    d |= (uint64_t)1 << 46;                 // descriptor version of sm_100
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
-    return d;
-}
-// instruction descriptor: S32 accumulate, signed x signed, B K-major, A K-major or MN-major, M = 128, N = n
-__device__ __forceinline__ uint32_t instr_desc(int n, bool a_mn) {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-}
-
 // ---- slicing ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void slice4(const double x[4], double scale, int S, uint32_t w[MAXS]) {
     uint32_t lo[4], hi[4];
@@ -199,27 +184,125 @@ __global__ void __launch_bounds__(128) factor_slice_kernel(const double *__restr
 }
 
 // ---- the contraction --------------------------------------------------------------------------------------------------
+// One kernel for every pass.  A unit of work is (row tile of 128, K segment); a segment is at most 128 chunks of 128 bytes
+// (16384 products per INT32 accumulator) and the segments of one tile are summed in order from FP64 slabs.  The factor
+// planes are either resident in shared memory (BRES: short contractions, loaded once per CTA) or travel chunk by chunk
+// through a two-slot ring beside the A ring.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (owns the tensor memory), warps 2..5 = epilogue (one TMEM lane quarter
+// each).  Warps 0 and 1 run their loops with all 32 lanes and issue through elect.sync: every descriptor is then
+// warp-uniform by construction and lives in uniform registers (with a single-lane `if (lane == 0)` loop the compiler wraps
+// each UTCIMMA in an election loop and ~35 uniform-datapath instructions, which made the issue thread the bottleneck of
+// the rank-64 passes: 1.57 ms per 160^4 pass against 0.9 after this change).
 struct GemmParams {
     long long rows;      // output rows (GEMM M)
     int tiles;           // ceil(rows / 128)
     int nchunk;          // ceil(Kc / 128)
-    int S, R, NS, smin;
-    double *T;           // rows x R
+    int nseg, cps;       // K segments, chunks per segment
+    int Kc;
+    int R, NS;
+    double *T;           // rows x R (nseg == 1) ...
+    double *slabs;       // ... or nseg slabs of rows x R
     const double *inv;   // per column
 };
 
-// warp 0: TMA producer, warp 1: MMA issuer (owns the tensor memory), warps 2..5: epilogue (one TMEM lane quarter each)
-template <bool A_MN>
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, descriptor version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
+__host__ __device__ constexpr uint32_t idesc_of(int n, bool a_mn) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__host__ __device__ constexpr int smin_of(int S) { return S == 6 ? 4 : 2; }       // pairs below it: < 2^-52 of full scale
+
+// blocks [FIRST, FIRST + COUNT) of the stacked B slices, at most 256 columns per instruction
+template <bool A_MN, int NBW, int FIRST, int COUNT>
+__device__ __forceinline__ void issue_groups(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc) {
+    constexpr int GMAX = 256 / NBW;
+    constexpr uint32_t BT16 = (NBW * KC) >> 4;
+#pragma unroll
+    for (int b = FIRST; b < FIRST + COUNT; b += GMAX) {
+        const int g = (FIRST + COUNT - b) < GMAX ? (FIRST + COUNT - b) : GMAX;
+        umma_i8(d + (uint32_t)(b * NBW), desc64(a_lo), desc64(b_lo + (uint32_t)b * BT16), idesc_of(NBW * g, A_MN), acc);
+    }
+}
+
+// all products of A slice I with the B slices j >= smin - I of one 32-byte k-step.  They lie one after the other in shared
+// memory and belong to the consecutive accumulators I + j: one MMA of N = NBW (S - j0) columns (split at 256) covers them.
+template <bool A_MN, int NBW, int S, int I>
+__device__ __forceinline__ void issue_slice(uint32_t tacc, uint32_t a_lo, uint32_t b_lo_chunk, bool head) {
+    constexpr int SMIN = smin_of(S);
+    constexpr int J0 = SMIN - I > 0 ? SMIN - I : 0;
+    constexpr int NBLK = S - J0;
+    constexpr uint32_t BT16 = (NBW * KC) >> 4;
+    const uint32_t d = tacc + (uint32_t)((I + J0 - SMIN) * NBW);
+    const uint32_t b_lo = b_lo_chunk + (uint32_t)J0 * BT16;
+    if (head && I == S - 1) {
+        issue_groups<A_MN, NBW, 0, NBLK>(d, a_lo, b_lo, 0u);               // first product of the unit: overwrite
+    } else if (head && I >= SMIN) {
+        issue_groups<A_MN, NBW, 0, 1>(d, a_lo, b_lo, 0u);                  // opens one more accumulator ...
+        issue_groups<A_MN, NBW, 1, NBLK - 1>(d, a_lo, b_lo, 1u);           // ... the others hold data already
+    } else {
+        issue_groups<A_MN, NBW, 0, NBLK>(d, a_lo, b_lo, 1u);
+    }
+}
+
+template <bool A_MN, int NBW, int S, int I>
+struct SliceLoop {
+    // A slices S-1 .. 0 of one chunk: wait for the stage, issue, release it
+    static __device__ __forceinline__ void run(const bool elected, const uint32_t tacc, unsigned char *sA, uint64_t *full,
+                                               uint64_t *empty, const uint32_t b_lo_chunk, const int nks, const bool first_chunk,
+                                               int &st, uint32_t &ph, const int NS) {
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a_lo = desc_lo(smem_u32(sA + (size_t)st * STAGE_BYTES));
+        constexpr uint32_t A_STEP16 = (A_MN ? 32 * 128 : 32) >> 4;   // K-major: 32 bytes along the rows; MN-major: 32 rows on
+        if (elected) {
+#pragma unroll
+            for (int ks = 0; ks < KC / 32; ++ks)
+                if (ks < nks) issue_slice<A_MN, NBW, S, I>(tacc, a_lo + ks * A_STEP16, b_lo_chunk + ks * 2u, first_chunk && ks == 0);
+            umma_commit(&empty[st]);
+        }
+        __syncwarp();
+        if (++st == NS) {
+            st = 0;
+            ph ^= 1u;
+        }
+        SliceLoop<A_MN, NBW, S, I - 1>::run(elected, tacc, sA, full, empty, b_lo_chunk, nks, first_chunk, st, ph, NS);
+    }
+};
+template <bool A_MN, int NBW, int S>
+struct SliceLoop<A_MN, NBW, S, -1> {
+    static __device__ __forceinline__ void run(bool, uint32_t, unsigned char *, uint64_t *, uint64_t *, uint32_t, int, bool, int &,
+                                               uint32_t &, int) {}
+};
+
+template <bool A_MN, int NBW, int S, bool BRES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int S = p.S, NS = p.NS, smin = p.smin;
-    unsigned char *sB = smem;                                      // [chunk][slice] tiles of 32 rows x 128 bytes
-    unsigned char *sA = smem + (size_t)p.nchunk * S * BTILE_BYTES;  // NS stages of 128 x 128 bytes
+    constexpr uint32_t BT = NBW * KC;                              // one B slice tile
+    constexpr int NSETS = NBW == 32 ? 2 : 1;                       // accumulator sets in the 512 columns of tensor memory
+    constexpr int ACC_COLS = MAXACC * NBW;
+    constexpr int SMIN = smin_of(S);
+    const int NS = p.NS;
+    const int nbslots = BRES ? p.nchunk : 2;
+    unsigned char *sB = smem;                                      // nbslots x S tiles
+    unsigned char *sA = smem + (size_t)nbslots * S * BT;           // NS stages of 128 x 128 bytes
     uint64_t *bars = (uint64_t *)(sA + (size_t)NS * STAGE_BYTES);
-    uint64_t *full = bars, *empty = bars + NS, *bfull = bars + 2 * NS, *tfull = bars + 2 * NS + 1, *tempty = bars + 2 * NS + 3;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NS + 5);
+    uint64_t *full = bars, *empty = bars + NS, *bfull = bars + 2 * NS, *bempty = bars + 2 * NS + 2, *tfull = bars + 2 * NS + 4,
+             *tempty = bars + 2 * NS + 6;
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NS + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -227,8 +310,9 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(bfull, 1);
         for (int b = 0; b < 2; ++b) {
+            mbar_init(&bfull[b], 1);
+            mbar_init(&bempty[b], 1);
             mbar_init(&tfull[b], 1);
             mbar_init(&tempty[b], 4);
         }
@@ -242,131 +326,147 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    constexpr int ACC_COLS = MAXACC * NB;                          // columns of one accumulator set (two sets: 448 of 512)
+    const int nunits = p.tiles * p.nseg;
 
     if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bfull, (uint32_t)(p.nchunk * S * BTILE_BYTES));
-            for (int c = 0; c < p.nchunk; ++c)
-                for (int j = 0; j < S; ++j) tma_load_3d(sB + (size_t)(c * S + j) * BTILE_BYTES, &tmB, bfull, c * KC, 0, j);
-            int st = 0;
-            uint32_t ph = 0;
-            bool wrapped = false;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
+        const bool elected = elect_one();
+        if (BRES) {
+            if (elected) {
+                mbar_arrive_expect_tx(&bfull[0], (uint32_t)(p.nchunk * S * BT));
                 for (int c = 0; c < p.nchunk; ++c)
-                    for (int i = S - 1; i >= 0; --i) {
-                        if (wrapped) mbar_wait(&empty[st], ph ^ 1u);
+                    for (int j = 0; j < S; ++j) tma_load_3d(sB + (size_t)(c * S + j) * BT, &tmB, &bfull[0], c * KC, 0, j);
+            }
+            __syncwarp();
+        }
+        int st = 0, bs = 0;
+        uint32_t ph = 0, bph = 0;
+        bool wrapped = false, bwrapped = false;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            const int tile = u / p.nseg, g = u - tile * p.nseg;
+            const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
+            for (int c = c0; c < c1; ++c) {
+                if (!BRES) {
+                    if (bwrapped) mbar_wait(&bempty[bs], bph ^ 1u);
+                    if (elected) {
+                        mbar_arrive_expect_tx(&bfull[bs], (uint32_t)(S * BT));
+#pragma unroll
+                        for (int j = 0; j < S; ++j) tma_load_3d(sB + ((size_t)bs * S + j) * BT, &tmB, &bfull[bs], c * KC, 0, j);
+                    }
+                    __syncwarp();
+                    if (++bs == 2) {
+                        bs = 0;
+                        bph ^= 1u;
+                        bwrapped = true;
+                    }
+                }
+#pragma unroll
+                for (int i = S - 1; i >= 0; --i) {
+                    if (wrapped) mbar_wait(&empty[st], ph ^ 1u);
+                    if (elected) {
                         mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
                         if (A_MN)
                             tma_load_3d(sA + (size_t)st * STAGE_BYTES, &tmA, &full[st], tile * TM, c * KC, i);
                         else
                             tma_load_3d(sA + (size_t)st * STAGE_BYTES, &tmA, &full[st], c * KC, tile * TM, i);
-                        if (++st == NS) {
-                            st = 0;
-                            ph ^= 1u;
-                            wrapped = true;
-                        }
                     }
+                    __syncwarp();
+                    if (++st == NS) {
+                        st = 0;
+                        ph ^= 1u;
+                        wrapped = true;
+                    }
+                }
+            }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            mbar_wait(bfull, 0);
-            int st = 0;
-            uint32_t ph = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
-                const uint32_t ab = lt & 1u;
-                if (lt >= 2) mbar_wait(&tempty[ab], ((lt >> 1) - 1) & 1u);
-                tc_fence_after();
-                const uint32_t tacc = tmem + ab * (uint32_t)ACC_COLS;
-                for (int c = 0; c < p.nchunk; ++c)
-                    for (int i = S - 1; i >= 0; --i) {
-                        mbar_wait(&full[st], ph);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(sA + (size_t)st * STAGE_BYTES);
-                        const int j0 = smin - i > 0 ? smin - i : 0;
-                        const uint32_t b_addr = smem_u32(sB + (size_t)(c * S + j0) * BTILE_BYTES);
-                        const uint32_t idesc = instr_desc(NB * (S - j0), A_MN);
-                        const uint32_t d = tacc + (uint32_t)((i + j0 - smin) * NB);
-                        // K-major A: 32 bytes further along the 128-byte rows; MN-major A: 32 rows (4 groups of 8) further
-                        constexpr uint32_t A_STEP = A_MN ? 32 * 128 : 32;
-#pragma unroll
-                        for (int ks = 0; ks < KC / 32; ++ks) {
-                            const uint64_t da = smem_desc_sw128(a_addr + ks * A_STEP), db = smem_desc_sw128(b_addr + ks * 32);
-                            if (c == 0 && ks == 0 && i == S - 1) {
-                                umma_i8(d, da, db, idesc, 0u);           // first product of the tile: overwrite
-                            } else if (c == 0 && ks == 0 && i >= smin) {
-                                // this slice opens one more accumulator (its first 32 columns); the others hold data already
-                                umma_i8(d, da, db, instr_desc(NB, A_MN), 0u);
-                                umma_i8(d + NB, da, smem_desc_sw128(b_addr + BTILE_BYTES + ks * 32), instr_desc(NB * (S - 1), A_MN),
-                                        1u);
-                            } else {
-                                umma_i8(d, da, db, idesc, 1u);
-                            }
-                        }
-                        umma_commit(&empty[st]);
-                        if (++st == NS) {
-                            st = 0;
-                            ph ^= 1u;
-                        }
+        const bool elected = elect_one();
+        int st = 0, bs = 0;
+        uint32_t ph = 0, bph = 0, lu = 0;
+        if (BRES) mbar_wait(&bfull[0], 0);
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++lu) {
+            const int tile = u / p.nseg, g = u - tile * p.nseg;
+            const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
+            const uint32_t set = lu % NSETS, use = lu / NSETS;
+            if (use >= 1) mbar_wait(&tempty[set], (use - 1) & 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem + set * (uint32_t)ACC_COLS;
+            for (int c = c0; c < c1; ++c) {
+                if (!BRES) mbar_wait(&bfull[bs], bph);
+                const int valid = min(KC, p.Kc - c * KC);
+                const int nks = (valid + 31) >> 5;                     // the zero-filled tail of the last chunk is skipped
+                const uint32_t b_lo_chunk = desc_lo(smem_u32(sB + (size_t)(BRES ? c : bs) * S * BT));
+                SliceLoop<A_MN, NBW, S, S - 1>::run(elected, tacc, sA, full, empty, b_lo_chunk, nks, c == c0, st, ph, NS);
+                if (!BRES) {
+                    if (elected) umma_commit(&bempty[bs]);
+                    __syncwarp();
+                    if (++bs == 2) {
+                        bs = 0;
+                        bph ^= 1u;
                     }
-                umma_commit(&tfull[ab]);
+                }
             }
+            if (elected) umma_commit(&tfull[set]);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;                                    // the TMEM lane quarter this warp may read
-        const int nacc = 2 * (S - 1) - smin + 1;
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
-            const uint32_t ab = lt & 1u;
-            mbar_wait(&tfull[ab], (lt >> 1) & 1u);
+        constexpr int NACC = 2 * (S - 1) - SMIN + 1;
+        uint32_t lu = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++lu) {
+            const int tile = u / p.nseg, g = u - tile * p.nseg;
+            const uint32_t set = lu % NSETS, use = lu / NSETS;
+            mbar_wait(&tfull[set], use & 1u);
             tc_fence_after();
-            double r[NB];
+            const long long row = (long long)tile * TM + q * 32 + lane;
+            double *out = (p.nseg == 1 ? p.T : p.slabs + (size_t)g * p.rows * p.R) + row * p.R;
+#pragma unroll 1
+            for (int h = 0; h < NBW / 32; ++h) {
+                double r[32];
 #pragma unroll
-            for (int n = 0; n < NB; ++n) r[n] = 0.0;
-            for (int a = nacc - 1; a >= 0; --a) {
-                uint32_t v[NB];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)ACC_COLS + (uint32_t)(a * NB);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                    "tcgen05.wait::ld.sync.aligned;\n"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr)
-                    : "memory");
+                for (int n = 0; n < 32; ++n) r[n] = 0.0;
+#pragma unroll 1
+                for (int a = NACC - 1; a >= 0; --a) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + set * (uint32_t)ACC_COLS + (uint32_t)(a * NBW + h * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                        "tcgen05.wait::ld.sync.aligned;\n"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr)
+                        : "memory");
 #pragma unroll
-                for (int n = 0; n < NB; ++n) r[n] = fma(r[n], 256.0, (double)(int)v[n]);
+                    for (int n = 0; n < 32; ++n) r[n] = fma(r[n], 256.0, (double)(int)v[n]);
+                }
+                if (row < p.rows) {
+                    if (p.R == NBW) {
+#pragma unroll
+                        for (int n = 0; n < 32; n += 2) {
+                            double2 o;
+                            o.x = r[n] * p.inv[h * 32 + n];
+                            o.y = r[n + 1] * p.inv[h * 32 + n + 1];
+                            *reinterpret_cast<double2 *>(out + h * 32 + n) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int n = 0; n < 32; ++n)
+                            if (h * 32 + n < p.R) out[h * 32 + n] = r[n] * p.inv[h * 32 + n];
+                    }
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[ab]);
-            const long long row = (long long)tile * TM + q * 32 + lane;
-            if (row < p.rows) {
-                double *out = p.T + row * p.R;
-                if (p.R == NB) {
-#pragma unroll
-                    for (int n = 0; n < NB; n += 2) {
-                        double2 o;
-                        o.x = r[n] * p.inv[n];
-                        o.y = r[n + 1] * p.inv[n + 1];
-                        *reinterpret_cast<double2 *>(out + n) = o;
-                    }
-                } else {
-#pragma unroll
-                    for (int n = 0; n < NB; ++n)
-                        if (n < p.R) out[n] = r[n] * p.inv[n];
-                }
-            }
+            if (lane == 0) mbar_arrive(&tempty[set]);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
 }
-
 
 // ---- general tree pass: long contractions, rank up to 64 --------------------------------------------------------------
 // X seen as the matrix [P x Q] (P = product of the modes before the split, Q = of the others):
@@ -382,11 +482,12 @@ struct KrDesc {
     const double *U[SKT_MAX_NDIM];
 };
 
-__device__ __forceinline__ double kr_value(const KrDesc &d, long long k, int n) {
+__device__ __forceinline__ double kr_value(const KrDesc &d, long long k64, int n) {
     double v = 1.0;
+    unsigned int k = (unsigned int)k64;                            // the contraction length is below 2^31
     for (int m = d.nfac - 1; m >= 0; --m) {
-        const int idx = (int)(k % d.dims[m]);
-        k /= d.dims[m];
+        const unsigned int idx = k % (unsigned int)d.dims[m];
+        k /= (unsigned int)d.dims[m];
         v *= d.U[m][(size_t)idx * d.R + n];
     }
     return v;
@@ -437,202 +538,6 @@ __global__ void __launch_bounds__(256) kr_slice_kernel(const KrDesc d, long long
 #pragma unroll
     for (int s = 0; s < MAXS; ++s)
         if (s < S) Bp[((size_t)s * nb + n) * kpad4 + k4] = pad ? 0u : w[s];
-}
-
-struct StreamParams {
-    long long rows;
-    int tiles, nchunk, nseg, cps;      // row tiles, k-chunks, K segments, chunks per segment
-    int Kc;
-    int S, R, NS, smin;
-    double *T;                         // rows x R (nseg == 1) ...
-    double *slabs;                     // ... or nseg slabs of rows x R
-    const double *inv;
-};
-
-template <int NBW>
-__device__ __forceinline__ void issue_blocks(uint32_t d, uint64_t da, uint32_t b_addr, int ks, int nblk, bool a_mn, uint32_t acc_first,
-                                             uint32_t acc_rest) {
-    // nblk stacked B slices of NBW columns each, at most 256 columns per instruction; the first block may carry its own
-    // accumulate flag (it opens a new accumulator)
-    constexpr int GMAX = 256 / NBW;
-    constexpr uint32_t BT = NBW * KC;
-    int b = 0;
-    if (acc_first != acc_rest) {
-        umma_i8(d, da, smem_desc_sw128(b_addr + ks * 32), instr_desc(NBW, a_mn), acc_first);
-        b = 1;
-    }
-    while (b < nblk) {
-        const int g = min(GMAX, nblk - b);
-        umma_i8(d + (uint32_t)(b * NBW), da, smem_desc_sw128(b_addr + b * BT + ks * 32), instr_desc(NBW * g, a_mn), b == 0 ? acc_first : acc_rest);
-        b += g;
-    }
-}
-
-template <bool A_MN, int NBW>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-slice_gemm_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const StreamParams p) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    constexpr uint32_t BT = NBW * KC;                              // one B slice tile
-    constexpr int NSETS = NBW == 32 ? 2 : 1;                       // accumulator sets in the 512 columns of tensor memory
-    constexpr int ACC_COLS = MAXACC * NBW;
-    const int S = p.S, NS = p.NS, smin = p.smin;
-    unsigned char *sB = smem;                                      // 2 slots of S tiles
-    unsigned char *sA = smem + 2 * (size_t)S * BT;
-    uint64_t *bars = (uint64_t *)(sA + (size_t)NS * STAGE_BYTES);
-    uint64_t *full = bars, *empty = bars + NS, *bfull = bars + 2 * NS, *bempty = bars + 2 * NS + 2, *tfull = bars + 2 * NS + 4,
-             *tempty = bars + 2 * NS + 6;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * NS + 8);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-        }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&bfull[b], 1);
-            mbar_init(&bempty[b], 1);
-            mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 4);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-    const int nunits = p.tiles * p.nseg;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int st = 0, bs = 0;
-            uint32_t ph = 0, bph = 0;
-            bool wrapped = false, bwrapped = false;
-            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-                const int tile = u / p.nseg, g = u % p.nseg;
-                const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
-                for (int c = c0; c < c1; ++c) {
-                    if (bwrapped) mbar_wait(&bempty[bs], bph ^ 1u);
-                    mbar_arrive_expect_tx(&bfull[bs], (uint32_t)(S * BT));
-                    for (int j = 0; j < S; ++j) tma_load_3d(sB + ((size_t)bs * S + j) * BT, &tmB, &bfull[bs], c * KC, 0, j);
-                    if (++bs == 2) {
-                        bs = 0;
-                        bph ^= 1u;
-                        bwrapped = true;
-                    }
-                    for (int i = S - 1; i >= 0; --i) {
-                        if (wrapped) mbar_wait(&empty[st], ph ^ 1u);
-                        mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
-                        if (A_MN)
-                            tma_load_3d(sA + (size_t)st * STAGE_BYTES, &tmA, &full[st], tile * TM, c * KC, i);
-                        else
-                            tma_load_3d(sA + (size_t)st * STAGE_BYTES, &tmA, &full[st], c * KC, tile * TM, i);
-                        if (++st == NS) {
-                            st = 0;
-                            ph ^= 1u;
-                            wrapped = true;
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            int st = 0, bs = 0;
-            uint32_t ph = 0, bph = 0, lu = 0;
-            for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++lu) {
-                const int g = u % p.nseg;
-                const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
-                const uint32_t set = lu % NSETS, use = lu / NSETS;
-                if (use >= 1) mbar_wait(&tempty[set], (use - 1) & 1u);
-                tc_fence_after();
-                const uint32_t tacc = tmem + set * (uint32_t)ACC_COLS;
-                for (int c = c0; c < c1; ++c) {
-                    mbar_wait(&bfull[bs], bph);
-                    const int valid = min(KC, p.Kc - c * KC);
-                    const int nks = (valid + 31) / 32;                 // the zero-filled tail of the last chunk is skipped
-                    for (int i = S - 1; i >= 0; --i) {
-                        mbar_wait(&full[st], ph);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(sA + (size_t)st * STAGE_BYTES);
-                        const int j0 = smin - i > 0 ? smin - i : 0;
-                        const uint32_t b_addr = smem_u32(sB + ((size_t)bs * S + j0) * BT);
-                        const uint32_t d = tacc + (uint32_t)((i + j0 - smin) * NBW);
-                        constexpr uint32_t A_STEP = A_MN ? 32 * 128 : 32;
-                        for (int ks = 0; ks < nks; ++ks) {
-                            const uint64_t da = smem_desc_sw128(a_addr + ks * A_STEP);
-                            const bool head = (c == c0 && ks == 0);
-                            const uint32_t acc_first = (head && (i == S - 1 || i >= smin)) ? 0u : 1u;
-                            const uint32_t acc_rest = (head && i == S - 1) ? 0u : 1u;
-                            issue_blocks<NBW>(d, da, b_addr, ks, S - j0, A_MN, acc_first, acc_rest);
-                        }
-                        umma_commit(&empty[st]);
-                        if (++st == NS) {
-                            st = 0;
-                            ph ^= 1u;
-                        }
-                    }
-                    umma_commit(&bempty[bs]);
-                    if (++bs == 2) {
-                        bs = 0;
-                        bph ^= 1u;
-                    }
-                }
-                umma_commit(&tfull[set]);
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        const int nacc = 2 * (S - 1) - smin + 1;
-        uint32_t lu = 0;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++lu) {
-            const int tile = u / p.nseg, g = u % p.nseg;
-            const uint32_t set = lu % NSETS, use = lu / NSETS;
-            mbar_wait(&tfull[set], use & 1u);
-            tc_fence_after();
-            const long long row = (long long)tile * TM + q * 32 + lane;
-            double *out = (p.nseg == 1 ? p.T : p.slabs + (size_t)g * p.rows * p.R) + row * p.R;
-#pragma unroll 1
-            for (int h = 0; h < NBW / 32; ++h) {
-                double r[32];
-#pragma unroll
-                for (int n = 0; n < 32; ++n) r[n] = 0.0;
-                for (int a = nacc - 1; a >= 0; --a) {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + set * (uint32_t)ACC_COLS + (uint32_t)(a * NBW + h * 32);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                        "tcgen05.wait::ld.sync.aligned;\n"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr)
-                        : "memory");
-#pragma unroll
-                    for (int n = 0; n < 32; ++n) r[n] = fma(r[n], 256.0, (double)(int)v[n]);
-                }
-                if (row < p.rows) {
-#pragma unroll
-                    for (int n = 0; n < 32; ++n)
-                        if (h * 32 + n < p.R) out[h * 32 + n] = r[n] * p.inv[h * 32 + n];
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[set]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
 }
 
 // T[e] = sum_g slab[g][e], g ascending (fixed order)
@@ -771,20 +676,35 @@ PassWs pass_ws(const PassPlan &pl, int S, int R) {
     return w;
 }
 
-template <bool A_MN, int NBW>
-int launch_stream(const CUtensorMap &tmA, const CUtensorMap &tmB, StreamParams &sp, cudaStream_t st) {
-    const size_t fixed = 1024 + 2 * (size_t)sp.S * NBW * KC + 512;         // alignment slack, two B slots, barriers
+constexpr size_t BRES_BYTES = 98304;        // factor planes up to this size stay resident in shared memory
+
+template <bool A_MN, int NBW, int S, bool BRES>
+int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams &gp, cudaStream_t st) {
+    const size_t bbytes = (size_t)(BRES ? gp.nchunk : 2) * S * NBW * KC;
+    const size_t fixed = 1024 + bbytes + 512;                       // alignment slack, factor tiles, barriers
     const size_t cap = smem_optin_bytes();
-    SKT_REQUIRE(cap >= fixed + 3 * STAGE_BYTES, SKT_EUNSUPPORTED, "not enough shared memory for the sliced tree pass");
-    sp.NS = (int)std::min<size_t>(12, (cap - fixed) / STAGE_BYTES);
-    const size_t smem = fixed + (size_t)sp.NS * STAGE_BYTES;
+    SKT_REQUIRE(cap >= fixed + 3 * STAGE_BYTES, SKT_EUNSUPPORTED, "not enough shared memory for the sliced contraction");
+    gp.NS = (int)std::min<size_t>(12, (cap - fixed) / STAGE_BYTES);
+    const size_t smem = fixed + (size_t)gp.NS * STAGE_BYTES;
     static unsigned long long mask = 0;
     if (first_use_on_device(mask))
-        SKT_CUDA(cudaFuncSetAttribute(slice_gemm_stream_kernel<A_MN, NBW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-    const int grid = std::min(sp.tiles * sp.nseg, sm_count());
-    slice_gemm_stream_kernel<A_MN, NBW><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, sp);
+        SKT_CUDA(cudaFuncSetAttribute(slice_gemm_kernel<A_MN, NBW, S, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    const int grid = std::min(gp.tiles * gp.nseg, sm_count());
+    slice_gemm_kernel<A_MN, NBW, S, BRES><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, gp);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
+}
+
+template <bool A_MN, int NBW>
+int launch_gemm_s(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams &gp, int S, cudaStream_t st) {
+    const bool bres = (size_t)gp.nchunk * S * NBW * KC <= BRES_BYTES;
+    if (S == 6) return bres ? launch_gemm<A_MN, NBW, 6, true>(tmA, tmB, gp, st) : launch_gemm<A_MN, NBW, 6, false>(tmA, tmB, gp, st);
+    return bres ? launch_gemm<A_MN, NBW, 5, true>(tmA, tmB, gp, st) : launch_gemm<A_MN, NBW, 5, false>(tmA, tmB, gp, st);
+}
+
+int launch_gemm_any(bool a_mn, int nb, const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams &gp, int S, cudaStream_t st) {
+    if (a_mn) return nb == 32 ? launch_gemm_s<true, 32>(tmA, tmB, gp, S, st) : launch_gemm_s<true, 64>(tmA, tmB, gp, S, st);
+    return nb == 32 ? launch_gemm_s<false, 32>(tmA, tmB, gp, S, st) : launch_gemm_s<false, 64>(tmA, tmB, gp, S, st);
 }
 
 }  // namespace
@@ -880,15 +800,13 @@ int skt_planes_ttm(const skt_planes *P, int mode, const double *U_d, int rank, d
     if (rc) return rc;
     SKT_REQUIRE(U_d && T_d, SKT_EINVAL, "null argument");
     const int S = P->S;
-    int smin = S == 6 ? 4 : 2;                          // pairs below it: < 2^-52 of full scale
-    if (const char *e = getenv("SKT_I8_SMIN")) smin = std::max(2 * (S - 1) + 1 - MAXACC, std::min(S - 1, atoi(e)));
     const size_t need = ttm_ws(pl, S);
     SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
     SKT_REQUIRE((((uintptr_t)ws_d) & 255) == 0 && (((uintptr_t)T_d) & 15) == 0, SKT_EINVAL, "misaligned workspace or output");
     unsigned char *Bp = (unsigned char *)ws_d;
     double *inv = (double *)(Bp + align_up((size_t)S * NB * pl.kpad, 256));
 
-    factor_slice_kernel<<<NB, 128, 0, st>>>(U_d, pl.Kc, rank, pl.kpad, S, smin, P->scale, (uint32_t *)Bp, inv);
+    factor_slice_kernel<<<NB, 128, 0, st>>>(U_d, pl.Kc, rank, pl.kpad, S, smin_of(S), P->scale, (uint32_t *)Bp, inv);
     SKT_LAUNCH_CHECK();
 
     CUtensorMap tmA, tmB;
@@ -905,31 +823,15 @@ int skt_planes_ttm(const skt_planes *P, int mode, const double *U_d, int rank, d
     gp.rows = pl.rows;
     gp.tiles = (int)((pl.rows + TM - 1) / TM);
     gp.nchunk = pl.nchunk;
-    gp.S = S;
+    gp.nseg = 1;
+    gp.cps = pl.nchunk;
+    gp.Kc = pl.Kc;
     gp.R = rank;
-    gp.smin = smin;
     gp.T = T_d;
+    gp.slabs = nullptr;
     gp.inv = inv;
-    const size_t fixed = 1024 + (size_t)pl.nchunk * S * BTILE_BYTES + 256;
-    const size_t cap = smem_optin_bytes();
-    SKT_REQUIRE(cap >= fixed + 2 * STAGE_BYTES, SKT_EUNSUPPORTED, "not enough shared memory for the sliced contraction");
-    gp.NS = (int)std::min<size_t>(12, (cap - fixed) / STAGE_BYTES);
-    const size_t smem = fixed + (size_t)gp.NS * STAGE_BYTES;
-    const int grid = std::min(gp.tiles, sm_count());
-    static unsigned long long attr_mask[2] = {0, 0};
-    if (pl.a_mn) {
-        if (first_use_on_device(attr_mask[1]))
-            SKT_CUDA(cudaFuncSetAttribute(slice_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-        slice_gemm_kernel<true><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, gp);
-    } else {
-        if (first_use_on_device(attr_mask[0]))
-            SKT_CUDA(cudaFuncSetAttribute(slice_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-        slice_gemm_kernel<false><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, gp);
-    }
-    SKT_LAUNCH_CHECK();
-    return SKT_OK;
+    return launch_gemm_any(pl.a_mn, NB, tmA, tmB, gp, S, st);
 }
-
 
 int skt_planes_pass_supported(const int64_t *shape, int ndim, int split, int rank) {
     if (!shape || ndim < 2 || ndim > SKT_MAX_NDIM || split < 1 || split >= ndim || rank < 1 || rank > 64) return 0;
@@ -955,8 +857,7 @@ int skt_planes_pass(const skt_planes *P, int split, int group, const double *con
     if (rc) return rc;
     SKT_REQUIRE(U_d && T_d, SKT_EINVAL, "null argument");
     const int S = P->S;
-    int smin = S == 6 ? 4 : 2;
-    if (const char *e = getenv("SKT_I8_SMIN")) smin = std::max(2 * (S - 1) + 1 - MAXACC, std::min(S - 1, atoi(e)));
+    const int smin = smin_of(S);
     const PassWs w = pass_ws(pl, S, rank);
     SKT_REQUIRE(ws_d && ws_bytes >= w.total, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", w.total, ws_bytes);
     SKT_REQUIRE((((uintptr_t)ws_d) & 255) == 0, SKT_EINVAL, "misaligned workspace");
@@ -989,23 +890,18 @@ int skt_planes_pass(const skt_planes *P, int split, int group, const double *con
     e = byte_map3(Bp, (uint64_t)pl.kpad, (uint64_t)pl.nb, (uint64_t)S, (uint64_t)pl.kpad, (uint64_t)pl.nb * pl.kpad, (uint32_t)pl.nb, tmB);
     if (e) return e;
 
-    StreamParams sp;
-    sp.rows = pl.rows;
-    sp.tiles = pl.tiles;
-    sp.nchunk = pl.nchunk;
-    sp.nseg = pl.nseg;
-    sp.cps = pl.cps;
-    sp.Kc = (int)pl.Kc;
-    sp.S = S;
-    sp.R = rank;
-    sp.smin = smin;
-    sp.T = T_d;
-    sp.slabs = slabs;
-    sp.inv = inv;
-    if (pl.a_mn)
-        e = pl.nb == 32 ? launch_stream<true, 32>(tmA, tmB, sp, st) : launch_stream<true, 64>(tmA, tmB, sp, st);
-    else
-        e = pl.nb == 32 ? launch_stream<false, 32>(tmA, tmB, sp, st) : launch_stream<false, 64>(tmA, tmB, sp, st);
+    GemmParams gp;
+    gp.rows = pl.rows;
+    gp.tiles = pl.tiles;
+    gp.nchunk = pl.nchunk;
+    gp.nseg = pl.nseg;
+    gp.cps = pl.cps;
+    gp.Kc = (int)pl.Kc;
+    gp.R = rank;
+    gp.T = T_d;
+    gp.slabs = slabs;
+    gp.inv = inv;
+    e = launch_gemm_any(pl.a_mn, pl.nb, tmA, tmB, gp, S, st);
     if (e) return e;
     if (pl.nseg > 1) {
         const long long n = pl.rows * rank;

@@ -25,7 +25,7 @@ def engine(env):
     return _parallel.CpAlsEngine(Xt, R, U), Xt
 
 
-for env in ('', '6', '5'):
+for env in (sys.argv[1].split(',') if len(sys.argv) > 1 else ['', '6', '5']):
     eng, Xt = engine(env)
     ms, fit = bench.timed_sweeps(t, None, 1, eng, 10, 3)
     print('SKT_DENSE_I8=%-2s  %.3f ms per iteration, fit %.12f, sliced=%s general=%s' %

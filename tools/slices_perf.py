@@ -45,14 +45,19 @@ for S in (6, 5):
     e1.record()
     t.cuda.synchronize()
     print('S=%d: planes built in %.3f ms (%.2f GB)' % (S, e0.elapsed_time(e1), P.device_bytes() / 1e9))
-    for smin in ((4, 5) if S == 6 else (2, 3)):
-        os.environ['SKT_I8_SMIN'] = str(smin)
-        a = timed(lambda: P.ttm(2, U[2], R, out=TA))
-        b = timed(lambda: P.ttm(0, U[0], R, out=TB))
-        ea = float((TA - refA).abs().max() / refA.abs().max())
-        eb = float((TB - refB).abs().max() / refB.abs().max())
-        c = timed(lambda: K.kr_reduce(TB, (side, side), [U[1], None], R, 1, out=M2))
-        print('  smin=%d: last-mode %.4f ms (%.0f GB/s of planes, err %.2e)   first-mode %.4f ms (err %.2e)   + kr_reduce %.4f ms'
-              % (smin, a, S * side ** 3 / a * 1e-6, ea, b, eb, c))
-    os.environ.pop('SKT_I8_SMIN', None)
+    a = timed(lambda: P.ttm(2, U[2], R, out=TA))
+    b = timed(lambda: P.ttm(0, U[0], R, out=TB))
+    ea = float((TA - refA).abs().max() / refA.abs().max())
+    eb = float((TB - refB).abs().max() / refB.abs().max())
+    c = timed(lambda: K.kr_reduce(TB, (side, side), [U[1], None], R, 1, out=M2))
+    print('  last-mode %.4f ms (%.0f GB/s of planes, err %.2e)   first-mode %.4f ms (err %.2e)   + kr_reduce %.4f ms'
+          % (a, S * side ** 3 / a * 1e-6, ea, b, eb, c))
+    # the general pass on the same tensor: [512^2 x 512] against U_2 (resident planes) and the transposed product against KR(U_0, U_1)
+    TA2 = P.tree_pass(2, 0, [None, None, U[2]], R)
+    a2 = timed(lambda: P.tree_pass(2, 0, [None, None, U[2]], R, out=TA2))
+    M2b = P.tree_pass(2, 1, [U[0], U[1], None], R)
+    b2 = timed(lambda: P.tree_pass(2, 1, [U[0], U[1], None], R, out=M2b))
+    K.mttkrp_dense(X, shape, [U[0], U[1], None], R, 2, out=M2)
+    print('  general pass: group 0 %.4f ms (err %.2e)   group 1 (K = 512^2, split-K) %.4f ms (err %.2e)'
+          % (a2, float((TA2 - refA).abs().max() / refA.abs().max()), b2, float((M2b - M2).abs().max() / M2.abs().max())))
     P.close()
