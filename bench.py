@@ -727,7 +727,23 @@ def secondary_configs(torch, dist, world, rank, steps):
     strong['cfg5_dense_160^4_rank64'] = {'ms_per_iteration': ms, 'als_iters_per_sec': 1e3 / ms, 'GBps_algorithmic': alg / ms / 1e6,
                                          'sharded_mode': smode, 'final_fit': fit,
                                          'flops_per_iteration_reference': 4 * 2.0 * 64 * 160.0 ** 4}
-    del eng, X
+    del eng
+    # the same with the opt-in sliced passes (INT8 tensor cores): reported beside the default, never instead of it
+    os.environ['SKT_DENSE_I8'] = '6'
+    try:
+        np.random.seed(1)
+        U = [None] + [np.random.rand(gshape[n], 64) for n in range(1, 4)]
+        eng = _parallel.CpAlsEngine(X, 64, U)
+        if eng.i8 is not None:
+            ms8, fit8 = timed_sweeps(torch, dist, world, eng, max(3, min(steps, 10)), 3)
+            strong['cfg5_dense_160^4_rank64']['opt_in_int8_slices'] = {
+                'ms_per_iteration': ms8, 'als_iters_per_sec': 1e3 / ms8, 'final_fit': fit8, 'fit_delta_vs_default': abs(fit8 - fit),
+                'speedup_vs_default': ms / ms8}
+        eng.release()
+        del eng
+    finally:
+        os.environ.pop('SKT_DENSE_I8', None)
+    del X
     torch.cuda.empty_cache()
     # ---- configs[2]
     X, gshape, nnz = device_shard_cfg3(torch, K, _parallel, sptensor, world, rank, 200000000)

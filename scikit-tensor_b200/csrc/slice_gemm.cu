@@ -216,6 +216,11 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// one lane polls the barrier, the warp follows (32 lanes polling one mbarrier cost ~5 % of a pass)
+__device__ __forceinline__ void mbar_wait_warp(bool elected, uint64_t *bar, uint32_t parity) {
+    if (elected) mbar_wait(bar, parity);
+    __syncwarp();
+}
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024 B, descriptor version 1, SWIZZLE_128B
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
@@ -262,7 +267,7 @@ struct SliceLoop {
     static __device__ __forceinline__ void run(const bool elected, const uint32_t tacc, unsigned char *sA, uint64_t *full,
                                                uint64_t *empty, const uint32_t b_lo_chunk, const int nks, const bool first_chunk,
                                                int &st, uint32_t &ph, const int NS) {
-        mbar_wait(&full[st], ph);
+        mbar_wait_warp(elected, &full[st], ph);
         tc_fence_after();
         const uint32_t a_lo = desc_lo(smem_u32(sA + (size_t)st * STAGE_BYTES));
         constexpr uint32_t A_STEP16 = (A_MN ? 32 * 128 : 32) >> 4;   // K-major: 32 bytes along the rows; MN-major: 32 rows on
@@ -346,7 +351,7 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
             for (int c = c0; c < c1; ++c) {
                 if (!BRES) {
-                    if (bwrapped) mbar_wait(&bempty[bs], bph ^ 1u);
+                    if (bwrapped) mbar_wait_warp(elected, &bempty[bs], bph ^ 1u);
                     if (elected) {
                         mbar_arrive_expect_tx(&bfull[bs], (uint32_t)(S * BT));
 #pragma unroll
@@ -361,7 +366,7 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
 #pragma unroll
                 for (int i = S - 1; i >= 0; --i) {
-                    if (wrapped) mbar_wait(&empty[st], ph ^ 1u);
+                    if (wrapped) mbar_wait_warp(elected, &empty[st], ph ^ 1u);
                     if (elected) {
                         mbar_arrive_expect_tx(&full[st], STAGE_BYTES);
                         if (A_MN)
@@ -382,16 +387,16 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool elected = elect_one();
         int st = 0, bs = 0;
         uint32_t ph = 0, bph = 0, lu = 0;
-        if (BRES) mbar_wait(&bfull[0], 0);
+        if (BRES) mbar_wait_warp(elected, &bfull[0], 0);
         for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++lu) {
             const int tile = u / p.nseg, g = u - tile * p.nseg;
             const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
             const uint32_t set = lu % NSETS, use = lu / NSETS;
-            if (use >= 1) mbar_wait(&tempty[set], (use - 1) & 1u);
+            if (use >= 1) mbar_wait_warp(elected, &tempty[set], (use - 1) & 1u);
             tc_fence_after();
             const uint32_t tacc = tmem + set * (uint32_t)ACC_COLS;
             for (int c = c0; c < c1; ++c) {
-                if (!BRES) mbar_wait(&bfull[bs], bph);
+                if (!BRES) mbar_wait_warp(elected, &bfull[bs], bph);
                 const int valid = min(KC, p.Kc - c * KC);
                 const int nks = (valid + 31) >> 5;                     // the zero-filled tail of the last chunk is skipped
                 const uint32_t b_lo_chunk = desc_lo(smem_u32(sB + (size_t)(BRES ? c : bs) * S * BT));

@@ -12,4 +12,6 @@ import json
 d=json.loads([l for l in open('gpurun_out/j_bench_n$N.json') if l.startswith('{')][-1])
 print('N', d['n_gpus'], 'value', d['value'], 'ms', d['ms_per_step'], 'e2e it/s', d['e2e']['als_iters_per_sec'], d['e2e']['runs_s'])
 print(d.get('strong_scaling')); print(d.get('extras_error'))
+o=d.get('opt_in_int8_slices') or {}
+print('opt-in int8 slices:', {k: o.get(k) for k in ('ms_per_step', 'als_iters_per_sec', 'speedup_vs_default', 'fit_delta_vs_default', 'e2e_als_iters_per_sec', 'error')})
 PY
