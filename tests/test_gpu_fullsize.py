@@ -49,10 +49,24 @@ def test_cfg2_full_size_vs_oracle(K, dev):
     U = [rng.rand(512, 32) for _ in range(3)]
     Xd = dev.to_device(X)
     Ud = [dev.to_device(u) for u in U]
+    refs = []
     for n in range(3):
         got = dev.to_host(K.mttkrp_dense(Xd, X.shape, Ud, 32, n))
-        ref = orc.mttkrp_dense(X, U, n)
-        assert relerr(got, ref) < TOL, n
+        refs.append(orc.mttkrp_dense(X, U, n))
+        assert relerr(got, refs[n]) < TOL, n
+    # the opt-in sliced passes (INT8 tensor cores, csrc/slice_gemm.cu) through the same dimension tree, same tolerance
+    for S in (6, 5):
+        P = K.PlanesHandle(Xd, X.shape, S)
+        TA = P.ttm(2, Ud[2], 32)
+        T2 = P.ttm(0, Ud[0], 32)
+        got = [K.kr_reduce(TA, (512, 512), [Ud[0], Ud[1]], 32, 0), K.kr_reduce(TA, (512, 512), [Ud[0], Ud[1]], 32, 1),
+               K.kr_reduce(T2, (512, 512), [Ud[1], Ud[2]], 32, 1)]
+        for n in range(3):
+            assert relerr(dev.to_host(got[n]), refs[n]) < TOL, (S, n)
+        TB = P.tree_pass(2, 1, Ud, 32)                           # the general route: X^T KR(U_0, U_1), K = 512^2, split-K
+        assert relerr(dev.to_host(TB), refs[2]) < TOL, S
+        P.close()
+        del TA, T2, TB, got
     del Xd
     _free(dev)
 
@@ -168,7 +182,16 @@ def test_cfg5_full_size(K, dev):
         Mn = K.mttkrp_dense(Xd, shape, Ud, 64, n, naive=True)
         got.append(dev.to_host(M))
         assert relerr(got[n], dev.to_host(Mn)) < TOL, n
-    del Xd, M, Mn
+    # the opt-in sliced tree passes at rank 64: X as [160^2 x 160^2] against the Khatri-Rao factor planes, then the second stage
+    P8 = K.PlanesHandle(Xd, shape, 6)
+    TA = P8.tree_pass(2, 0, Ud, 64)
+    TB = P8.tree_pass(2, 1, Ud, 64)
+    sl = [K.kr_reduce(TA, (160, 160), Ud[:2], 64, 0), K.kr_reduce(TA, (160, 160), Ud[:2], 64, 1),
+          K.kr_reduce(TB, (160, 160), Ud[2:], 64, 0), K.kr_reduce(TB, (160, 160), Ud[2:], 64, 1)]
+    for n in range(4):
+        assert relerr(dev.to_host(sl[n]), got[n]) < TOL, n
+    P8.close()
+    del Xd, M, Mn, TA, TB, sl, P8
     _free(dev)
     ref1 = orc.mttkrp_dense(X, U, 1)                         # one mode against the oracle (25 s of host time)
     assert relerr(got[1], ref1) < TOL
@@ -195,3 +218,14 @@ def test_cfg5_full_size(K, dev):
     assert relerr(np.asarray(P.lmbda), lam) < 1e-7
     for m in range(4):
         assert relerr(np.asarray(P.U[m]), Uo[m]) < 1e-7, m
+    # and the same call with the sliced passes switched on
+    import os
+    os.environ['SKT_DENSE_I8'] = '6'
+    try:
+        np.random.seed(1)
+        P8, fit8, itr8, _ = cp_als(dtensor(X), 64, init='random', max_iter=2, conv=0)
+    finally:
+        os.environ.pop('SKT_DENSE_I8', None)
+    assert itr8 == 1 and abs(float(fit8) - fit_o) < 1e-6
+    for m in range(4):
+        assert relerr(np.asarray(P8.U[m]), Uo[m]) < 1e-7, m
