@@ -49,7 +49,7 @@ constexpr int MAXS = 6;
 constexpr int MAXK = 512;
 constexpr int STAGE_BYTES = TM * KC;
 constexpr int BTILE_BYTES = NB * KC;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 224;        // 7 warps: A producer, MMA issuer, 4 epilogue warps, factor-plane producer
 
 constexpr int MAXACC = 7;               // accumulators (pair sums smin .. 2(S-1)) per set; two sets of 224 columns
 
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(128) factor_slice_kernel(const double *__restr
 // (16384 products per INT32 accumulator) and the segments of one tile are summed in order from FP64 slabs.  The factor
 // planes are either resident in shared memory (BRES: short contractions, loaded once per CTA) or travel chunk by chunk
 // through a two-slot ring beside the A ring.
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (owns the tensor memory), warps 2..5 = epilogue (one TMEM lane quarter
-// each).  Warps 0 and 1 run their loops with all 32 lanes and issue through elect.sync: every descriptor is then
+// Roles: warp 0 = TMA producer of the A ring, warp 6 = TMA producer of the factor planes, warp 1 = MMA issuer (owns the
+// tensor memory), warps 2..5 = epilogue (one TMEM lane quarter each).  Warps 0 and 1 run their loops with all 32 lanes and issue through elect.sync: every descriptor is then
 // warp-uniform by construction and lives in uniform registers (with a single-lane `if (lane == 0)` loop the compiler wraps
 // each UTCIMMA in an election loop and ~35 uniform-datapath instructions, which made the issue thread the bottleneck of
 // the rank-64 passes: 1.57 ms per 160^4 pass against 0.9 after this change).
@@ -334,36 +334,15 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int nunits = p.tiles * p.nseg;
 
     if (warp == 0) {
+        // A ring: runs ahead of the MMAs as far as the ring allows, independent of the factor-plane slots
         const bool elected = elect_one();
-        if (BRES) {
-            if (elected) {
-                mbar_arrive_expect_tx(&bfull[0], (uint32_t)(p.nchunk * S * BT));
-                for (int c = 0; c < p.nchunk; ++c)
-                    for (int j = 0; j < S; ++j) tma_load_3d(sB + (size_t)(c * S + j) * BT, &tmB, &bfull[0], c * KC, 0, j);
-            }
-            __syncwarp();
-        }
-        int st = 0, bs = 0;
-        uint32_t ph = 0, bph = 0;
-        bool wrapped = false, bwrapped = false;
+        int st = 0;
+        uint32_t ph = 0;
+        bool wrapped = false;
         for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
             const int tile = u / p.nseg, g = u - tile * p.nseg;
             const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
             for (int c = c0; c < c1; ++c) {
-                if (!BRES) {
-                    if (bwrapped) mbar_wait_warp(elected, &bempty[bs], bph ^ 1u);
-                    if (elected) {
-                        mbar_arrive_expect_tx(&bfull[bs], (uint32_t)(S * BT));
-#pragma unroll
-                        for (int j = 0; j < S; ++j) tma_load_3d(sB + ((size_t)bs * S + j) * BT, &tmB, &bfull[bs], c * KC, 0, j);
-                    }
-                    __syncwarp();
-                    if (++bs == 2) {
-                        bs = 0;
-                        bph ^= 1u;
-                        bwrapped = true;
-                    }
-                }
 #pragma unroll
                 for (int i = S - 1; i >= 0; --i) {
                     if (wrapped) mbar_wait_warp(elected, &empty[st], ph ^ 1u);
@@ -379,6 +358,39 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         st = 0;
                         ph ^= 1u;
                         wrapped = true;
+                    }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // factor planes: once (resident) or one chunk per slot, two slots
+        const bool elected = elect_one();
+        if (BRES) {
+            if (elected) {
+                mbar_arrive_expect_tx(&bfull[0], (uint32_t)(p.nchunk * S * BT));
+                for (int c = 0; c < p.nchunk; ++c)
+                    for (int j = 0; j < S; ++j) tma_load_3d(sB + (size_t)(c * S + j) * BT, &tmB, &bfull[0], c * KC, 0, j);
+            }
+            __syncwarp();
+        } else {
+            int bs = 0;
+            uint32_t bph = 0;
+            bool bwrapped = false;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                const int tile = u / p.nseg, g = u - tile * p.nseg;
+                const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
+                for (int c = c0; c < c1; ++c) {
+                    if (bwrapped) mbar_wait_warp(elected, &bempty[bs], bph ^ 1u);
+                    if (elected) {
+                        mbar_arrive_expect_tx(&bfull[bs], (uint32_t)(S * BT));
+#pragma unroll
+                        for (int j = 0; j < S; ++j) tma_load_3d(sB + ((size_t)bs * S + j) * BT, &tmB, &bfull[bs], c * KC, 0, j);
+                    }
+                    __syncwarp();
+                    if (++bs == 2) {
+                        bs = 0;
+                        bph ^= 1u;
+                        bwrapped = true;
                     }
                 }
             }
@@ -413,7 +425,7 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (elected) umma_commit(&tfull[set]);
             __syncwarp();
         }
-    } else {
+    } else if (warp < 6) {
         const int q = warp & 3;                                    // the TMEM lane quarter this warp may read
         constexpr int NACC = 2 * (S - 1) - SMIN + 1;
         uint32_t lu = 0;
