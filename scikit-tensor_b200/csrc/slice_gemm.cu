@@ -37,6 +37,7 @@ struct skt_planes {
     double *scale;              // device: [0] = 2^e, [1] = 2^-e (NaN when max|X| is not finite)
     unsigned long long *amax;   // device: bits of max|X|
     int device;
+    cudaStream_t stream;        // the planes come from the stream-ordered pool of this stream's device
 };
 
 namespace skt {
@@ -767,9 +768,20 @@ int skt_planes_create(const double *X_d, const int64_t *shape, int ndim, int nsl
     P->planes = nullptr;
     P->scale = nullptr;
     P->amax = nullptr;
-    cudaError_t e = cudaMalloc((void **)&P->planes, (size_t)nslices * total);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&P->scale, 256);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&P->amax, 256);
+    // stream-ordered pool: a second cp_als call on the same stream gets the block of the first one back without a
+    // cudaMalloc (1.5 .. 35 ms for 0.8 GB); the pool keeps up to 8 GB instead of returning them to the driver at once
+    P->stream = st;
+    static unsigned long long pool_mask = 0;
+    if (first_use_on_device(pool_mask)) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = 8ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    cudaError_t e = cudaMallocAsync((void **)&P->planes, (size_t)nslices * total, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&P->scale, 256, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&P->amax, 256, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(P->amax, 0, 8, st);
     if (e != cudaSuccess) {
         skt_planes_destroy(P);
@@ -793,9 +805,9 @@ int skt_planes_create(const double *X_d, const int64_t *shape, int ndim, int nsl
 
 int skt_planes_destroy(skt_planes *P) {
     if (!P) return SKT_OK;
-    if (P->planes) cudaFree(P->planes);
-    if (P->scale) cudaFree(P->scale);
-    if (P->amax) cudaFree(P->amax);
+    if (P->planes) cudaFreeAsync(P->planes, P->stream);
+    if (P->scale) cudaFreeAsync(P->scale, P->stream);
+    if (P->amax) cudaFreeAsync(P->amax, P->stream);
     delete P;
     return SKT_OK;
 }
