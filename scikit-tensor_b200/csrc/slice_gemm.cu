@@ -1,22 +1,25 @@
-// Opt-in: the two partial contractions of the 3-way dimension tree on the INT8 tensor cores (tcgen05.mma.kind::i8, TMEM
+// Opt-in: the partial contractions of the dense dimension tree on the INT8 tensor cores (tcgen05.mma.kind::i8, TMEM
 // accumulators, TMA), FP64-accurate by error-free slicing.  The default dense path stays the FP64 DMMA kernel of
-// mttkrp_dense.cu; this one exists because at rank <= 32 that kernel is bound by the 37 TFLOP/s of the FP64 tensor pipe
+// mttkrp_dense.cu; this one exists because at rank 32 / 64 that kernel is bound by the 37 TFLOP/s of the FP64 tensor pipe
 // (0.28 ms per 512^3 pass) while HBM would allow 0.16 ms.  Prototype and measurements: tools/slice_gemm_probe.cu.
 //
-//   T[row, r] = sum_c X[.., c, ..] U[c, r]     c = the LAST mode (rows = the other modes in memory order; K-major A operand)
-//                                              or the FIRST mode (MN-major A operand)
-//   replaces skt_mttkrp_dense on the 2-way views of sktensor/_parallel.py (`_tree_pass`), i.e. the unfolded product the
-//   reference forms with khatrirao + dot (sktensor/dtensor.py:117-137).
+//   skt_planes_ttm:   T[row, r] = sum_c X[.., c, ..] U[c, r]   c = the LAST mode (K-major A operand; rows = the other modes in
+//                     memory order) or the FIRST mode (MN-major A operand); rank <= 32, contracted mode <= 512
+//   skt_planes_pass:  X as the matrix [P x Q]:  T = X KR(U_s..)  or  X^T KR(U_0..U_{s-1})  against the Khatri-Rao product of a
+//                     tree group's factors; rank <= 64, any length
+//   Both replace skt_mttkrp_dense on the 2-way views of sktensor/_parallel.py (`_tree_pass`), i.e. the unfolded product the
+//   reference forms with khatrirao + dot (sktensor/dtensor.py:117-137, core.py:333-378).
 //
 // Numbers.  v = rint(x * 2^e) is an S-byte two's-complement integer (S = 6: 48 bits, or 5: 40 bits; 2^e is one scale for
 // the whole tensor, one per column for the factor).  With 0x80 added to every lower byte its bytes, XOR 0x80, are BALANCED
 // digits d_s in [-128, 127], v = sum_s d_s 256^s: one DFMA with the constant 1.5 * 2^52 + 0x80..80 puts them in the low
 // mantissa bits, byte permutes move them into S planes.  X is sliced ONCE (it does not change during an ALS run), so a
 // pass streams S bytes per element instead of 8.  A slice product sum_c a_i[row, c] b_j[c, r] is an exact INT32 dot
-// product (128 * 128 * K * 6 pairs < 2^31 for K <= 512); all B slices j >= smin - i that pair with one A slice lie one after
-// the other in shared memory and feed the consecutive accumulators i + j, so ONE MMA of N = 32 (S - j0) columns covers
-// them.  Pairs with i + j < smin (S = 6: 4, S = 5: 2; at most 2^-52 of full scale) are skipped.  The epilogue recombines
-// the accumulators in FP64 (Horner in powers of 256) and applies the exact power-of-two scales.
+// product (128 * 128 * 6 pairs * 16384 products < 2^31; longer contractions are cut into segments); all B slices
+// j >= smin - i that pair with one A slice lie one after the other in shared memory and feed the consecutive accumulators
+// i + j, so ONE MMA of N = 32 (S - j0) columns (64 (S - j0) above rank 32, split at 256) covers them.  Pairs with
+// i + j < smin (S = 6: 4, S = 5: 2; at most 2^-52 of full scale) are skipped.  The epilogue recombines the accumulators in
+// FP64 (Horner in powers of 256) and applies the exact power-of-two scales.
 // Error: |dT| <= 2^-(8S-1) max|X| sum_c |U[c, r]| + the same with the roles swapped (normwise 1e-14 .. 1e-13 for S = 6 on
 // uniform / normal data, see tests/test_gpu_slices.py); non-finite input poisons the output with NaN.
 #include <cuda.h>
@@ -47,9 +50,8 @@ constexpr int NB = 32;                  // columns per slice (rank padded with z
 constexpr int TM = 128;                 // rows per tile = TMEM lanes
 constexpr int KC = 128;                 // contraction bytes per stage
 constexpr int MAXS = 6;
-constexpr int MAXK = 512;
+constexpr int MAXK = 512;               // skt_planes_ttm: the factor planes stay resident in shared memory
 constexpr int STAGE_BYTES = TM * KC;
-constexpr int BTILE_BYTES = NB * KC;
 constexpr int GEMM_THREADS = 224;        // 7 warps: A producer, MMA issuer, 4 epilogue warps, factor-plane producer
 
 constexpr int MAXACC = 7;               // accumulators (pair sums smin .. 2(S-1)) per set; two sets of 224 columns
