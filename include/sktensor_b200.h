@@ -263,6 +263,14 @@ SKT_API int    skt_planes_nslices(const skt_planes *p);
 SKT_API size_t skt_planes_ttm_workspace(const skt_planes *p, int mode, int rank);
 SKT_API int    skt_planes_ttm(const skt_planes *p, int mode, const double *U_d, int rank, double *T_d, void *ws_d,
                       size_t ws_bytes, skt_stream stream);
+/* 3-way tensors, mode = 0: skt_planes_ttm with the second stage of the dimension tree folded into its epilogue.  W_d = the
+ * factor of the MIDDLE mode (shape[1] x rank).  Writes slabs of M_2[k,r] = sum_j (sum_i X[i,j,k] U[i,r]) W[j,r]; T_d is not
+ * written (may be NULL).  The MTTKRP is the SUM of the slabs (skt_planes_fused_slabs slabs of *slab_rows x rank, contiguous),
+ * the form skt_cp_update_cluster_slabs consumes.  Needs shape[2] to be a multiple of 128; skt_planes_fused_slabs returns 0
+ * when the shape or the mode is not supported.                                                                        */
+SKT_API int    skt_planes_fused_slabs(const skt_planes *p, int mode, int rank, int64_t *slab_rows);
+SKT_API int    skt_planes_ttm_fused(const skt_planes *p, int mode, const double *U_d, const double *W_d, int rank, double *T_d,
+                            double *slabs_d, size_t slabs_bytes, void *ws_d, size_t ws_bytes, skt_stream stream);
 /* General tree pass on the same planes: X seen as the matrix [P x Q], P = prod(shape[:split]), Q = prod(shape[split:]).
  * group 0: T_d[P x rank] = X KR(U_split .. U_{ndim-1});  group 1: T_d[Q x rank] = X^T KR(U_0 .. U_{split-1}), KR = the
  * Khatri-Rao product of the group's factors in X's memory order (the khatrirao + dot of dtensor.uttkrp, dtensor.py:117-137

@@ -206,6 +206,36 @@ struct GemmParams {
     double *T;           // rows x R (nseg == 1) ...
     double *slabs;       // ... or nseg slabs of rows x R
     const double *inv;   // per column
+    // fused second stage (EMODE 2, 3-way tensors): weights W[J x R] of the middle mode, slabs of the finished MTTKRP
+    const double *W;
+    double *aux;
+    int J;               // rows of W
+    int arows;           // rows of one aux slab
+    int nj, jper, kt;    // EMODE 2: CTAs per 128-row block of the last mode, middle indices per CTA, blocks per fibre
+};
+
+// Work of one CTA.  EMODE 0: units (row tile, K segment) round-robin over the grid.  EMODE 2 (first-mode contraction with
+// the middle mode folded in): CTA = (128-row block kb of the last mode, range of middle indices j); its units are the tiles
+// (j, kb), j ascending, whole contraction each.
+template <int EMODE>
+struct Units {
+    int beg, end, step, kb;
+    __device__ __forceinline__ Units(const GemmParams &p) {
+        if (EMODE == 2) {
+            kb = blockIdx.x / p.nj;
+            const int jr = blockIdx.x - kb * p.nj;
+            beg = jr * p.jper;
+            end = min(p.J, beg + p.jper);
+            step = 1;
+        } else {
+            kb = 0;
+            beg = blockIdx.x;
+            end = p.tiles * p.nseg;
+            step = gridDim.x;
+        }
+    }
+    __device__ __forceinline__ int tile(int u, const GemmParams &p) const { return EMODE == 2 ? u * p.kt + kb : u / p.nseg; }
+    __device__ __forceinline__ int seg(int u, const GemmParams &p) const { return EMODE == 2 ? 0 : u - (u / p.nseg) * p.nseg; }
 };
 
 __device__ __forceinline__ bool elect_one() {
@@ -294,7 +324,7 @@ struct SliceLoop<A_MN, NBW, S, -1> {
                                                uint32_t &, int) {}
 };
 
-template <bool A_MN, int NBW, int S, bool BRES>
+template <bool A_MN, int NBW, int S, bool BRES, int EMODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -334,7 +364,7 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int nunits = p.tiles * p.nseg;
+    const Units<EMODE> un(p);
 
     if (warp == 0) {
         // A ring: runs ahead of the MMAs as far as the ring allows, independent of the factor-plane slots
@@ -342,8 +372,8 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int st = 0;
         uint32_t ph = 0;
         bool wrapped = false;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-            const int tile = u / p.nseg, g = u - tile * p.nseg;
+        for (int u = un.beg; u < un.end; u += un.step) {
+            const int tile = un.tile(u, p), g = un.seg(u, p);
             const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
             for (int c = c0; c < c1; ++c) {
 #pragma unroll
@@ -379,8 +409,8 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int bs = 0;
             uint32_t bph = 0;
             bool bwrapped = false;
-            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-                const int tile = u / p.nseg, g = u - tile * p.nseg;
+            for (int u = un.beg; u < un.end; u += un.step) {
+                const int g = un.seg(u, p);
                 const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
                 for (int c = c0; c < c1; ++c) {
                     if (bwrapped) mbar_wait_warp(elected, &bempty[bs], bph ^ 1u);
@@ -403,8 +433,8 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int st = 0, bs = 0;
         uint32_t ph = 0, bph = 0, lu = 0;
         if (BRES) mbar_wait_warp(elected, &bfull[0], 0);
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++lu) {
-            const int tile = u / p.nseg, g = u - tile * p.nseg;
+        for (int u = un.beg; u < un.end; u += un.step, ++lu) {
+            const int g = un.seg(u, p);
             const int c0 = g * p.cps, c1 = min(p.nchunk, c0 + p.cps);
             const uint32_t set = lu % NSETS, use = lu / NSETS;
             if (use >= 1) mbar_wait_warp(elected, &tempty[set], (use - 1) & 1u);
@@ -432,12 +462,15 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp & 3;                                    // the TMEM lane quarter this warp may read
         constexpr int NACC = 2 * (S - 1) - SMIN + 1;
         uint32_t lu = 0;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++lu) {
-            const int tile = u / p.nseg, g = u - tile * p.nseg;
+        double wacc[EMODE == 2 ? 32 : 1];                          // EMODE 2: running sum over the CTA's middle indices
+#pragma unroll
+        for (int n = 0; n < (EMODE == 2 ? 32 : 1); ++n) wacc[n] = 0.0;
+        for (int u = un.beg; u < un.end; u += un.step, ++lu) {
+            const int tile = un.tile(u, p), g = un.seg(u, p);
             const uint32_t set = lu % NSETS, use = lu / NSETS;
+            const long long row = (long long)tile * TM + q * 32 + lane;
             mbar_wait(&tfull[set], use & 1u);
             tc_fence_after();
-            const long long row = (long long)tile * TM + q * 32 + lane;
             double *out = (p.nseg == 1 ? p.T : p.slabs + (size_t)g * p.rows * p.R) + row * p.R;
 #pragma unroll 1
             for (int h = 0; h < NBW / 32; ++h) {
@@ -462,7 +495,13 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int n = 0; n < 32; ++n) r[n] = fma(r[n], 256.0, (double)(int)v[n]);
                 }
-                if (row < p.rows) {
+                if (EMODE == 2) {
+                    // M_last[k, r] += T[(j, k), r] U_mid[j, r]: the tile's rows are 128 consecutive k of fibre j = u
+                    const double *w = p.W + (size_t)u * p.R;
+#pragma unroll
+                    for (int n = 0; n < 32; ++n)
+                        if (n < p.R) wacc[n] = fma(r[n] * p.inv[n], __ldg(w + n), wacc[n]);
+                } else if (row < p.rows) {
                     if (p.R == NBW) {
 #pragma unroll
                         for (int n = 0; n < 32; n += 2) {
@@ -481,6 +520,13 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[set]);
+        }
+        if (EMODE == 2) {
+            const int jr = blockIdx.x - un.kb * p.nj;
+            double *dst = p.aux + ((size_t)jr * p.arows + (size_t)un.kb * TM + q * 32 + lane) * p.R;
+#pragma unroll
+            for (int n = 0; n < 32; ++n)
+                if (n < p.R) dst[n] = wacc[n];
         }
     }
     tc_fence_before();
@@ -698,8 +744,8 @@ PassWs pass_ws(const PassPlan &pl, int S, int R) {
 
 constexpr size_t BRES_BYTES = 98304;        // factor planes up to this size stay resident in shared memory
 
-template <bool A_MN, int NBW, int S, bool BRES>
-int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams &gp, cudaStream_t st) {
+template <bool A_MN, int NBW, int S, bool BRES, int EMODE>
+int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams &gp, int grid, cudaStream_t st) {
     const size_t bbytes = (size_t)(BRES ? gp.nchunk : 2) * S * NBW * KC;
     const size_t fixed = 1024 + bbytes + 512;                       // alignment slack, factor tiles, barriers
     const size_t cap = smem_optin_bytes();
@@ -708,9 +754,10 @@ int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams &gp, 
     const size_t smem = fixed + (size_t)gp.NS * STAGE_BYTES;
     static unsigned long long mask = 0;
     if (first_use_on_device(mask))
-        SKT_CUDA(cudaFuncSetAttribute(slice_gemm_kernel<A_MN, NBW, S, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-    const int grid = std::min(gp.tiles * gp.nseg, sm_count());
-    slice_gemm_kernel<A_MN, NBW, S, BRES><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, gp);
+        SKT_CUDA(cudaFuncSetAttribute(slice_gemm_kernel<A_MN, NBW, S, BRES, EMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)cap));
+    if (grid <= 0) grid = std::min(gp.tiles * gp.nseg, sm_count());
+    slice_gemm_kernel<A_MN, NBW, S, BRES, EMODE><<<grid, GEMM_THREADS, smem, st>>>(tmA, tmB, gp);
     SKT_LAUNCH_CHECK();
     return SKT_OK;
 }
@@ -718,8 +765,9 @@ int launch_gemm(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams &gp, 
 template <bool A_MN, int NBW>
 int launch_gemm_s(const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams &gp, int S, cudaStream_t st) {
     const bool bres = (size_t)gp.nchunk * S * NBW * KC <= BRES_BYTES;
-    if (S == 6) return bres ? launch_gemm<A_MN, NBW, 6, true>(tmA, tmB, gp, st) : launch_gemm<A_MN, NBW, 6, false>(tmA, tmB, gp, st);
-    return bres ? launch_gemm<A_MN, NBW, 5, true>(tmA, tmB, gp, st) : launch_gemm<A_MN, NBW, 5, false>(tmA, tmB, gp, st);
+    if (S == 6)
+        return bres ? launch_gemm<A_MN, NBW, 6, true, 0>(tmA, tmB, gp, 0, st) : launch_gemm<A_MN, NBW, 6, false, 0>(tmA, tmB, gp, 0, st);
+    return bres ? launch_gemm<A_MN, NBW, 5, true, 0>(tmA, tmB, gp, 0, st) : launch_gemm<A_MN, NBW, 5, false, 0>(tmA, tmB, gp, 0, st);
 }
 
 int launch_gemm_any(bool a_mn, int nb, const CUtensorMap &tmA, const CUtensorMap &tmB, GemmParams &gp, int S, cudaStream_t st) {
@@ -861,7 +909,88 @@ int skt_planes_ttm(const skt_planes *P, int mode, const double *U_d, int rank, d
     gp.T = T_d;
     gp.slabs = nullptr;
     gp.inv = inv;
+    gp.W = nullptr;
+    gp.aux = nullptr;
+    gp.J = gp.arows = gp.nj = gp.jper = gp.kt = 0;
     return launch_gemm_any(pl.a_mn, NB, tmA, tmB, gp, S, st);
+}
+
+// ---- 3-way tensors: the second stage of the last mode folded into the epilogue of the first-mode contraction ------------
+// slabs of M_2[k, r] = sum_j (sum_i X[i, j, k] U[i, r]) W[j, r]; the partial tensor T[(j, k), r] is never written.  One slab of
+// shape[2] x rank per CTA range of j; W = the factor of the middle mode.  The slabs are what skt_cp_update_cluster_slabs sums
+// while it stages M.  (The same for mode 0 inside the last-mode contraction -- a cross-row reduction by warp shuffles in the
+// epilogue -- was measured at +0.06 ms per 512^3 pass against 0.023 ms for the separate reduction kernel and dropped.)
+static int fused_plan(const skt_planes *P, int mode, int rank, TtmPlan &pl, int &nslabs, long long &arows, int &nj, int &jper) {
+    const int rc = plan_ttm(P, mode, rank, pl);
+    if (rc) return rc;
+    SKT_REQUIRE(P->ndim == 3 && mode == 0, SKT_EUNSUPPORTED, "the fused second stage is the first-mode contraction of a 3-way tensor");
+    SKT_REQUIRE(P->shape[2] % TM == 0, SKT_EUNSUPPORTED, "the fused second stage needs the last mode to be a multiple of 128");
+    const long long J = P->shape[1];
+    const int nkb = (int)(P->shape[2] / TM);
+    nj = (int)std::max<long long>(1, std::min<long long>(J, sm_count() / nkb));
+    jper = (int)((J + nj - 1) / nj);
+    nj = (int)((J + jper - 1) / jper);
+    nslabs = nj;
+    arows = P->shape[2];
+    return SKT_OK;
+}
+
+int skt_planes_fused_slabs(const skt_planes *P, int mode, int rank, int64_t *slab_rows) {
+    TtmPlan pl;
+    int nslabs = 0, nj, jper;
+    long long arows = 0;
+    if (fused_plan(P, mode, rank, pl, nslabs, arows, nj, jper) != SKT_OK) return 0;
+    if (slab_rows) *slab_rows = arows;
+    return nslabs;
+}
+
+int skt_planes_ttm_fused(const skt_planes *P, int mode, const double *U_d, const double *W_d, int rank, double *T_d,
+                         double *slabs_d, size_t slabs_bytes, void *ws_d, size_t ws_bytes, skt_stream stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    TtmPlan pl;
+    int nslabs = 0, nj = 0, jper = 0;
+    long long arows = 0;
+    const int rc = fused_plan(P, mode, rank, pl, nslabs, arows, nj, jper);
+    if (rc) return rc;
+    SKT_REQUIRE(U_d && W_d && slabs_d, SKT_EINVAL, "null argument");
+    SKT_REQUIRE(slabs_bytes >= (size_t)nslabs * arows * rank * sizeof(double), SKT_EWORKSPACE, "slab buffer too small");
+    const int S = P->S;
+    const size_t need = ttm_ws(pl, S);
+    SKT_REQUIRE(ws_d && ws_bytes >= need, SKT_EWORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+    SKT_REQUIRE((((uintptr_t)ws_d) & 255) == 0 && (((uintptr_t)T_d) & 15) == 0, SKT_EINVAL, "misaligned workspace or output");
+    unsigned char *Bp = (unsigned char *)ws_d;
+    double *inv = (double *)(Bp + align_up((size_t)S * NB * pl.kpad, 256));
+    factor_slice_kernel<<<NB, 128, 0, st>>>(U_d, pl.Kc, rank, pl.kpad, S, smin_of(S), P->scale, (uint32_t *)Bp, inv);
+    SKT_LAUNCH_CHECK();
+    CUtensorMap tmA, tmB;
+    int e;
+    if (pl.a_mn)
+        e = byte_map3(P->planes, (uint64_t)pl.rows, (uint64_t)pl.Kc, (uint64_t)S, (uint64_t)pl.rows, (uint64_t)P->total, KC, tmA);
+    else
+        e = byte_map3(P->planes, (uint64_t)pl.Kc, (uint64_t)pl.rows, (uint64_t)S, (uint64_t)pl.Kc, (uint64_t)P->total, TM, tmA);
+    if (e) return e;
+    e = byte_map3(Bp, (uint64_t)pl.kpad, NB, (uint64_t)S, (uint64_t)pl.kpad, (uint64_t)NB * pl.kpad, NB, tmB);
+    if (e) return e;
+    GemmParams gp;
+    gp.rows = pl.rows;
+    gp.tiles = (int)((pl.rows + TM - 1) / TM);
+    gp.nchunk = pl.nchunk;
+    gp.nseg = 1;
+    gp.cps = pl.nchunk;
+    gp.Kc = pl.Kc;
+    gp.R = rank;
+    gp.T = T_d;
+    gp.slabs = nullptr;
+    gp.inv = inv;
+    gp.W = W_d;
+    gp.aux = slabs_d;
+    gp.J = (int)P->shape[1];
+    gp.arows = (int)arows;
+    gp.nj = nj;
+    gp.jper = jper;
+    gp.kt = (int)(P->shape[2] / TM);
+    const int grid = gp.kt * nj;
+    return S == 6 ? launch_gemm<true, 32, 6, true, 2>(tmA, tmB, gp, grid, st) : launch_gemm<true, 32, 5, true, 2>(tmA, tmB, gp, grid, st);
 }
 
 int skt_planes_pass_supported(const int64_t *shape, int ndim, int split, int rank) {
@@ -932,6 +1061,9 @@ int skt_planes_pass(const skt_planes *P, int split, int group, const double *con
     gp.T = T_d;
     gp.slabs = slabs;
     gp.inv = inv;
+    gp.W = nullptr;
+    gp.aux = nullptr;
+    gp.J = gp.arows = gp.nj = gp.jper = gp.kt = 0;
     e = launch_gemm_any(pl.a_mn, pl.nb, tmA, tmB, gp, S, st);
     if (e) return e;
     if (pl.nseg > 1) {

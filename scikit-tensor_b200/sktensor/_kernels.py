@@ -178,6 +178,21 @@ class PlanesHandle(object):
         _lib.check(lib.skt_planes_ttm(self.h, mode, dev.ptr(U), rank, dev.ptr(out), ws, wsz, dev.stream_ptr()))
         return out
 
+    def fused_slabs(self, mode, rank):
+        """(number of slabs, rows per slab) of ``ttm_fused`` for this mode, or (0, 0) when the shape is not supported."""
+        rows = C.c_int64(0)
+        n = int(_lib.load().skt_planes_fused_slabs(self.h, int(mode), int(rank), C.byref(rows)))
+        return n, int(rows.value)
+
+    def ttm_fused(self, mode, U, W, rank, slabs, out=None):
+        """``ttm`` of a 3-way tensor with the tree's second stage folded in: ``slabs`` receives partial sums of the
+        finished MTTKRP (mode 0 for ``mode = 2``, mode 2 for ``mode = 0``), ``W`` is the middle mode's factor."""
+        lib = _lib.load()
+        ws, wsz = dev.workspace('mttkrp').get(lib.skt_planes_ttm_workspace(self.h, mode, rank))
+        _lib.check(lib.skt_planes_ttm_fused(self.h, mode, dev.ptr(U), dev.ptr(W), rank, dev.ptr(out) if out is not None else None,
+                                            dev.ptr(slabs), slabs.numel() * slabs.element_size(), ws, wsz, dev.stream_ptr()))
+        return out
+
     @staticmethod
     def pass_supported(shape, split, rank):
         shape = tuple(int(s) for s in shape)

@@ -101,6 +101,9 @@ PROTOTYPES = {
     'skt_planes_nslices': (C.c_int, [C.c_void_p]),
     'skt_planes_ttm_workspace': (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
     'skt_planes_ttm': (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, c_dp, C.c_void_p, C.c_size_t, c_stream]),
+    'skt_planes_fused_slabs': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
+    'skt_planes_ttm_fused': (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp, C.c_size_t, C.c_void_p, C.c_size_t,
+                                       c_stream]),
     'skt_planes_pass_supported': (C.c_int, [c_i64p, C.c_int, C.c_int, C.c_int]),
     'skt_planes_pass_workspace': (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     'skt_planes_pass': (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_voidpp, C.c_int, c_dp, C.c_void_p, C.c_size_t, c_stream]),

@@ -147,6 +147,8 @@ class CudaBackend(object):
     def planes_supported(self, shape, mode, R): return self.K.PlanesHandle.supported(shape, mode, R)
     def planes_create(self, Xd, shape, nslices): return self.K.PlanesHandle(Xd, shape, nslices)
     def planes_ttm(self, planes, mode, U, R, out): return planes.ttm(mode, U, R, out=out)
+    def planes_fused_slabs(self, planes, mode, R): return planes.fused_slabs(mode, R)
+    def planes_ttm_fused(self, planes, mode, U, W, R, slabs, out): return planes.ttm_fused(mode, U, W, R, slabs, out=out)
     def planes_pass_supported(self, shape, split, R): return self.K.PlanesHandle.pass_supported(shape, split, R)
     def planes_pass(self, planes, split, group, U, R, out): return planes.tree_pass(split, group, U, R, out=out)
     def kr_reduce_slab_buffer(self, dims, R, n): return self.empty((max(1, self.K.kr_reduce_workspace(dims, R, n) // 8),))
@@ -476,6 +478,7 @@ class CpAlsEngine(object):
         self.slabbuf = [None] * N        # per mode: buffer for un-summed second-stage slabs (see below)
         self.i8 = None                   # byte planes of X for the opt-in sliced passes
         self.i8_general = False
+        self.i8_fused = [False] * N      # modes whose MTTKRP arrives as slabs from a fused sliced pass
         self.nslabs = [0] * N
         self.tree = (not self.sparse) and N >= 3 and hasattr(be, 'kr_reduce') and \
             os.environ.get('SKT_NO_DIMTREE', '0') != '1'
@@ -499,6 +502,15 @@ class CpAlsEngine(object):
                     self.i8 = be.planes_create(self.Xd, self.lshape, 5 if want == '5' else 6)
                     keep = self.lshape[1:] if s == N - 1 else self.lshape[:N - 1]
                     self.T2 = be.empty((int(np.prod(keep)), R))
+                    # single process: the second stage of the last mode rides in the epilogue of the first-mode contraction
+                    # and arrives as slabs that the cluster update sums while it stages M (no partial tensor, no kr_reduce)
+                    if s == N - 1 and not comm.active and hasattr(be, 'planes_ttm_fused') and \
+                            os.environ.get('SKT_I8_NO_FUSED', '0') != '1':
+                        ns, rows = be.planes_fused_slabs(self.i8, 0, R)
+                        if ns > 0 and self.cluster[N - 1] and rows == self.lshape[N - 1]:
+                            self.i8_fused[N - 1] = True
+                            self.slabbuf[N - 1] = be.empty((ns, rows, R))
+                            self.nslabs[N - 1] = ns
                 elif be.planes_pass_supported(self.lshape, s, R):
                     self.i8 = be.planes_create(self.Xd, self.lshape, 5 if want == '5' else 6)
                     self.i8_general = True
@@ -507,7 +519,7 @@ class CpAlsEngine(object):
             if not comm.active and hasattr(be, 'kr_reduce_slabs') and os.environ.get('SKT_NO_KR_SLABS', '0') != '1':
                 for m in range(N):
                     two_stage = (m < s and s > 1) or (m >= s and s < N - 1)
-                    if two_stage and self.cluster[m]:
+                    if two_stage and self.cluster[m] and not self.i8_fused[m]:
                         dims = self.lshape[:s] if m < s else self.lshape[s:]
                         self.slabbuf[m] = be.kr_reduce_slab_buffer(dims, R, m if m < s else m - s)
 
@@ -540,7 +552,9 @@ class CpAlsEngine(object):
             return
         if self.i8 is not None:
             R, Ud, ls = self.R, self.Ud, self.lshape
-            if group == 0 and s == N - 1:
+            if group == 1 and s == N - 1 and self.i8_fused[N - 1]:
+                be.planes_ttm_fused(self.i8, 0, Ud[0], Ud[1], R, self.slabbuf[N - 1], None)
+            elif group == 0 and s == N - 1:
                 be.planes_ttm(self.i8, N - 1, Ud[N - 1], R, self.TA)
             elif group == 0:                                    # s == 1: T_A = M_0
                 be.planes_ttm(self.i8, N - 1, Ud[N - 1], R, self.T2)
@@ -568,7 +582,9 @@ class CpAlsEngine(object):
                 self._tree_pass(0)
             elif n == s:
                 self._tree_pass(1)
-            if n < s and s > 1:
+            if self.i8_fused[n]:
+                pass                                            # the pass left the slabs of this mode
+            elif n < s and s > 1:
                 if self.slabbuf[n] is not None:
                     self.nslabs[n] = be.kr_reduce_slabs(self.TA, self.lshape[:s], self.Ud[:s], self.R, n, self.slabbuf[n])
                 else:

@@ -265,3 +265,57 @@ def test_cp_als_sliced_general_passes_match_fp64_engine(monkeypatch, shape, R):
     assert abs(fit1 - fit0) < 1e-9
     for a, b in zip(P1.U, P0.U):
         assert relerr(a, b) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the second stage folded into the epilogue (skt_planes_ttm_fused): slabs whose sum is the finished MTTKRP
+@pytest.mark.parametrize('shape,R', [((16, 128, 128), 4), ((40, 256, 384), 32), ((130, 128, 256), 7), ((512, 512, 128), 32)])
+@pytest.mark.parametrize('S', [6, 5])
+def test_planes_ttm_fused_slabs_sum_to_the_mttkrp(K, dev, shape, R, S):
+    rng = np.random.RandomState(sum(shape) + R + S)
+    X = rng.rand(*shape) - 0.3
+    U = [rng.rand(d, R) - 0.2 for d in shape]
+    Ud = [dev.to_device(u) for u in U]
+    P = K.PlanesHandle(dev.to_device(X), shape, S)
+    tol = 1e-12 if S == 6 else 1e-10
+    try:
+        assert P.fused_slabs(2, R) == (0, 0)                     # only the first-mode contraction has a fused form
+        # first-mode contraction: only slabs of the mode-2 MTTKRP
+        ns, rows = P.fused_slabs(0, R)
+        assert ns >= 1 and rows == shape[2]
+        slabs = dev.zeros((ns, rows, R)) + 7.0
+        P.ttm_fused(0, Ud[0], Ud[1], R, slabs)
+        M2 = np.einsum('ijk,ir,jr->kr', X, U[0], U[1])
+        assert relerr(dev.to_host(slabs).sum(axis=0), M2) < tol
+    finally:
+        P.close()
+
+
+def test_planes_fused_needs_multiples_of_128(K, dev):
+    shape = (32, 96, 160)
+    P = K.PlanesHandle(dev.to_device(np.ones(shape)), shape, 6)
+    try:
+        assert P.fused_slabs(2, 8) == (0, 0) and P.fused_slabs(0, 8) == (0, 0)
+    finally:
+        P.close()
+
+
+@pytest.mark.parametrize('shape,R', [((48, 128, 128), 8), ((128, 256, 128), 32)])
+def test_cp_als_sliced_fused_matches_unfused_and_fp64(monkeypatch, shape, R):
+    from sktensor import _parallel as par, dtensor
+    rng = np.random.RandomState(sum(shape))
+    X = rng.rand(*shape)
+    U0 = [rng.rand(d, R) for d in shape]
+    P0, fit0, itr0, _ = _cp(X, R, U0, max_iter=10, conv=0)
+    monkeypatch.setenv('SKT_DENSE_I8', '6')
+    eng = par.CpAlsEngine(dtensor(X), R, [u.copy() for u in U0])
+    try:
+        assert eng.i8 is not None and eng.i8_fused[2] and not eng.i8_fused[0]
+    finally:
+        eng.release()
+    P1, fit1, itr1, _ = _cp(X, R, U0, max_iter=10, conv=0)
+    monkeypatch.setenv('SKT_I8_NO_FUSED', '1')
+    P2, fit2, itr2, _ = _cp(X, R, U0, max_iter=10, conv=0)
+    assert abs(fit1 - fit0) < 1e-9 and abs(fit2 - fit0) < 1e-9
+    for a, b, c in zip(P1.U, P0.U, P2.U):
+        assert relerr(a, b) < 1e-8 and relerr(c, b) < 1e-8
