@@ -323,7 +323,11 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)          # let nvidia-smi come up so that samples exist from the warm-up on
-    for w in range(W):
+    # device / host pre-conditioning: the first process on a fresh box runs its first ~0.2 s of sweeps 5 % slower (power state,
+    # cold host path: 0.728 ms per step with 5 warm-up steps against 0.688 from the second process on, or with 300 warm-up
+    # steps).  The same count on every rank (the sweeps contain collectives); then the W warm-up steps the caller asked for.
+    PRE = max(0, int(os.environ.get('SKT_BENCH_PRECONDITION', '300')) - W)
+    for w in range(PRE + W):
         eng.sweep(first_iter=(w == 0))
         eng.begin_read()
         eng.prefetch_next_sweep()
@@ -443,7 +447,7 @@ def run_gpu(args):
             if eng2.i8 is not None:
                 plane_bytes = eng2.i8.device_bytes()
                 be2.record = True
-                ms2, fit2_ = timed_sweeps(torch, dist, world, eng2, args.steps, W)
+                ms2, fit2_ = timed_sweeps(torch, dist, world, eng2, args.steps, PRE + W)     # same iteration count as the default arm
                 be2.record = False
                 ev = be2.events[-2 * args.steps:]
                 pass_ms = {}
@@ -515,7 +519,8 @@ def run_gpu(args):
                        'algorithm': 'dimension tree: X is streamed twice per iteration (pass A = X x_2 U_2 serves the '
                                     'MTTKRPs of modes 0 and 1, pass B is the mode-2 MTTKRP); value counts the '
                                     "reference's three MTTKRPs per iteration as the algorithmic bytes",
-                       'cache': 'tensor slab 1.07 GB per GPU >> 126 MB L2: every pass streams it from HBM'},
+                       'cache': 'tensor slab 1.07 GB per GPU >> 126 MB L2: every pass streams it from HBM',
+                       'preconditioning_steps': PRE},
             'als_iters_per_sec': 1e3 / ms_step, 'final_fit': fit,
             'clocks': clocks, 'e2e': e2e_obj, 'gpu_launches': int(launches),
             'roofline': roofline, 'cpu_baseline': cpu_obj,
