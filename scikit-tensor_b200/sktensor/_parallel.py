@@ -500,8 +500,6 @@ class CpAlsEngine(object):
             if want not in ('', '0') and hasattr(be, 'planes_create'):
                 if N == 3 and be.planes_supported(self.lshape, 0, R) and be.planes_supported(self.lshape, N - 1, R):
                     self.i8 = be.planes_create(self.Xd, self.lshape, 5 if want == '5' else 6)
-                    keep = self.lshape[1:] if s == N - 1 else self.lshape[:N - 1]
-                    self.T2 = be.empty((int(np.prod(keep)), R))
                     # single process: the second stage of the last mode rides in the epilogue of the first-mode contraction
                     # and arrives as slabs that the cluster update sums while it stages M (no partial tensor, no kr_reduce)
                     if s == N - 1 and not comm.active and hasattr(be, 'planes_ttm_fused') and \
@@ -511,6 +509,9 @@ class CpAlsEngine(object):
                             self.i8_fused[N - 1] = True
                             self.slabbuf[N - 1] = be.empty((ns, rows, R))
                             self.nslabs[N - 1] = ns
+                    if not self.i8_fused[N - 1]:                # partial tensor of the two-mode group's GEMM
+                        keep = self.lshape[1:] if s == N - 1 else self.lshape[:N - 1]
+                        self.T2 = be.empty((int(np.prod(keep)), R))
                 elif be.planes_pass_supported(self.lshape, s, R):
                     self.i8 = be.planes_create(self.Xd, self.lshape, 5 if want == '5' else 6)
                     self.i8_general = True
