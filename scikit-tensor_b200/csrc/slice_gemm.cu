@@ -37,7 +37,7 @@ struct skt_planes {
     int64_t total;
     int S;
     unsigned char *planes;      // S planes of `total` bytes, each in X's memory order
-    double *scale;              // device: [0] = 2^e, [1] = 2^-e (NaN when max|X| is not finite)
+    double *scale;              // device: [0] * [1] = 2^e, [2] = e, [3] = 0 (NaN when max|X| is not finite)
     unsigned long long *amax;   // device: bits of max|X|
     int device;
     cudaStream_t stream;        // the planes come from the stream-ordered pool of this stream's device
@@ -73,12 +73,12 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
         : "memory");
 }
 // ---- slicing ----------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void slice4(const double x[4], double scale, int S, uint32_t w[MAXS]) {
+__device__ __forceinline__ void slice4(const double x[4], double s1, double s2, int S, uint32_t w[MAXS]) {
     uint32_t lo[4], hi[4];
     const double magic = 6755399441055744.0 + (S == 6 ? 551911719040.0 : 2155905152.0);     // 1.5 * 2^52 + 0x80..80
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const double t = fma(x[e], scale, magic);
+        const double t = fma(x[e] * s1, s2, magic);          // scale = s1 * s2, both powers of two (see split_pow2)
         lo[e] = (uint32_t)__double2loint(t) ^ 0x80808080u;
         hi[e] = (uint32_t)__double2hiint(t) ^ (S == 6 ? 0x80u : 0u);
     }
@@ -93,13 +93,19 @@ __device__ __forceinline__ void slice4(const double x[4], double scale, int S, u
     w[5] = __byte_perm(t4, t5, 0x7632);
 }
 
-// largest 2^e with rint(amax 2^e) representable by S balanced digits (<= 127 * 256^(S-1)); 1 for amax = 0
-__device__ double pow2_scale(double amax, int S) {
-    if (!(amax > 0.0)) return 1.0;
+// largest e with rint(amax 2^e) representable by S balanced digits (<= 127 * 256^(S-1)); 0 for amax = 0
+__device__ int pow2_exp(double amax, int S) {
+    if (!(amax > 0.0)) return 0;
     const int ex = ilogb(amax) + 1;                     // amax = f 2^ex, f in [0.5, 1)
-    double sc = ldexp(1.0, max(-1000, min(1000, 8 * S - 1 - ex)));
-    if (rint(amax * sc) > ldexp(127.0, 8 * S - 8)) sc *= 0.5;
-    return sc;
+    int e = 8 * S - 1 - ex;
+    if (rint(scalbn(amax, e)) > ldexp(127.0, 8 * S - 8)) e -= 1;
+    return e;
+}
+// 2^e as a product of two representable powers of two (e reaches +-1120 for tensors of magnitude 1e-300 / 1e300)
+__device__ void split_pow2(int e, double &a, double &b) {
+    const int e1 = max(-1000, min(1000, e));
+    a = ldexp(1.0, e1);
+    b = ldexp(1.0, e - e1);
 }
 
 __global__ void planes_absmax_kernel(const double *__restrict__ X, long long n, unsigned long long *out) {
@@ -118,23 +124,24 @@ __global__ void planes_absmax_kernel(const double *__restrict__ X, long long n, 
 __global__ void planes_scale_kernel(const unsigned long long *amax_bits, int S, double *scale) {
     const double amax = __longlong_as_double((long long)amax_bits[0]);
     if (!(amax <= DBL_MAX)) {
-        scale[0] = 0.0;
-        scale[1] = nan("");
+        scale[0] = scale[1] = scale[2] = 0.0;
+        scale[3] = nan("");
     } else {
-        const double sc = pow2_scale(amax, S);
-        scale[0] = sc;
-        scale[1] = 1.0 / sc;
+        const int e = pow2_exp(amax, S);
+        split_pow2(e, scale[0], scale[1]);
+        scale[2] = (double)e;
+        scale[3] = 0.0;
     }
 }
 
 __global__ void planes_slice_kernel(const double *__restrict__ X, long long total4, long long plane4, const double *scale_d, int S,
                                     uint32_t *__restrict__ P) {
-    const double scale = scale_d[0];
+    const double s1 = scale_d[0], s2 = scale_d[1];
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total4; q += (long long)gridDim.x * blockDim.x) {
         const double2 a = reinterpret_cast<const double2 *>(X)[2 * q], b = reinterpret_cast<const double2 *>(X)[2 * q + 1];
         const double x[4] = {a.x, a.y, b.x, b.y};
         uint32_t w[MAXS];
-        slice4(x, scale, S, w);
+        slice4(x, s1, s2, S, w);
 #pragma unroll
         for (int s = 0; s < MAXS; ++s)
             if (s < S) P[s * plane4 + q] = w[s];
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(128) factor_slice_kernel(const double *__restr
                                                            int smin, const double *__restrict__ xscale,
                                                            uint32_t *__restrict__ Bp, double *__restrict__ inv) {
     __shared__ double red[4];
-    __shared__ double sc_s;
+    __shared__ double sc_s[2];
     const int n = blockIdx.x;
     double m = 0.0;
     bool bad = false;
@@ -164,12 +171,15 @@ __global__ void __launch_bounds__(128) factor_slice_kernel(const double *__restr
     if (threadIdx.x == 0) {
         const double amax = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
         const bool finite = amax <= DBL_MAX;
-        const double sc = finite ? pow2_scale(amax, S) : 0.0;
-        sc_s = sc;
-        inv[n] = finite ? ldexp(1.0, 8 * smin) * xscale[1] / sc : nan("");
+        const int e = finite ? pow2_exp(amax, S) : 0;
+        sc_s[0] = sc_s[1] = 0.0;
+        if (finite) split_pow2(e, sc_s[0], sc_s[1]);
+        split_pow2(8 * smin - (int)xscale[2] - e, inv[n], inv[64 + n]);           // 256^smin / (scale_X * scale_n), in two factors
+        if (!finite) inv[n] = nan("");
+        inv[n] += xscale[3];                                                       // NaN when X is not finite
     }
     __syncthreads();
-    const double sc = sc_s;
+    const double sc = sc_s[0], sc2 = sc_s[1];
     for (int k4 = threadIdx.x; k4 < kpad / 4; k4 += 128) {
         double x[4];
 #pragma unroll
@@ -178,7 +188,7 @@ __global__ void __launch_bounds__(128) factor_slice_kernel(const double *__restr
             x[e] = (n < R && k < Kc) ? U[(size_t)k * R + n] : 0.0;
         }
         uint32_t w[MAXS];
-        slice4(x, sc, S, w);
+        slice4(x, sc, sc2, S, w);
         const bool pad = n >= R || sc == 0.0;
 #pragma unroll
         for (int s = 0; s < MAXS; ++s)
@@ -205,7 +215,7 @@ struct GemmParams {
     int R, NS;
     double *T;           // rows x R (nseg == 1) ...
     double *slabs;       // ... or nseg slabs of rows x R
-    const double *inv;   // per column
+    const double *inv;   // per column: inv[n] * inv[64 + n] = 256^smin / (scale_X scale_n), two representable powers of two
     // fused second stage (EMODE 2, 3-way tensors): weights W[J x R] of the middle mode, slabs of the finished MTTKRP
     const double *W;
     double *aux;
@@ -500,20 +510,20 @@ slice_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const double *w = p.W + (size_t)u * p.R;
 #pragma unroll
                     for (int n = 0; n < 32; ++n)
-                        if (n < p.R) wacc[n] = fma(r[n] * p.inv[n], __ldg(w + n), wacc[n]);
+                        if (n < p.R) wacc[n] = fma(r[n] * p.inv[n] * p.inv[64 + n], __ldg(w + n), wacc[n]);
                 } else if (row < p.rows) {
                     if (p.R == NBW) {
 #pragma unroll
                         for (int n = 0; n < 32; n += 2) {
                             double2 o;
-                            o.x = r[n] * p.inv[h * 32 + n];
-                            o.y = r[n + 1] * p.inv[h * 32 + n + 1];
+                            o.x = r[n] * p.inv[h * 32 + n] * p.inv[64 + h * 32 + n];
+                            o.y = r[n + 1] * p.inv[h * 32 + n + 1] * p.inv[64 + h * 32 + n + 1];
                             *reinterpret_cast<double2 *>(out + h * 32 + n) = o;
                         }
                     } else {
 #pragma unroll
                         for (int n = 0; n < 32; ++n)
-                            if (h * 32 + n < p.R) out[h * 32 + n] = r[n] * p.inv[h * 32 + n];
+                            if (h * 32 + n < p.R) out[h * 32 + n] = r[n] * p.inv[h * 32 + n] * p.inv[64 + h * 32 + n];
                     }
                 }
             }
@@ -579,9 +589,12 @@ __global__ void kr_scale_kernel(const unsigned long long *colmax, int S, int smi
     const int n = threadIdx.x;
     const double amax = __longlong_as_double((long long)colmax[n]);
     const bool finite = amax <= DBL_MAX;
-    const double s = finite ? pow2_scale(amax, S) : 0.0;
-    sc[n] = s;
-    inv[n] = finite ? ldexp(1.0, 8 * smin) * xscale[1] / s : nan("");
+    const int e = finite ? pow2_exp(amax, S) : 0;
+    sc[n] = sc[64 + n] = 0.0;
+    if (finite) split_pow2(e, sc[n], sc[64 + n]);
+    split_pow2(8 * smin - (int)xscale[2] - e, inv[n], inv[64 + n]);
+    if (!finite) inv[n] = nan("");
+    inv[n] += xscale[3];
 }
 
 // planes Bp[s][n][kpad] of KR^T; thread = (column n, four consecutive k)
@@ -591,7 +604,7 @@ __global__ void __launch_bounds__(256) kr_slice_kernel(const KrDesc d, long long
     if (q >= kpad4 * nb) return;
     const int n = (int)(q / kpad4);
     const long long k4 = q % kpad4;
-    const double scale = sc[n];
+    const double scale = sc[n], scale2 = sc[64 + n];
     double x[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -599,7 +612,7 @@ __global__ void __launch_bounds__(256) kr_slice_kernel(const KrDesc d, long long
         x[e] = (n < d.R && k < K) ? kr_value(d, k, n) : 0.0;
     }
     uint32_t w[MAXS];
-    slice4(x, scale, S, w);
+    slice4(x, scale, scale2, S, w);
     const bool pad = n >= d.R || scale == 0.0;
 #pragma unroll
     for (int s = 0; s < MAXS; ++s)
@@ -672,7 +685,7 @@ int plan_ttm(const skt_planes *P, int mode, int R, TtmPlan &pl) {
     return SKT_OK;
 }
 
-size_t ttm_ws(const TtmPlan &pl, int S) { return align_up((size_t)S * NB * pl.kpad, 256) + align_up(NB * sizeof(double), 256); }
+size_t ttm_ws(const TtmPlan &pl, int S) { return align_up((size_t)S * NB * pl.kpad, 256) + align_up(128 * sizeof(double), 256); }
 
 
 struct PassPlan {
@@ -733,9 +746,9 @@ PassWs pass_ws(const PassPlan &pl, int S, int R) {
     w.colmax = off;
     off += align_up(64 * sizeof(unsigned long long), 256);
     w.sc = off;
-    off += align_up(64 * sizeof(double), 256);
+    off += align_up(128 * sizeof(double), 256);
     w.inv = off;
-    off += align_up(64 * sizeof(double), 256);
+    off += align_up(128 * sizeof(double), 256);
     w.slabs = off;
     if (pl.nseg > 1) off += align_up((size_t)pl.nseg * pl.rows * R * sizeof(double), 256);
     w.total = off;

@@ -319,3 +319,26 @@ def test_cp_als_sliced_fused_matches_unfused_and_fp64(monkeypatch, shape, R):
     assert abs(fit1 - fit0) < 1e-9 and abs(fit2 - fit0) < 1e-9
     for a, b, c in zip(P1.U, P0.U, P2.U):
         assert relerr(a, b) < 1e-8 and relerr(c, b) < 1e-8
+
+
+@pytest.mark.parametrize('top', [1.0, 2.0 ** -30, 0.9921875, 0.9921875 * (1 + 2.0 ** -40), 0.9921875 * (1 - 2.0 ** -40), 1 - 2.0 ** -50,
+                                 3.0, 1e-300, 1e300])
+@pytest.mark.parametrize('S', [6, 5])
+def test_planes_scale_boundaries(K, dev, top, S):
+    """The largest magnitude decides the power-of-two scale; values at the edge of the balanced-digit range (127.x * 256^(S-1))
+    must neither overflow the top digit nor lose more than the stated bound."""
+    rng = np.random.RandomState(3)
+    shape = (16, 16, 32)
+    X = (rng.rand(*shape) - 0.5) * top
+    X[0, 0, 0], X[1, 2, 3], X[5, 5, 5] = top, -top, top * (1 - 2.0 ** -20)
+    U = rng.rand(32, 4) - 0.5
+    U[3, 1], U[4, 2] = -1.0, 0.9921875
+    P = K.PlanesHandle(dev.to_device(X), shape, S)
+    try:
+        T = dev.to_host(P.ttm(2, dev.to_device(U), 4))
+        ref = X.reshape(-1, 32).dot(U)
+        bound = 2.0 ** -(8 * S - 1) * (np.abs(X).max() * np.abs(U).sum(axis=0).max() + np.abs(U).max() * np.abs(X).sum(axis=2).max())
+        assert np.isfinite(T).all()
+        assert np.abs(T - ref).max() <= 4 * bound + 4e-16 * np.abs(ref).max()
+    finally:
+        P.close()
