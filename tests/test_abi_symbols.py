@@ -66,3 +66,35 @@ def test_argument_errors_without_a_gpu():
         _lib.check(rc)
     assert lib.skt_gram(None, 10, 4, None, None, 0, None) == -1
     assert lib.skt_hadamard_pinv(None, 3, 200, 0, None, None, None) == -1
+
+
+def test_sliced_contraction_eligibility_is_host_logic():
+    """What the opt-in INT8 path accepts is decided on the host (skt_planes_supported / skt_planes_pass_supported): the
+    engine asks before it builds byte planes, and silently keeps the FP64 passes otherwise."""
+    from sktensor import _lib
+    lib = _lib.load()
+
+    def ttm_ok(shape, mode, rank):
+        return bool(lib.skt_planes_supported(_lib.shape_array(shape), len(shape), mode, rank))
+
+    def pass_ok(shape, split, rank):
+        return bool(lib.skt_planes_pass_supported(_lib.shape_array(shape), len(shape), split, rank))
+
+    assert ttm_ok((512, 512, 512), 0, 32) and ttm_ok((512, 512, 512), 2, 32)      # BASELINE configs[1]
+    assert not ttm_ok((512, 512, 512), 1, 32)                                     # only the outer modes contract
+    assert not ttm_ok((512, 512, 512), 2, 33)                                     # one 32-column block per slice
+    assert not ttm_ok((512, 512, 528), 2, 32)                                     # factor planes no longer resident
+    assert not ttm_ok((512, 512, 500), 2, 32)                                     # plane rows must be 16-byte aligned
+    assert not ttm_ok((30, 5, 7), 0, 4)
+    assert pass_ok((160, 160, 160, 160), 2, 64)                                   # BASELINE configs[4]
+    assert pass_ok((160, 20, 160, 160), 2, 64)                                    # ... one rank's slab of it on 8 GPUs
+    assert pass_ok((512, 512, 528), 2, 32) and pass_ok((64, 32, 32), 1, 50)
+    assert not pass_ok((160, 160, 160, 160), 2, 65)
+    assert not pass_ok((10, 11, 8), 2, 3)                                         # trailing modes not a multiple of 16 bytes
+    assert not pass_ok((16, 16), 0, 4) and not pass_ok((16, 16), 2, 4)            # the split lies strictly inside
+    # without a handle the sizing queries answer 0 instead of touching the device
+    assert lib.skt_planes_ttm_workspace(None, 0, 8) == 0
+    assert lib.skt_planes_pass_workspace(None, 1, 0, 8) == 0
+    assert lib.skt_planes_fused_slabs(None, 0, 8, None) == 0
+    assert lib.skt_planes_device_bytes(None) == 0 and lib.skt_planes_nslices(None) == 0
+    assert lib.skt_planes_destroy(None) == 0
