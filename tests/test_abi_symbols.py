@@ -98,3 +98,18 @@ def test_sliced_contraction_eligibility_is_host_logic():
     assert lib.skt_planes_fused_slabs(None, 0, 8, None) == 0
     assert lib.skt_planes_device_bytes(None) == 0 and lib.skt_planes_nslices(None) == 0
     assert lib.skt_planes_destroy(None) == 0
+
+
+def test_shipped_cubins_are_sm_100a_and_use_the_blackwell_units():
+    """The library is built for sm_100a only and its SASS contains what DESIGN.md says the kernels use: TMA tensor loads,
+    FP64 tensor-core MMA, and -- in the opt-in sliced contraction -- tcgen05 MMA / tensor-memory loads."""
+    import shutil
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not on PATH')
+    from sktensor import _lib
+    path = _lib.library_path() if hasattr(_lib, 'library_path') else os.path.join(ROOT, 'scikit-tensor_b200', 'lib', 'libsktensor_b200.so')
+    archs = subprocess.run(['cuobjdump', '-lelf', path], capture_output=True, text=True, timeout=300).stdout
+    assert 'sm_100a' in archs and 'sm_90' not in archs and 'sm_80' not in archs
+    sass = subprocess.run(['cuobjdump', '-sass', path], capture_output=True, text=True, timeout=600).stdout
+    for mnemonic in ('UTMALDG', 'DMMA.8x8x4', 'UTCIMMA', 'LDTM', 'UTCBAR', 'UCGABAR_ARV', 'LDGSTS'):
+        assert mnemonic in sass, mnemonic
