@@ -342,3 +342,18 @@ def test_planes_scale_boundaries(K, dev, top, S):
         assert np.abs(T - ref).max() <= 4 * bound + 4e-16 * np.abs(ref).max()
     finally:
         P.close()
+
+
+def test_cp_als_sliced_with_five_slices(monkeypatch):
+    """SKT_DENSE_I8=5 (40-bit operands): still far inside the reference tolerances (MTTKRP 1e-10, fit 1e-6)."""
+    from oracle import sktensor_oracle as orc
+    rng = np.random.RandomState(9)
+    shape, R = (64, 128, 128), 16
+    X = rng.rand(*shape)
+    U0 = [rng.rand(d, R) for d in shape]
+    monkeypatch.setenv('SKT_DENSE_I8', '5')
+    P1, fit1, itr1, _ = _cp(X, R, U0, max_iter=10, conv=0)
+    Uo, lamo, fito, itro = orc.cp_als(X, R, init=[u.copy() for u in U0], max_iter=10, conv=0)[:4]
+    assert itr1 == itro and abs(fit1 - fito) < 1e-8
+    for a, b in zip(P1.U, Uo):
+        assert relerr(a, b) < 1e-6
