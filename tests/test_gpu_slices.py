@@ -357,3 +357,49 @@ def test_cp_als_sliced_with_five_slices(monkeypatch):
     assert itr1 == itro and abs(fit1 - fito) < 1e-8
     for a, b in zip(P1.U, Uo):
         assert relerr(a, b) < 1e-6
+
+
+def test_planes_fuzz_random_shapes_splits_and_ranks(K, dev):
+    """Seeded sweep over the corner structure of the general pass and the resident kernel: ragged row tiles, contraction tails
+    that are not a multiple of 32 or 128 bytes, 1 .. 64 columns (partial 32- and 64-column blocks), split-K with few rows,
+    2- to 5-way tensors, both groups, both slice counts."""
+    rng = np.random.RandomState(20261020)
+    tail_dims = [16, 32, 48, 80, 144, 160, 272, 400, 528]
+    done = 0
+    for trial in range(48):
+        ndim = int(rng.randint(2, 6))
+        split = int(rng.randint(1, ndim))
+        shape = [int(rng.choice([1, 2, 3, 5, 7, 9, 12, 17, 33])) for _ in range(ndim)]
+        shape[-1] = int(rng.choice(tail_dims))                         # Q = prod(shape[split:]) becomes a multiple of 16
+        if rng.rand() < 0.4:
+            shape[0] = int(rng.choice([130, 257, 600, 1500]))          # many row tiles on one side ...
+        if rng.rand() < 0.3 and split < ndim - 1:
+            shape[split] = int(rng.choice([64, 129, 300]))             # ... or a long contraction for group 0
+        if np.prod(shape) > 3e6:
+            shape[0] = max(1, int(3e6 // np.prod(shape[1:])))
+        shape = tuple(shape)
+        R = int(rng.choice([1, 2, 7, 16, 31, 32, 33, 40, 63, 64]))
+        S = int(rng.choice([5, 6]))
+        if not K.PlanesHandle.pass_supported(shape, split, R):
+            continue
+        X = rng.randn(*shape) if rng.rand() < 0.5 else rng.rand(*shape) - 0.3
+        U = [rng.rand(d, R) - 0.4 for d in shape]
+        Ud = [dev.to_device(u) for u in U]
+        P = K.PlanesHandle(dev.to_device(X), shape, S)
+        try:
+            X2 = X.reshape(int(np.prod(shape[:split])), -1)
+            tol = 1e-12 if S == 6 else 1e-10
+            TA = dev.to_host(P.tree_pass(split, 0, Ud, R))
+            TB = dev.to_host(P.tree_pass(split, 1, Ud, R))
+            refA, refB = X2.dot(_kr(U[split:])), X2.T.dot(_kr(U[:split]))
+            assert relerr(TA, refA) < tol, (trial, shape, split, R, S, 'group 0')
+            assert relerr(TB, refB) < tol, (trial, shape, split, R, S, 'group 1')
+            for mode in (0, ndim - 1):
+                if K.PlanesHandle.supported(shape, mode, R):
+                    T = dev.to_host(P.ttm(mode, Ud[mode], R))
+                    ref = X.reshape(shape[0], -1).T.dot(U[0]) if mode == 0 else X.reshape(-1, shape[-1]).dot(U[-1])
+                    assert relerr(T, ref) < tol, (trial, shape, mode, R, S, 'ttm')
+            done += 1
+        finally:
+            P.close()
+    assert done >= 30
