@@ -7,7 +7,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'scikit-tensor_b200'))
 sys.path.insert(0, ROOT)
-from sktensor import _device as dev, _kernels as K, _parallel, dtensor   # noqa: E402
+from sktensor import _device as dev, _parallel, dtensor   # noqa: E402
 import bench                                                              # noqa: E402
 
 t = dev.torch()
